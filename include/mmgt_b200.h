@@ -1,0 +1,191 @@
+/*
+ * mmgt_b200.h -- C ABI of the B200-native kernels behind MMGT's stage-2 denoising hot path.
+ *
+ * Drop-in boundary: the reference is 100 % Python/PyTorch and has no FFI of
+ * its own; the operators below are exactly the implicit library kernels its hot path dispatches
+ * (SURVEY.md section 2.3), one entry point per fused operator.  Each declaration cites the reference
+ * call site it replaces (paths relative to the reference checkout).  The Python host in
+ * mmgt_b200/ binds them with ctypes (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *   - every entry point returns int: 0 = OK, <0 = invalid argument (MMGT_E_*), >0 = cudaError_t.
+ *   - nothing here allocates device memory, synchronises the stream, or throws.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.
+ *   - activations are channels-last: a frame batch is (N, T, C) row-major with N = batch*frames,
+ *     T = H*W tokens, C channels; "rows" = N*T.
+ *   - dtype: MMGT_F32 or MMGT_BF16 selects the storage type of activations / GEMM weights.
+ *     bias / norm affine / scale vectors are always float32.  Accumulation is always float32.
+ *   - stream is a cudaStream_t passed as void*.
+ */
+#ifndef MMGT_B200_H
+#define MMGT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMGT_F32 0
+#define MMGT_BF16 1
+
+#define MMGT_E_INVALID (-1)      /* bad shape / null pointer / unsupported combination */
+#define MMGT_E_ALIGN (-2)        /* pointer or leading dimension not aligned as required */
+#define MMGT_E_UNSUPPORTED (-3)  /* valid request but no kernel for it (never silently emulated) */
+#define MMGT_E_NODRIVER (-4)     /* cuTensorMapEncodeTiled could not be resolved */
+
+#if defined(__GNUC__)
+#define MMGT_API __attribute__((visibility("default")))
+#else
+#define MMGT_API
+#endif
+
+typedef struct mmgt_ctx mmgt_ctx;
+
+/* Library / context ------------------------------------------------------------------------- */
+MMGT_API int mmgt_abi_version(void);
+/* Creates the per-device context (SM count, opt-in shared memory, driver entry points). */
+MMGT_API int mmgt_ctx_create(mmgt_ctx** out, int device);
+MMGT_API int mmgt_ctx_destroy(mmgt_ctx* ctx);
+/* Last error message of the calling thread (static storage, never NULL). */
+MMGT_API const char* mmgt_last_error(void);
+/* flag 0: enable (1) / disable (0) the tcgen05 tensor-core kernels for bf16 (default 1).
+ * flag 1: number of kernels launched through this context since creation (read with value<0). */
+MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);
+
+/* Layout ------------------------------------------------------------------------------------- */
+/* (B,C,F,H,W) float32|bf16 -> (B*F, H*W, C) in `dtype`, optionally adding a second NCFHW tensor.
+ * Replaces the rearranges at resnet.py:13, transformer_3d.py:158 and the pose add unet_3d.py:517-519. */
+MMGT_API int mmgt_ncfhw_to_tokens(mmgt_ctx*, const void* src, const void* add_or_null, void* dst, int B, int C, int F,
+                         int H, int W, int src_dtype, int dst_dtype, void* stream);
+/* (B*F, H*W, C) -> (B,C,F,H,W); inverse of the above (resnet.py:15, transformer_3d.py:264). */
+MMGT_API int mmgt_tokens_to_ncfhw(mmgt_ctx*, const void* src, void* dst, int B, int C, int F, int H, int W, int src_dtype,
+                         int dst_dtype, void* stream);
+
+/* Normalisation ------------------------------------------------------------------------------ */
+/* GroupNorm over (T, C/groups) per frame on a channels-last tensor, optional fused SiLU.  The input may
+ * be the virtual channel-concat [x1 (C1) || x2 (C2)] (x2 may be NULL, C2 = 0); the output is the
+ * concatenated normalised tensor (N,T,C1+C2).  stats_ws: >= N*groups*2 doubles of scratch.
+ * Replaces InflatedGroupNorm/nn.GroupNorm + F.silu (resnet.py:20-28,220-221,231-237;
+ * transformer_3d.py:174; motion_module.py:156; unet_3d.py:618-619) and torch.cat
+ * (unet_3d_blocks.py:894,1057). */
+MMGT_API int mmgt_groupnorm(mmgt_ctx*, const void* x1, const void* x2_or_null, void* y, const float* gamma,
+                   const float* beta, double* stats_ws, int N, int T, int C1, int C2, int groups, float eps,
+                   int silu, int dtype, void* stream);
+/* LayerNorm over C per row (eps as given); optional positional-encoding add: y += pe[(row/T) % F, :]
+ * (pe is (max_len, C) float32, NULL = none).  Replaces nn.LayerNorm (attention.py:331-362,576-644;
+ * motion_module.py:228-244) and PositionalEncoding.forward (motion_module.py:275-277,365-366). */
+MMGT_API int mmgt_layernorm(mmgt_ctx*, const void* x, void* y, const float* gamma, const float* beta,
+                   const float* pe_or_null, int64_t rows, int C, int T, int F, float eps, int dtype,
+                   void* stream);
+
+/* GEMM / convolution --------------------------------------------------------------------------- */
+typedef struct {
+  const void* A;        /* (M,K) row-major, leading dim lda (elements) */
+  const void* W;        /* (N,K) row-major (nn.Linear / 1x1-conv weight), leading dim ldw */
+  void* D;              /* (M,N) or (M,N/2) for GEGLU, leading dim ldd */
+  const float* bias;    /* (N) or NULL */
+  const float* rowscale;/* (M) or NULL: per-row multiplier applied after bias (MM-HAA mask gate) */
+  const float* rowbias; /* (ceil(M/rows_per_group), N) or NULL: broadcast add (time embedding, CLIP) */
+  const void* residual; /* (M,N_out) or NULL, leading dim ldr; may alias D */
+  int64_t lda, ldw, ldd, ldr;
+  int M, N, K;
+  int rows_per_group;
+  float alpha;          /* D = alpha*rowscale*(A W^T + bias) + rowbias + residual */
+  int geglu_block;      /* 0 = off; else W rows are interleaved [value(gb) | gate(gb)]* and
+                           D[m, j] = value * gelu_erf(gate), N_out = N/2 (diffusers GEGLU) */
+  int dtype;            /* storage type of A, W, D, residual */
+  int out_f32;          /* 1: D is float32 regardless of dtype (small-M vectors) */
+} mmgt_gemm_params;
+/* Replaces nn.Linear / 1x1 nn.Conv2d + bias + residual adds + GEGLU (diffusers Attention.to_q/k/v/out,
+ * FeedForward; transformer_3d.py:176,253; resnet.py:226,243; attention.py:730-767;
+ * motion_module.py:161,172). */
+MMGT_API int mmgt_gemm(mmgt_ctx*, const mmgt_gemm_params*, void* stream);
+/* N-tile width the tensor-core kernel uses for a weight with N rows (0 = none divides N).  A GEGLU weight
+ * must be row-interleaved with geglu_block = mmgt_gemm_tc_block_n(N) / 2 to take the tensor-core path. */
+MMGT_API int mmgt_gemm_tc_block_n(int N);
+
+typedef struct {
+  const void* x;        /* (N, H, W, Cin) channels-last */
+  const void* w;        /* (Cout, 3, 3, Cin) "KRSC" repack of the (Cout,Cin,3,3) weight */
+  void* y;              /* (N, Ho, Wo, Cout) */
+  const float* bias;    /* (Cout) or NULL */
+  const float* rowbias; /* (N/frames_per_group, Cout) or NULL: time-embedding add (resnet.py:226-229) */
+  const void* residual; /* (N, Ho, Wo, Cout) or NULL; may alias y */
+  int N, H, W, Cin, Cout;
+  int stride;           /* 1 or 2 (Downsample3D, resnet.py:106-108), padding is always 1 */
+  int upsample2x;       /* 1: x is nearest-upsampled x2 on the fly before the conv (Upsample3D, resnet.py:70-88) */
+  int frames_per_group; /* frames sharing one rowbias row (= F) */
+  int dtype;
+} mmgt_conv3x3_params;
+/* Replaces InflatedConv3d k=3 (resnet.py:9-17) incl. the fused epilogue of ResnetBlock3D.
+ * workspace: scratch of at least mmgt_conv3x3_workspace_bytes() bytes (may be NULL when that is 0;
+ * only the stride-2 / upsampling tensor-core paths stage an im2col matrix). */
+MMGT_API int64_t mmgt_conv3x3_workspace_bytes(mmgt_ctx*, const mmgt_conv3x3_params*);
+MMGT_API int mmgt_conv3x3(mmgt_ctx*, const mmgt_conv3x3_params*, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Attention ------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* q;  /* (N, Lq, heads*d), row stride ldq */
+  const void* k;  /* (N, Lk, heads*d), row stride ldk: per-frame keys   */
+  const void* v;  /* (N, Lk, heads*d), row stride ldv                  */
+  const void* k2; /* (B2, Lk2, heads*d) row stride ldk2: shared second key segment (reference bank) or NULL */
+  const void* v2;
+  const int32_t* seg2_index; /* (N) device: row of k2/v2 used by frame n, or -1 = first segment only
+                                (the CFG uncond half, mutual_self_attention.py:168-188).  NULL with k2 => 0 */
+  void* out;      /* (N, Lq, heads*d), row stride ldo */
+  int64_t ldq, ldk, ldv, ldk2, ldv2, ldo;
+  int64_t kv_batch_stride; /* elements between consecutive frames of k/v (0 = Lk*ldk) */
+  int N, Lq, Lk, Lk2, heads, d;
+  float scale;    /* d^-0.5 */
+  int dtype;
+} mmgt_attention_params;
+/* softmax(q k^T * scale) v over [k ; k2].  Replaces diffusers AttnProcessor2_0 /
+ * F.scaled_dot_product_attention for spatial self(+reference) attention and the audio cross-attention
+ * (mutual_self_attention.py:157-188; attention.py:694,720-750). */
+MMGT_API int mmgt_attention(mmgt_ctx*, const mmgt_attention_params*, void* stream);
+
+/* Temporal self-attention of the motion module: sequences run over the F frames of each (batch, token).
+ * qkv: (B*F*T, 3*C) fused projections [q|k|v] of rows ordered (b, f, t); out: (B*F*T, C).
+ * Replaces VersatileAttention.forward incl. both rearranges (motion_module.py:351-388). */
+MMGT_API int mmgt_temporal_attention(mmgt_ctx*, const void* qkv, void* out, int B, int F, int T, int heads, int d,
+                            float scale, int dtype, void* stream);
+
+/* Small element-wise pieces -------------------------------------------------------------------- */
+/* Timesteps(dim, flip_sin_to_cos, freq_shift) (diffusers embeddings; unet_3d.py:496): t (B) float32 device. */
+MMGT_API int mmgt_timestep_embedding(mmgt_ctx*, const float* t, float* out, int B, int dim, int flip_sin_to_cos,
+                            float freq_shift, void* stream);
+/* y = silu(x), float32 (resnet.py:226 nonlinearity on temb). */
+MMGT_API int mmgt_silu_f32(mmgt_ctx*, const float* x, float* y, int64_t n, void* stream);
+/* nearest x2 upsample of (N,H,W,C) -> (N,2H,2W,C) (resnet.py:71-73). */
+MMGT_API int mmgt_upsample_nearest2x(mmgt_ctx*, const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream);
+/* im2col for 3x3 / pad 1 with stride and optional x2 nearest upsample: (N,H,W,C) -> (N*Ho*Wo, 9*C). */
+MMGT_API int mmgt_im2col3x3(mmgt_ctx*, const void* x, void* col, int N, int H, int W, int C, int stride, int upsample2x,
+                   int dtype, void* stream);
+
+/* dst[i, :] = src[idx[i], :]; rows of row_bytes (multiple of 16) bytes.  Assembles a context window from
+ * whole-video tensors (latents[:, :, c], pose_fea[:, :, c], masks.view(2, L, -1)[:, c];
+ * pipeline_pose2vid_long.py:556-586). */
+MMGT_API int mmgt_gather_rows(mmgt_ctx*, const void* src, const int32_t* idx, void* dst, int n_out, int64_t row_bytes,
+                              void* stream);
+
+/* Denoise-loop pieces (pipeline_pose2vid_long.py:622-635 + diffusers DDIMScheduler.step) ---------- */
+/* noise_acc[(b), c, frames[j], :, :] += pred[(b), c, j, :, :]; noise_acc float32 (2|1,C,L,H,W);
+ * pred (Bp,C,Fw,H,W) in pred_dtype, added into batch rows [b0, b0+Bp). */
+MMGT_API int mmgt_window_accumulate(mmgt_ctx*, float* noise_acc, const void* pred, const int32_t* frames, int Bp, int b0,
+                           int C, int L, int Fw, int HW, int pred_dtype, void* stream);
+/* latents = cx*latents + cv*(u + g*(c-u)), u/c = noise_acc[0|1]/count[frame]; cfg=0 => v = noise_acc[0]/count. */
+MMGT_API int mmgt_cfg_ddim_step(mmgt_ctx*, float* latents, const float* noise_acc, const float* inv_count, int C, int L,
+                       int HW, int cfg, float guidance, float cx, float cv, void* stream);
+
+/* Motion-mask pyramid (src/dataset/image_processor.py:75-102,311-333) ------------------------------ */
+/* src: (L, Hs, Ws) uint8.  Bit-exact Pillow 8-bit bilinear resize (horizontal then vertical, 22-bit fixed
+ * point) to (L, S, S), then out = offset + u8/255 in float32 (offset 1.0 builds "1 + lips",
+ * scripts/audio2vid.py:475).  tmp: >= L*Hs*S bytes scratch.  out_u8 may be NULL. */
+MMGT_API int mmgt_mask_resize(mmgt_ctx*, const uint8_t* src, uint8_t* tmp, uint8_t* out_u8, float* out_f32, int L, int Hs,
+                     int Ws, int S, float offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMGT_B200_H */

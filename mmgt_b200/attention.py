@@ -1,0 +1,265 @@
+"""Host mirror of src/models/attention.py + the diffusers primitives it builds on.
+
+``Attention`` / ``FeedForward`` here are parameter containers with the diffusers-0.24 state-dict layout
+(``to_q/to_k/to_v.weight``, ``to_out.0.{weight,bias}``, ``net.0.proj``, ``net.2``); the math runs in the
+CUDA kernels through ``run`` helpers on the block classes.
+"""
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .kernels import Engine
+from .packing import Pack, conv1x1, f32, geglu_interleave, run
+
+
+class Attention(nn.Module):
+    """diffusers Attention(query_dim, cross_attention_dim, heads, dim_head, bias=False, out_bias=True)."""
+
+    def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64, dropout=0.0, bias=False,
+                 upcast_attention=False, **unused):
+        super().__init__()
+        if bias:
+            raise NotImplementedError("attention_bias=True is not used by the reference config")
+        inner = heads * dim_head
+        self.heads, self.dim_head, self.inner_dim, self.query_dim = heads, dim_head, inner, query_dim
+        self.kv_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(self.kv_dim, inner, bias=False)
+        self.to_v = nn.Linear(self.kv_dim, inner, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim, bias=True), nn.Dropout(dropout)])
+        self._pack = Pack()
+
+    def packed(self, eng: Engine):
+        """-> dict(qkv (3*inner, C) if self-attention, q, kv (2*inner, kv_dim), o, bo)."""
+        def build():
+            d = {}
+            q, k, v = self.to_q.weight, self.to_k.weight, self.to_v.weight
+            if self.kv_dim == self.query_dim:
+                d["qkv"] = run(torch.cat([q, k, v], dim=0), eng)
+                d["q"] = d["qkv"][: self.inner_dim]
+                d["kv"] = d["qkv"][self.inner_dim:]
+            else:
+                d["q"] = run(q, eng)
+                d["kv"] = run(torch.cat([k, v], dim=0), eng)
+            d["o"] = run(self.to_out[0].weight, eng)
+            d["bo"] = f32(self.to_out[0].bias, eng)
+            return d
+        return self._pack.get(eng, [self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_out[0].weight,
+                                    self.to_out[0].bias], build)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+
+class FeedForward(nn.Module):
+    """diffusers FeedForward(dim, activation_fn='geglu'): net = [GEGLU(dim, 4*dim), Dropout, Linear(4*dim, dim)]."""
+
+    def __init__(self, dim, dropout=0.0, activation_fn="geglu", mult=4):
+        super().__init__()
+        if activation_fn != "geglu":
+            raise NotImplementedError(activation_fn)
+        self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(dropout), nn.Linear(dim * mult, dim)])
+        self._pack = Pack()
+
+    def run(self, eng: Engine, x_norm, residual):
+        """x_norm: (rows, dim) already layer-normed -> ff(x_norm) + residual."""
+        p1, p2 = self.net[0].proj, self.net[2]
+
+        def build():
+            gb = eng.geglu_block(p1.weight.shape[0])
+            w1, b1 = geglu_interleave(p1.weight.detach(), p1.bias.detach(), gb)
+            return dict(gb=gb, w1=run(w1, eng), b1=f32(b1, eng), w2=run(p2.weight, eng), b2=f32(p2.bias, eng))
+        pk = self._pack.get(eng, [p1.weight, p1.bias, p2.weight, p2.bias], build)
+        h = eng.gemm(x_norm, pk["w1"], bias=pk["b1"], geglu_block=pk["gb"])
+        return eng.gemm(h, pk["w2"], bias=pk["b2"], residual=residual)
+
+
+class _LN(nn.LayerNorm):
+    def __init__(self, dim):
+        super().__init__(dim)
+        self._pack = Pack()
+
+    def run(self, eng: Engine, x, pe=None, T=0, F=0):
+        g, b = self._pack.get(eng, [self.weight, self.bias], lambda: (f32(self.weight, eng), f32(self.bias, eng)))
+        return eng.layernorm(x, g, b, self.eps, pe=pe, T=T, F=F)
+
+
+class TemporalBasicTransformerBlock(nn.Module):
+    """Spatial block of the denoising UNet: self-attention with ReferenceNet feature injection, CLIP
+    cross-attention, GEGLU feed-forward.  The computation is the *read-mode hacked forward* that
+    ReferenceAttentionControl installs (mutual_self_attention.py:93-230), not attention.py:382-481:
+
+      x1 = attn1(LN1 x, kv = [LN1 x ; bank])  (+x)      frames flagged "uncond" use kv = LN1 x only -- the net
+                                                         effect of the CFG re-do at :168-188, computed once
+      x2 = attn2(LN2 x1, clip) + x1                      one CLIP token => softmax == 1 => to_out(to_v(clip))
+      x3 = ff(LN3 x2) + x2
+
+    ``bank`` is the list ReferenceAttentionControl.update() fills ((Bb, T, C) reference features)."""
+
+    def __init__(self, dim, num_attention_heads, attention_head_dim, dropout=0.0, cross_attention_dim=None,
+                 activation_fn="geglu", num_embeds_ada_norm=None, attention_bias=False, only_cross_attention=False,
+                 upcast_attention=False, unet_use_cross_frame_attention=None, unet_use_temporal_attention=None,
+                 name=None):
+        super().__init__()
+        if num_embeds_ada_norm is not None or only_cross_attention or unet_use_cross_frame_attention \
+                or unet_use_temporal_attention:
+            raise NotImplementedError("option not used by config/prompts/animation.yaml")
+        self.name = name
+        self.attn1 = Attention(dim, heads=num_attention_heads, dim_head=attention_head_dim, bias=attention_bias)
+        self.norm1 = _LN(dim)
+        self.attn2 = Attention(dim, cross_attention_dim=cross_attention_dim, heads=num_attention_heads,
+                               dim_head=attention_head_dim, bias=attention_bias) if cross_attention_dim else None
+        self.norm2 = _LN(dim) if cross_attention_dim else None
+        self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
+        self.norm3 = _LN(dim)
+        self.bank: List[torch.Tensor] = []
+        self._bank_kv = None       # (key, k2, v2) projected reference keys / values
+        self._clip_pack = Pack()
+
+    # -- reference K/V: the bank is constant over all steps and windows => project once
+    def bank_kv(self, eng: Engine):
+        if not self.bank:
+            return None
+        bank = self.bank[0]
+        pk = self.attn1.packed(eng)
+        key = (bank.data_ptr(), bank._version, tuple(bank.shape), pk["kv"].data_ptr(), str(eng.device), eng.dtype)
+        if self._bank_kv is None or self._bank_kv[0] != key:
+            Bb, T, C = bank.shape
+            b = bank.to(device=eng.device, dtype=eng.dtype).contiguous().view(Bb * T, C)
+            kv = eng.gemm(b, pk["kv"]).view(Bb, T, 2 * C)
+            self._bank_kv = (key, kv[:, :, :C], kv[:, :, C:])
+        return self._bank_kv[1], self._bank_kv[2]
+
+    def clip_vector(self, eng: Engine, clip_b):
+        """attn2 with a single key/value token: (B, 1, 768) -> (B, C) float32 = to_out(to_v(clip))."""
+        a = self.attn2
+        wv, wo, bo = self._clip_pack.get(
+            eng, [a.to_v.weight, a.to_out[0].weight, a.to_out[0].bias],
+            lambda: (f32(a.to_v.weight, eng), f32(a.to_out[0].weight, eng), f32(a.to_out[0].bias, eng)))
+        v = eng.gemm(clip_b.reshape(clip_b.shape[0], -1).float().contiguous(), wv, dtype=torch.float32)
+        return eng.gemm(v, wo, bias=bo, dtype=torch.float32)
+
+    def run(self, eng: Engine, tok, clip_b, frames: int, seg2_index):
+        """tok: (N, T, C); clip_b: (B, L_clip, 768); seg2_index: (N,) int32 bank row per frame or -1."""
+        N, T, C = tok.shape
+        rows = N * T
+        heads = self.attn1.heads
+        x = tok.view(rows, C)
+        pk = self.attn1.packed(eng)
+        n1 = self.norm1.run(eng, x)
+        qkv = eng.gemm(n1, pk["qkv"]).view(N, T, 3 * C)
+        bkv = self.bank_kv(eng)
+        k2, v2 = bkv if bkv is not None else (None, None)
+        a = eng.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, k2=k2, v2=v2,
+                          seg2_index=seg2_index if bkv is not None else None)
+        if self.attn2 is not None and clip_b.shape[1] == 1:
+            cvec = self.clip_vector(eng, clip_b)
+            x = eng.gemm(a.view(rows, C), pk["o"], bias=pk["bo"], residual=x, rowbias=cvec, rows_per_group=frames * T)
+        else:
+            x = eng.gemm(a.view(rows, C), pk["o"], bias=pk["bo"], residual=x)
+            if self.attn2 is not None:
+                x = self._cross_general(eng, x, clip_b, N, T, frames)
+        n3 = self.norm3.run(eng, x)
+        return self.ff.run(eng, n3, x).view(N, T, C)
+
+    def _cross_general(self, eng, x, ctx_b, N, T, frames):
+        """attn2 for more than one context token (not exercised by the pipeline, kept for API parity)."""
+        a = self.attn2
+        pk = a.packed(eng)
+        C = x.shape[-1]
+        B, Lc, Dc = ctx_b.shape
+        n2 = self.norm2.run(eng, x)
+        q = eng.gemm(n2, pk["q"]).view(N, T, C)
+        kv = eng.gemm(ctx_b.to(eng.dtype).contiguous().view(B * Lc, Dc), pk["kv"]).view(B, Lc, 2 * C)
+        idx = torch.arange(B, device=x.device).repeat_interleave(frames)
+        kvn = kv[idx].contiguous()
+        o = eng.attention(q, kvn[:, :, :C], kvn[:, :, C:], a.heads)
+        return eng.gemm(o.view(N * T, C), pk["o"], bias=pk["bo"], residual=x)
+
+
+class AudioTemporalBasicTransformerBlock(nn.Module):
+    """MM-HAA: spatial self-attention, three audio cross-attentions gated by the full / face / lip motion
+    masks, zero-initialised 1x1 convs, weighted hierarchical sum, GEGLU FF (attention.py:486-771)."""
+
+    def __init__(self, dim, num_attention_heads, attention_head_dim, dropout=0.0, cross_attention_dim=None,
+                 activation_fn="geglu", num_embeds_ada_norm=None, attention_bias=False, only_cross_attention=False,
+                 upcast_attention=False, unet_use_cross_frame_attention=None, unet_use_temporal_attention=None, depth=0,
+                 unet_block_name=None, stack_enable_blocks_name=None, stack_enable_blocks_depth=None):
+        super().__init__()
+        if num_embeds_ada_norm is not None or unet_use_cross_frame_attention:
+            raise NotImplementedError("option not used by config/prompts/animation.yaml")
+        if not (cross_attention_dim is not None and stack_enable_blocks_name is not None
+                and stack_enable_blocks_depth is not None and unet_block_name in stack_enable_blocks_name
+                and depth in stack_enable_blocks_depth):
+            raise NotImplementedError("AudioTemporalBasicTransformerBlock without the 3-branch MM-HAA stack")
+        self.depth = depth
+        self.unet_block_name = unet_block_name
+        self.zero_conv_full = nn.Conv2d(dim, dim, kernel_size=1)
+        self.zero_conv_face = nn.Conv2d(dim, dim, kernel_size=1)
+        self.zero_conv_lip = nn.Conv2d(dim, dim, kernel_size=1)
+        for m in (self.zero_conv_full, self.zero_conv_face, self.zero_conv_lip):   # zero_module (attention.py:773-785)
+            nn.init.zeros_(m.weight)
+            nn.init.zeros_(m.bias)
+        mk = lambda ca: Attention(dim, cross_attention_dim=ca, heads=num_attention_heads,  # noqa: E731
+                                  dim_head=attention_head_dim, bias=attention_bias)
+        self.attn1 = mk(None)
+        self.norm1 = _LN(dim)
+        self.attn2_0, self.attn2_1, self.attn2_2 = mk(cross_attention_dim), mk(cross_attention_dim), mk(cross_attention_dim)
+        self.attn2 = None
+        self.norm2 = _LN(dim)
+        self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
+        self.norm3 = _LN(dim)
+        self._pack = Pack()
+
+    def _packed(self, eng: Engine):
+        branches = (self.attn2_0, self.attn2_1, self.attn2_2)
+        zcs = (self.zero_conv_full, self.zero_conv_face, self.zero_conv_lip)
+        params = [p for a in branches for p in (a.to_q.weight, a.to_k.weight, a.to_v.weight, a.to_out[0].weight,
+                                                 a.to_out[0].bias)] + [p for z in zcs for p in (z.weight, z.bias)]
+
+        def build():
+            d = {}
+            d["q3"] = run(torch.cat([a.to_q.weight for a in branches], dim=0), eng)                    # (3C, C)
+            d["kv6"] = run(torch.cat([w for a in branches for w in (a.to_k.weight, a.to_v.weight)], dim=0), eng)
+            d["o"] = [run(a.to_out[0].weight, eng) for a in branches]
+            d["bo"] = [f32(a.to_out[0].bias, eng) for a in branches]
+            d["z"] = [conv1x1(z.weight, eng) for z in zcs]
+            d["bz"] = [f32(z.bias, eng) for z in zcs]
+            return d
+        return self._pack.get(eng, params, build)
+
+    def run(self, eng: Engine, tok, audio_rows, masks, scale):
+        """tok (N,T,C); audio_rows (N*M, 768) run dtype; masks: 3 x (N*T,) float32; scale: 3 floats."""
+        N, T, C = tok.shape
+        rows = N * T
+        heads = self.attn1.heads
+        x = tok.view(rows, C)
+        p1 = self.attn1.packed(eng)
+        n1 = self.norm1.run(eng, x)
+        qkv = eng.gemm(n1, p1["qkv"]).view(N, T, 3 * C)
+        a = eng.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads)
+        x = eng.gemm(a.view(rows, C), p1["o"], bias=p1["bo"], residual=x)
+        pk = self._packed(eng)
+        n2 = self.norm2.run(eng, x)
+        q3 = eng.gemm(n2, pk["q3"]).view(N, T, 3 * C)
+        M = audio_rows.shape[0] // N
+        kv6 = eng.gemm(audio_rows, pk["kv6"]).view(N, M, 6 * C)
+        acc = x
+        for r in range(3):
+            o = eng.attention(q3[:, :, r * C:(r + 1) * C], kv6[:, :, 2 * r * C:(2 * r + 1) * C],
+                              kv6[:, :, (2 * r + 1) * C:(2 * r + 2) * C], heads)
+            y = eng.gemm(o.view(rows, C), pk["o"][r], bias=pk["bo"][r], rowscale=masks[r])
+            acc = eng.gemm(y, pk["z"][r], bias=pk["bz"][r], alpha=float(scale[r]), residual=acc)
+        x = acc
+        n3 = self.norm3.run(eng, x)
+        return self.ff.run(eng, n3, x).view(N, T, C)
+
+
+def zero_module(module):
+    for p in module.parameters():
+        nn.init.zeros_(p)
+    return module

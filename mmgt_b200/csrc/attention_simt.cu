@@ -1,0 +1,277 @@
+// CUDA-core attention kernels (fp32 math):
+//   * mmgt_attention          flash-style softmax(q k^T) v over up to two key segments  [per-frame ; shared bank]
+//   * mmgt_temporal_attention motion-module attention over the F frames of every (batch, pixel) without re-layout
+// They are the float32-tier path, the audio cross-attention path (Lk = 32) and the shape-generic path.
+#include "common.cuh"
+
+namespace {
+
+constexpr int AQ = 64;        // queries per block
+constexpr int AKV = 32;       // keys per tile (one per lane)
+constexpr int AWARPS = 4;
+constexpr int QG = 4;         // queries processed together per warp
+
+__host__ __device__ inline int padded_stride(int d) { return ((d / 4) % 2 == 0) ? d + 4 : d + 8; }
+
+template <typename T>
+__device__ __forceinline__ void load4g(const T* p, float (&o)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+  } else {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+    float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  }
+}
+
+template <typename T, int DPL>
+__global__ void __launch_bounds__(AWARPS * 32)
+attention_kernel(mmgt_attention_params p) {
+  extern __shared__ float smem[];
+  const int d = p.d, S = padded_stride(d);
+  float* Qs = smem;                 // [AQ][S]
+  float* Ks = Qs + AQ * S;          // [AKV][S]
+  float* Vs = Ks + AKV * S;         // [AKV][S]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
+  const int d4 = d >> 2;
+  const T* qg = reinterpret_cast<const T*>(p.q) + ((int64_t)n * p.Lq) * p.ldq + h * d;
+  const int64_t kvb = p.kv_batch_stride ? p.kv_batch_stride : (int64_t)p.Lk * p.ldk;
+  const int64_t vvb = p.kv_batch_stride ? p.kv_batch_stride : (int64_t)p.Lk * p.ldv;
+  const T* kg = reinterpret_cast<const T*>(p.k) + (int64_t)n * kvb + h * d;
+  const T* vg = reinterpret_cast<const T*>(p.v) + (int64_t)n * vvb + h * d;
+  int seg2 = -1;
+  if (p.k2) seg2 = p.seg2_index ? p.seg2_index[n] : 0;
+  const T* k2g = seg2 >= 0 ? reinterpret_cast<const T*>(p.k2) + ((int64_t)seg2 * p.Lk2) * p.ldk2 + h * d : nullptr;
+  const T* v2g = seg2 >= 0 ? reinterpret_cast<const T*>(p.v2) + ((int64_t)seg2 * p.Lk2) * p.ldv2 + h * d : nullptr;
+  const int Ltot = p.Lk + (seg2 >= 0 ? p.Lk2 : 0);
+
+  // stage Q (pre-scaled)
+  for (int i = tid; i < AQ * d4; i += AWARPS * 32) {
+    int r = i / d4, c = (i % d4) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (q0 + r < p.Lq) load4g<T>(qg + (int64_t)(q0 + r) * p.ldq + c, v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) Qs[r * S + c + e] = v[e] * p.scale;
+  }
+
+  float o[AQ / AWARPS][DPL];
+  float mrun[AQ / AWARPS], lrun[AQ / AWARPS];
+#pragma unroll
+  for (int i = 0; i < AQ / AWARPS; ++i) {
+    mrun[i] = -INFINITY; lrun[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) o[i][j] = 0.f;
+  }
+
+  for (int kt = 0; kt < Ltot; kt += AKV) {
+    __syncthreads();  // previous tile fully consumed (also orders the Q staging before first use)
+    for (int i = tid; i < AKV * d4; i += AWARPS * 32) {
+      int r = i / d4, c = (i % d4) * 4;
+      int key = kt + r;
+      float kv[4] = {0.f, 0.f, 0.f, 0.f}, vv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (key < p.Lk) {
+        load4g<T>(kg + (int64_t)key * p.ldk + c, kv);
+        load4g<T>(vg + (int64_t)key * p.ldv + c, vv);
+      } else if (key < Ltot) {
+        load4g<T>(k2g + (int64_t)(key - p.Lk) * p.ldk2 + c, kv);
+        load4g<T>(v2g + (int64_t)(key - p.Lk) * p.ldv2 + c, vv);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { Ks[r * S + c + e] = kv[e]; Vs[r * S + c + e] = vv[e]; }
+    }
+    __syncthreads();
+    const bool key_ok = kt + lane < Ltot;
+#pragma unroll
+    for (int g = 0; g < AQ / AWARPS / QG; ++g) {
+      float s[QG];
+#pragma unroll
+      for (int qi = 0; qi < QG; ++qi) s[qi] = 0.f;
+      const float* krow = Ks + lane * S;
+      const float* qrow = Qs + (warp * (AQ / AWARPS) + g * QG) * S;
+      for (int c = 0; c < d; c += 4) {
+        float4 k4 = *reinterpret_cast<const float4*>(krow + c);
+#pragma unroll
+        for (int qi = 0; qi < QG; ++qi) {
+          float4 q4 = *reinterpret_cast<const float4*>(qrow + qi * S + c);
+          s[qi] = fmaf(q4.x, k4.x, s[qi]); s[qi] = fmaf(q4.y, k4.y, s[qi]);
+          s[qi] = fmaf(q4.z, k4.z, s[qi]); s[qi] = fmaf(q4.w, k4.w, s[qi]);
+        }
+      }
+      float pr[QG];
+#pragma unroll
+      for (int qi = 0; qi < QG; ++qi) {
+        const int qq = g * QG + qi;
+        float sv = key_ok ? s[qi] : -INFINITY;
+        float mnew = fmaxf(mrun[qq], warp_max(sv));
+        float corr = __expf(mrun[qq] - mnew);   // exp(-inf) = 0 on the first tile
+        float pv = key_ok ? __expf(sv - mnew) : 0.f;
+        lrun[qq] = lrun[qq] * corr + warp_sum(pv);
+        mrun[qq] = mnew;
+        pr[qi] = pv;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) o[qq][j] *= corr;
+      }
+      for (int kk = 0; kk < AKV; ++kk) {
+        float vreg[DPL];
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+          int c = lane + 32 * j;
+          vreg[j] = c < d ? Vs[kk * S + c] : 0.f;
+        }
+#pragma unroll
+        for (int qi = 0; qi < QG; ++qi) {
+          float pk = __shfl_sync(0xffffffffu, pr[qi], kk);
+#pragma unroll
+          for (int j = 0; j < DPL; ++j) o[g * QG + qi][j] = fmaf(pk, vreg[j], o[g * QG + qi][j]);
+        }
+      }
+    }
+  }
+
+  T* og = reinterpret_cast<T*>(p.out) + ((int64_t)n * p.Lq) * p.ldo + h * d;
+#pragma unroll
+  for (int i = 0; i < AQ / AWARPS; ++i) {
+    int q = q0 + warp * (AQ / AWARPS) + i;
+    if (q >= p.Lq) continue;
+    float inv = 1.f / lrun[i];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
+      int c = lane + 32 * j;
+      if (c < d) og[(int64_t)q * p.ldo + c] = from_f32<T>(o[i][j] * inv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Temporal attention.  Row r = (b*F + f)*T + t of qkv holds [q | k | v] (3C).  One warp owns one
+// (b, t, head): lane = query frame; K, V, Q of the F frames are staged in shared memory.
+constexpr int TW = 4;  // warps per block
+template <typename T>
+__global__ void __launch_bounds__(TW * 32)
+temporal_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int B, int F, int T_tok, int heads, int d,
+                          float scale) {
+  extern __shared__ float smem[];
+  const int S = padded_stride(d);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* Qs = smem + (size_t)warp * 3 * F * S;
+  float* Ks = Qs + F * S;
+  float* Vs = Ks + F * S;
+  const int C = heads * d, d4 = d >> 2;
+  const int64_t total = (int64_t)B * T_tok * heads;
+  for (int64_t w = (int64_t)blockIdx.x * TW + warp; w < total; w += (int64_t)gridDim.x * TW) {
+    const int h = w % heads;
+    const int64_t bt = w / heads;
+    const int t = bt % T_tok, b = bt / T_tok;
+    __syncwarp();
+    for (int i = lane; i < F * d4; i += 32) {
+      int f = i / d4, c = (i % d4) * 4;
+      const T* row = qkv + (((int64_t)b * F + f) * T_tok + t) * (3 * C) + h * d + c;
+      float qv[4], kv[4], vv[4];
+      load4g<T>(row, qv); load4g<T>(row + C, kv); load4g<T>(row + 2 * C, vv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { Qs[f * S + c + e] = qv[e] * scale; Ks[f * S + c + e] = kv[e]; Vs[f * S + c + e] = vv[e]; }
+    }
+    __syncwarp();
+    float s[32];
+#pragma unroll
+    for (int f = 0; f < 32; ++f) s[f] = 0.f;
+    const int lq = lane < F ? lane : 0;
+    for (int c = 0; c < d; c += 4) {
+      float4 q4 = *reinterpret_cast<const float4*>(Qs + lq * S + c);
+#pragma unroll
+      for (int f = 0; f < 32; ++f) {
+        if (f < F) {
+          float4 k4 = *reinterpret_cast<const float4*>(Ks + f * S + c);
+          s[f] = fmaf(q4.x, k4.x, s[f]); s[f] = fmaf(q4.y, k4.y, s[f]);
+          s[f] = fmaf(q4.z, k4.z, s[f]); s[f] = fmaf(q4.w, k4.w, s[f]);
+        }
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int f = 0; f < 32; ++f) if (f < F) mx = fmaxf(mx, s[f]);
+    float sum = 0.f;
+#pragma unroll
+    for (int f = 0; f < 32; ++f) if (f < F) { s[f] = __expf(s[f] - mx); sum += s[f]; }
+    const float inv = 1.f / sum;
+    __syncwarp();  // all lanes finished reading Qs before it is reused for the output
+    for (int c = 0; c < d; c += 4) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int f = 0; f < 32; ++f) {
+        if (f < F) {
+          float4 v4 = *reinterpret_cast<const float4*>(Vs + f * S + c);
+          acc.x = fmaf(s[f], v4.x, acc.x); acc.y = fmaf(s[f], v4.y, acc.y);
+          acc.z = fmaf(s[f], v4.z, acc.z); acc.w = fmaf(s[f], v4.w, acc.w);
+        }
+      }
+      if (lane < F) *reinterpret_cast<float4*>(Qs + lane * S + c) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
+    __syncwarp();
+    for (int i = lane; i < F * d; i += 32) {
+      int f = i / d, c = i % d;
+      out[(((int64_t)b * F + f) * T_tok + t) * C + h * d + c] = from_f32<T>(Qs[f * S + c]);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int mmgt_attention(mmgt_ctx* ctx, const mmgt_attention_params* p, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MMGT_CHECK_ARG(ctx && p, MMGT_E_INVALID, "attention: null ctx/params");
+  MMGT_CHECK_ARG(p->q && p->k && p->v && p->out && p->N > 0 && p->Lq > 0 && p->Lk > 0 && p->heads > 0 && p->d > 0,
+                 MMGT_E_INVALID, "attention: bad args");
+  MMGT_CHECK_ARG(!p->k2 || (p->v2 && p->Lk2 > 0), MMGT_E_INVALID, "attention: second segment incomplete");
+  MMGT_CHECK_ARG(p->d % 4 == 0 && p->d <= 160, MMGT_E_UNSUPPORTED, "attention: head dim %d (need multiple of 4, <= 160)", p->d);
+  const int ev = p->dtype == MMGT_F32 ? 16 : 8;
+  MMGT_CHECK_ARG(p->ldq % 4 == 0 && p->ldk % 4 == 0 && p->ldv % 4 == 0 && (!p->k2 || (p->ldk2 % 4 == 0 && p->ldv2 % 4 == 0)) &&
+                     p->kv_batch_stride % 4 == 0,
+                 MMGT_E_ALIGN, "attention: leading dims must be multiples of 4 elements");
+  MMGT_CHECK_ARG((uintptr_t)p->q % ev == 0 && (uintptr_t)p->k % ev == 0 && (uintptr_t)p->v % ev == 0 &&
+                     (!p->k2 || ((uintptr_t)p->k2 % ev == 0 && (uintptr_t)p->v2 % ev == 0)),
+                 MMGT_E_ALIGN, "attention: pointers must be aligned to 4 elements");
+  MMGT_CHECK_ARG(p->N <= 65535 && p->heads <= 65535, MMGT_E_INVALID, "attention: grid too large");
+  const int S = padded_stride(p->d);
+  const size_t smem = sizeof(float) * (size_t)(AQ + 2 * AKV) * S;
+  dim3 grid((p->Lq + AQ - 1) / AQ, p->heads, p->N);
+  const int dpl = (p->d + 31) / 32;
+#define LAUNCH(TT, DPL)                                                                                            \
+  do {                                                                                                             \
+    MMGT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<TT, DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    attention_kernel<TT, DPL><<<grid, AWARPS * 32, smem, st>>>(*p);                                                \
+  } while (0)
+  MMGT_DISPATCH_DTYPE(p->dtype, T_, {
+    if (dpl <= 1) LAUNCH(T_, 1);
+    else if (dpl == 2) LAUNCH(T_, 2);
+    else if (dpl == 3) LAUNCH(T_, 3);
+    else LAUNCH(T_, 5);
+  });
+#undef LAUNCH
+  MMGT_LAUNCH_OK(ctx);
+  return 0;
+}
+
+extern "C" int mmgt_temporal_attention(mmgt_ctx* ctx, const void* qkv, void* out, int B, int F, int T, int heads, int d,
+                                       float scale, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MMGT_CHECK_ARG(ctx && qkv && out && B > 0 && F > 0 && T > 0 && heads > 0 && d > 0, MMGT_E_INVALID,
+                 "temporal_attention: bad args");
+  MMGT_CHECK_ARG(F <= 32, MMGT_E_UNSUPPORTED, "temporal_attention: F=%d > 32 (positional table max_len is 32)", F);
+  MMGT_CHECK_ARG(d % 4 == 0, MMGT_E_UNSUPPORTED, "temporal_attention: head dim must be a multiple of 4");
+  MMGT_CHECK_ARG(aligned16(qkv), MMGT_E_ALIGN, "temporal_attention: qkv must be 16B aligned");
+  const int S = padded_stride(d);
+  const size_t smem = sizeof(float) * (size_t)TW * 3 * F * S;
+  MMGT_CHECK_ARG((int)smem <= ctx->max_smem_optin, MMGT_E_UNSUPPORTED, "temporal_attention: smem %zu too large", smem);
+  const int64_t total = (int64_t)B * T * heads;
+  int blocks = (int)std::min<int64_t>((total + TW - 1) / TW, (int64_t)ctx->num_sms * 32);
+  MMGT_DISPATCH_DTYPE(dtype, T_, {
+    MMGT_CUDA_OK(cudaFuncSetAttribute(temporal_attention_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    temporal_attention_kernel<T_><<<blocks, TW * 32, smem, st>>>((const T_*)qkv, (T_*)out, B, F, T, heads, d, scale);
+  });
+  MMGT_LAUNCH_OK(ctx);
+  return 0;
+}

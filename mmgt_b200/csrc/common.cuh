@@ -1,0 +1,87 @@
+// Shared helpers for the mmgt_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mmgt_b200.h"
+
+struct mmgt_ctx {
+  int device;
+  int num_sms;
+  int max_smem_optin;
+  int use_tc;                 // tcgen05 kernels enabled for bf16
+  long long launches;         // kernels launched through this context
+  void* encode_tiled;         // PFN of cuTensorMapEncodeTiled (resolved lazily through the runtime)
+};
+
+void mmgt_set_error(const char* fmt, ...);
+
+#define MMGT_CHECK_ARG(cond, code, ...)      \
+  do {                                       \
+    if (!(cond)) {                           \
+      mmgt_set_error(__VA_ARGS__);           \
+      return (code);                         \
+    }                                        \
+  } while (0)
+
+#define MMGT_CUDA_OK(expr)                                                          \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      mmgt_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (int)_e;                                                               \
+    }                                                                               \
+  } while (0)
+
+// after a kernel launch: count it and surface launch errors (never synchronises)
+#define MMGT_LAUNCH_OK(ctx)                                                         \
+  do {                                                                              \
+    (ctx)->launches++;                                                              \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess) {                                                        \
+      mmgt_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (int)_e;                                                               \
+    }                                                                               \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// exact (erf) GELU as F.gelu default
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// dtype dispatch: calls fn(T{}) with T = float or bf16
+#define MMGT_DISPATCH_DTYPE(dtype, T, ...)                          \
+  do {                                                              \
+    if ((dtype) == MMGT_F32) { using T = float; __VA_ARGS__; }      \
+    else if ((dtype) == MMGT_BF16) { using T = bf16; __VA_ARGS__; } \
+    else { mmgt_set_error("bad dtype %d", (int)(dtype)); return MMGT_E_INVALID; } \
+  } while (0)
+
+// tensor-core paths (gemm_tc.cu)
+int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st);
+bool mmgt_gemm_tc_supported(const mmgt_ctx* ctx, const mmgt_gemm_params* p);
+int mmgt_conv3x3_tc(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, cudaStream_t st);
+bool mmgt_conv3x3_tc_supported(const mmgt_ctx* ctx, const mmgt_conv3x3_params* p);

@@ -1,0 +1,50 @@
+// Context, error reporting, ABI version.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mmgt_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* mmgt_last_error(void) { return g_err; }
+extern "C" int mmgt_abi_version(void) { return 1; }
+
+extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
+  MMGT_CHECK_ARG(out != nullptr, MMGT_E_INVALID, "mmgt_ctx_create: out is NULL");
+  MMGT_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MMGT_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  MMGT_CHECK_ARG(prop.major == 10, MMGT_E_UNSUPPORTED,
+                 "mmgt_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+  mmgt_ctx* c = new mmgt_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  c->use_tc = 1;
+  c->launches = 0;
+  c->encode_tiled = nullptr;
+  *out = c;
+  return 0;
+}
+
+extern "C" int mmgt_ctx_destroy(mmgt_ctx* ctx) {
+  delete ctx;
+  return 0;
+}
+
+extern "C" int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value) {
+  if (!ctx) return MMGT_E_INVALID;
+  if (flag == 0) {
+    if (value >= 0) ctx->use_tc = value ? 1 : 0;
+    return ctx->use_tc;
+  }
+  if (flag == 1) return ctx->launches;
+  return MMGT_E_INVALID;
+}

@@ -1,0 +1,504 @@
+// tcgen05 / TMEM / TMA GEMM and implicit-GEMM 3x3 convolution for sm_100a (bf16 operands, fp32 accumulate).
+//
+//   D[M, N] = epilogue( A[M, K] * W[N, K]^T )
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0 (one lane)  TMA producer: A / W tiles -> 128B-swizzled shared memory, mbarrier complete_tx
+//   warp 1 (one lane)  tcgen05.mma issuer: 128 x BN x 16 UMMAs into a double-buffered TMEM accumulator
+//   warps 2..5         epilogue: tcgen05.ld -> bias / row-scale / row-bias / residual / GEGLU -> global stores
+// Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty pair (MMA <-> epilogue), so the epilogue
+// of tile i overlaps the main loop of tile i+1.
+//
+// The convolution variant replaces the A loads by 4-D TMA boxes (C, W, H, N) shifted by the filter tap;
+// out-of-image coordinates are zero-filled by the TMA unit, which implements padding = 1 for free, and the
+// K loop runs over 9 taps x Cin/64 channel blocks against the (Cout, 3, 3, Cin) weight viewed as (Cout, 9*Cin).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;             // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+__host__ __device__ constexpr int acc_stride(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
+__host__ __device__ constexpr int num_stages(int bn) { return bn >= 256 ? 4 : bn >= 128 ? 6 : 8; }
+
+struct TcArgs {
+  int M, N_out, num_m_tiles, num_n_tiles, num_k_blocks;
+  // epilogue
+  const float* bias;
+  const float* rowscale;
+  const float* rowbias;
+  const bf16* residual;
+  bf16* D;
+  int64_t ldd, ldr;
+  int rows_per_group;
+  float alpha;
+  // conv geometry (CONV only)
+  int H, W, cin_blocks;
+};
+
+// ------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B swizzle: rows are 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused (1), version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void store16_bf16(bf16* dst, const float (&v)[16]) {
+  uint4 o[2];
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  reinterpret_cast<uint4*>(dst)[0] = o[0];
+  reinterpret_cast<uint4*>(dst)[1] = o[1];
+}
+__device__ __forceinline__ void load16_bf16(const bf16* src, float (&v)[16]) {
+  uint4 o[2];
+  o[0] = reinterpret_cast<const uint4*>(src)[0];
+  o[1] = reinterpret_cast<const uint4*>(src)[1];
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(o);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- kernel
+template <int BN, bool CONV, bool GEGLU>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs args) {
+  constexpr int STAGES = num_stages(BN);
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int ACC_STRIDE = acc_stride(BN);
+  constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  constexpr uint32_t IDESC = make_idesc(BN);
+  static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = args.num_m_tiles * args.num_n_tiles;
+
+  if (threadIdx.x == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / args.num_n_tiles, n_blk = tile % args.num_n_tiles;
+      int cn = 0, ch = 0, cw = 0;
+      if (CONV) {
+        const int m0 = m_blk * BM, hw = args.H * args.W;
+        cn = m0 / hw;
+        const int rem = m0 - cn * hw;
+        ch = rem / args.W;
+        cw = rem - ch * args.W;
+      }
+      for (int kb = 0; kb < args.num_k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        if (CONV) {
+          const int tap = kb / args.cin_blocks, cb = kb - tap * args.cin_blocks;
+          tma_load_4d(sa, &tmA, &full_bar[stage], cb * BK, cw + tap % 3 - 1, ch + tap / 3 - 1, cn);
+        } else {
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+        }
+        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (threadIdx.x == 32) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
+      for (int kb = 0; kb < args.num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // +32 bytes per UMMA_K step inside the 128B swizzle atom => +2 in the (addr >> 4) field
+          umma_bf16(tmem_d, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue =====================
+    const int lane_grp = warp & 3;                 // TMEM lanes this warp may touch: 32*(warp % 4) ..
+    const int row_in_tile = lane_grp * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / args.num_n_tiles, n_blk = tile % args.num_n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(lane_grp * 32) << 16);
+      const int m = m_blk * BM + row_in_tile;
+      const bool m_ok = m < args.M;
+      const float rs = (args.rowscale && m_ok ? args.rowscale[m] : 1.f) * args.alpha;
+      const float* rb = (args.rowbias && m_ok) ? args.rowbias + (int64_t)(m / args.rows_per_group) * args.N_out : nullptr;
+      constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
+      const int n_out0 = n_blk * OUT_COLS;
+#pragma unroll 1
+      for (int c = 0; c < OUT_COLS; c += 16) {
+        uint32_t r[16];
+        float v[16];
+        tmem_ld_x16(taddr + c, r);
+        if (GEGLU) {
+          uint32_t g[16];
+          tmem_ld_x16(taddr + BN / 2 + c, g);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float val = __uint_as_float(r[i]), gate = __uint_as_float(g[i]);
+            if (args.bias) {
+              val += __ldg(args.bias + n_blk * BN + c + i);
+              gate += __ldg(args.bias + n_blk * BN + BN / 2 + c + i);
+            }
+            v[i] = val * gelu_erf_f(gate);
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = __uint_as_float(r[i]);
+            if (args.bias) v[i] += __ldg(args.bias + n_out0 + c + i);
+          }
+        }
+        if (m_ok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= rs;
+          if (rb) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(rb + n_out0 + c + i);
+          }
+          if (args.residual) {
+            float res[16];
+            load16_bf16(args.residual + (int64_t)m * args.ldr + n_out0 + c, res);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += res[i];
+          }
+          store16_bf16(args.D + (int64_t)m * args.ldd + n_out0 + c, v);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int resolve_encode(mmgt_ctx* ctx, EncodeTiledFn* fn) {
+  if (!ctx->encode_tiled) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+      mmgt_set_error("cuTensorMapEncodeTiled not available (%s)", cudaGetErrorString(e));
+      return MMGT_E_NODRIVER;
+    }
+    ctx->encode_tiled = p;
+  }
+  *fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+  return 0;
+}
+
+int make_map(mmgt_ctx* ctx, CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+             const uint32_t* box) {
+  EncodeTiledFn fn;
+  int rc = resolve_encode(ctx, &fn);
+  if (rc) return rc;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mmgt_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,
+                   (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return MMGT_E_INVALID;
+  }
+  return 0;
+}
+
+int pick_bn(int N) {
+  const int cand[5] = {256, 160, 128, 64, 32};
+  for (int i = 0; i < 5; ++i)
+    if (N % cand[i] == 0) return cand[i];
+  return 0;
+}
+
+template <int BN, bool CONV, bool GEGLU>
+int launch_tc(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
+  constexpr int STAGES = num_stages(BN);
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    MMGT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles = a.num_m_tiles * a.num_n_tiles;
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  gemm_tc_kernel<BN, CONV, GEGLU><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a);
+  MMGT_LAUNCH_OK(ctx);
+  return 0;
+}
+
+template <bool CONV>
+int dispatch_tc(mmgt_ctx* ctx, int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a,
+                cudaStream_t st) {
+#define CASE(BN_)                                                              \
+  case BN_:                                                                    \
+    if (!CONV && geglu) return launch_tc<BN_, false, true>(ctx, tmA, tmB, a, st); \
+    return launch_tc<BN_, CONV, false>(ctx, tmA, tmB, a, st);
+  switch (bn) {
+    CASE(256)
+    CASE(160)
+    CASE(128)
+    CASE(64)
+    CASE(32)
+  }
+#undef CASE
+  mmgt_set_error("gemm_tc: no kernel for BN=%d", bn);
+  return MMGT_E_UNSUPPORTED;
+}
+
+}  // namespace
+
+extern "C" int mmgt_gemm_tc_block_n(int N) { return pick_bn(N); }
+
+bool mmgt_gemm_tc_supported(const mmgt_ctx* ctx, const mmgt_gemm_params* p) {
+  (void)ctx;
+  if (p->dtype != MMGT_BF16 || p->out_f32) return false;
+  const int bn = pick_bn(p->N);
+  if (!bn) return false;
+  if (p->geglu_block && p->geglu_block * 2 != bn) return false;
+  if (p->K % 8 || p->lda % 8 || p->ldw % 8) return false;
+  if (!aligned16(p->A) || !aligned16(p->W) || !aligned16(p->D)) return false;
+  const int n_out = p->geglu_block ? p->N / 2 : p->N;
+  if (n_out % 16 || p->ldd % 8) return false;
+  if (p->residual && (!aligned16(p->residual) || p->ldr % 8)) return false;
+  if (p->M < 1) return false;
+  return true;
+}
+
+int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
+  const int bn = pick_bn(p->N);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->M};
+    uint64_t str[1] = {(uint64_t)p->lda * 2};
+    uint32_t box[2] = {BK, BM};
+    int rc = make_map(ctx, &tmA, p->A, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
+    uint64_t str[1] = {(uint64_t)p->ldw * 2};
+    uint32_t box[2] = {BK, (uint32_t)bn};
+    int rc = make_map(ctx, &tmB, p->W, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  TcArgs a{};
+  a.M = p->M;
+  a.N_out = p->geglu_block ? p->N / 2 : p->N;
+  a.num_m_tiles = (p->M + BM - 1) / BM;
+  a.num_n_tiles = p->N / bn;
+  a.num_k_blocks = (p->K + BK - 1) / BK;
+  a.bias = p->bias; a.rowscale = p->rowscale; a.rowbias = p->rowbias;
+  a.residual = (const bf16*)p->residual; a.D = (bf16*)p->D;
+  a.ldd = p->ldd; a.ldr = p->ldr; a.rows_per_group = p->rows_per_group > 0 ? p->rows_per_group : 1; a.alpha = p->alpha;
+  return dispatch_tc<false>(ctx, bn, p->geglu_block != 0, tmA, tmB, a, st);
+}
+
+static bool conv_box(const mmgt_conv3x3_params* p, uint32_t* bw, uint32_t* bh, uint32_t* bn_frames) {
+  const int W = p->W, H = p->H;
+  if (W >= BM) {
+    if (W % BM) return false;
+    *bw = BM; *bh = 1; *bn_frames = 1;
+    return true;
+  }
+  if (BM % W) return false;
+  int rows = BM / W;
+  if (rows <= H) {
+    if (H % rows) return false;
+    *bw = W; *bh = rows; *bn_frames = 1;
+    return true;
+  }
+  if (rows % H) return false;
+  *bw = W; *bh = H; *bn_frames = rows / H;
+  return true;
+}
+
+bool mmgt_conv3x3_tc_supported(const mmgt_ctx* ctx, const mmgt_conv3x3_params* p) {
+  (void)ctx;
+  if (p->dtype != MMGT_BF16 || p->stride != 1 || p->upsample2x) return false;
+  if (p->Cin % BK || !pick_bn(p->Cout) || p->Cout % 16) return false;
+  uint32_t bw, bh, bf;
+  if (!conv_box(p, &bw, &bh, &bf)) return false;
+  if (!aligned16(p->x) || !aligned16(p->w) || !aligned16(p->y) || (p->residual && !aligned16(p->residual))) return false;
+  return true;
+}
+
+int mmgt_conv3x3_tc(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, cudaStream_t st) {
+  const int bn = pick_bn(p->Cout);
+  uint32_t bw, bh, bf;
+  conv_box(p, &bw, &bh, &bf);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
+    uint64_t str[3] = {(uint64_t)p->Cin * 2, (uint64_t)p->W * p->Cin * 2, (uint64_t)p->H * p->W * p->Cin * 2};
+    uint32_t box[4] = {BK, bw, bh, bf};
+    int rc = make_map(ctx, &tmA, p->x, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)9 * p->Cin, (uint64_t)p->Cout};
+    uint64_t str[1] = {(uint64_t)9 * p->Cin * 2};
+    uint32_t box[2] = {BK, (uint32_t)bn};
+    int rc = make_map(ctx, &tmB, p->w, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  TcArgs a{};
+  a.M = p->N * p->H * p->W;
+  a.N_out = p->Cout;
+  a.num_m_tiles = (a.M + BM - 1) / BM;
+  a.num_n_tiles = p->Cout / bn;
+  a.cin_blocks = p->Cin / BK;
+  a.num_k_blocks = 9 * a.cin_blocks;
+  a.bias = p->bias; a.rowscale = nullptr; a.rowbias = p->rowbias;
+  a.residual = (const bf16*)p->residual; a.D = (bf16*)p->y;
+  a.ldd = p->Cout; a.ldr = p->Cout;
+  a.rows_per_group = p->rowbias ? p->frames_per_group * p->H * p->W : 1;
+  a.alpha = 1.f;
+  a.H = p->H; a.W = p->W;
+  return dispatch_tc<true>(ctx, bn, false, tmA, tmB, a, st);
+}

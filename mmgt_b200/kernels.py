@@ -1,0 +1,279 @@
+"""Tensor-level wrappers over the C ABI: torch tensors in, torch tensors out, all math in libmmgt_b200.so.
+
+torch is used only for device memory (``torch.empty``), streams and dtype bookkeeping.
+Activations are channels-last token tensors ``(N, T, C)`` / ``(N, H, W, C)``, contiguous.
+"""
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import AttentionParams, Context, Conv3x3Params, GemmParams, check
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def dt_code(dtype: torch.dtype) -> int:
+    try:
+        return _DT[dtype]
+    except KeyError:
+        raise TypeError(f"mmgt_b200 kernels run in float32 or bfloat16, not {dtype} "
+                        "(the reference's fp16 mode maps to bfloat16 here)") from None
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """All kernels for one device + one storage dtype."""
+
+    def __init__(self, device: torch.device, dtype: torch.dtype):
+        if device.type != "cuda":
+            raise RuntimeError("mmgt_b200 has no CPU path: tensors must live on a CUDA (sm_100a) device")
+        self.device = device
+        self.dtype = dtype
+        self.dt = dt_code(dtype)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.ctx = Context.get(idx)
+        self.lib = self.ctx.lib
+        self.h = self.ctx.handle
+        self._stats_ws = None
+        self._conv_ws = None
+        self.prof = None          # optional: dict key -> [events..., flops, bytes] filled by bench.py's roofline pass
+
+    # ------------------------------------------------------------------ per-launch timing (bench.py only)
+    def _t0(self):
+        if self.prof is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def _t1(self, ev0, key, flops=0.0, nbytes=0.0):
+        if ev0 is None:
+            return
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        rec = self.prof.setdefault(key, dict(events=[], flops=0.0, bytes=0.0, calls=0))
+        rec["events"].append((ev0, ev1))
+        rec["flops"] += flops
+        rec["bytes"] += nbytes
+        rec["calls"] += 1
+
+    # ------------------------------------------------------------------ helpers
+    def empty(self, *shape, dtype=None):
+        return torch.empty(shape, device=self.device, dtype=dtype or self.dtype)
+
+    def _stats(self, n_doubles: int):
+        if self._stats_ws is None or self._stats_ws.numel() < n_doubles:
+            self._stats_ws = torch.empty(max(n_doubles, 8192), device=self.device, dtype=torch.float64)
+        return self._stats_ws
+
+    def geglu_block(self, n_rows: int) -> int:
+        """Row-interleave granularity a GEGLU weight with ``n_rows`` rows should be packed with."""
+        bn = self.lib.mmgt_gemm_tc_block_n(int(n_rows)) if self.dtype == torch.bfloat16 else 0
+        return bn // 2 if bn else n_rows // 2
+
+    # ------------------------------------------------------------------ layout
+    def ncfhw_to_tokens(self, x: torch.Tensor, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, Cc, F, H, W = x.shape
+        x = x.contiguous()
+        if x.dtype not in _DT:
+            x = x.float()
+        if add is not None:
+            add = add.contiguous().to(x.dtype)
+        out = self.empty(B * F, H, W, Cc)
+        check(self.lib.mmgt_ncfhw_to_tokens(self.h, _p(x), _p(add), _p(out), B, Cc, F, H, W, dt_code(x.dtype), self.dt,
+                                             _stream()), "mmgt_ncfhw_to_tokens")
+        return out
+
+    def tokens_to_ncfhw(self, x: torch.Tensor, B: int, F: int, out_dtype: torch.dtype) -> torch.Tensor:
+        N, H, W, Cc = x.shape
+        out = torch.empty((B, Cc, F, H, W), device=self.device, dtype=out_dtype)
+        check(self.lib.mmgt_tokens_to_ncfhw(self.h, _p(x), _p(out), B, Cc, F, H, W, self.dt, dt_code(out_dtype), _stream()),
+              "mmgt_tokens_to_ncfhw")
+        return out
+
+    # ------------------------------------------------------------------ norms
+    def groupnorm(self, x1, x2, gamma, beta, groups: int, eps: float, silu: bool):
+        N = x1.shape[0]
+        C1 = x1.shape[-1]
+        C2 = x2.shape[-1] if x2 is not None else 0
+        T = x1.numel() // (N * C1)
+        out = self.empty(*x1.shape[:-1], C1 + C2)
+        ws = self._stats(2 * N * groups)
+        ev = self._t0()
+        check(self.lib.mmgt_groupnorm(self.h, _p(x1), _p(x2), _p(out), _p(gamma), _p(beta), _p(ws), N, T, C1, C2, groups,
+                                       float(eps), int(silu), self.dt, _stream()), "mmgt_groupnorm")
+        self._t1(ev, ("groupnorm", C1 + C2), 0.0, 3.0 * out.numel() * out.element_size())
+        return out
+
+    def layernorm(self, x, gamma, beta, eps: float = 1e-5, pe=None, T: int = 0, F: int = 0):
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc
+        out = torch.empty_like(x)
+        ev = self._t0()
+        check(self.lib.mmgt_layernorm(self.h, _p(x), _p(out), _p(gamma), _p(beta), _p(pe), rows, Cc, T, F, float(eps),
+                                       self.dt, _stream()), "mmgt_layernorm")
+        self._t1(ev, ("layernorm", Cc), 0.0, 2.0 * out.numel() * out.element_size())
+        return out
+
+    # ------------------------------------------------------------------ gemm / conv
+    def gemm(self, A, W, bias=None, rowscale=None, rowbias=None, rows_per_group: int = 0, residual=None,
+             alpha: float = 1.0, geglu_block: int = 0, out=None, out_f32: bool = False, dtype=None):
+        """D = alpha * rowscale * (A @ W^T + bias) + rowbias[row // rows_per_group] + residual (then GEGLU).
+        A: (..., K) rows with an arbitrary leading stride on the last-but-one dim; W: (N, K)."""
+        K = A.shape[-1]
+        M = A.numel() // K if A.is_contiguous() else A.shape[0]
+        lda = K if A.is_contiguous() else A.stride(-2)
+        N = W.shape[0]
+        ldw = W.stride(0)
+        n_out = N // 2 if geglu_block else N
+        dt = self.dt if dtype is None else dt_code(dtype)
+        if out is None:
+            odt = torch.float32 if out_f32 else (self.dtype if dtype is None else dtype)
+            out = torch.empty(tuple(A.shape[:-1]) + (n_out,), device=self.device, dtype=odt)
+        p = GemmParams()
+        p.A, p.W, p.D = A.data_ptr(), W.data_ptr(), out.data_ptr()
+        p.bias = bias.data_ptr() if bias is not None else None
+        p.rowscale = rowscale.data_ptr() if rowscale is not None else None
+        p.rowbias = rowbias.data_ptr() if rowbias is not None else None
+        p.residual = residual.data_ptr() if residual is not None else None
+        p.lda, p.ldw, p.ldd = lda, ldw, out.stride(-2) if out.dim() > 1 else n_out
+        p.ldr = residual.stride(-2) if residual is not None else 0
+        p.M, p.N, p.K = M, N, K
+        p.rows_per_group = rows_per_group
+        p.alpha = alpha
+        p.geglu_block = geglu_block
+        p.dtype = dt
+        p.out_f32 = int(out_f32)
+        ev = self._t0()
+        check(self.lib.mmgt_gemm(self.h, C.byref(p), _stream()), "mmgt_gemm")
+        self._t1(ev, ("gemm", N, K, bool(geglu_block)), 2.0 * M * N * K,
+                 (M * K + N * K + M * n_out * (2 if residual is not None else 1)) * A.element_size())
+        return out
+
+    def conv3x3(self, x, w_krsc, bias=None, rowbias=None, frames_per_group: int = 0, residual=None, stride: int = 1,
+                upsample2x: bool = False):
+        N, H, W, Cin = x.shape
+        Cout = w_krsc.shape[0]
+        Hi, Wi = (2 * H, 2 * W) if upsample2x else (H, W)
+        Ho, Wo = (Hi - 1) // stride + 1, (Wi - 1) // stride + 1
+        out = self.empty(N, Ho, Wo, Cout)
+        p = Conv3x3Params()
+        p.x, p.w, p.y = x.data_ptr(), w_krsc.data_ptr(), out.data_ptr()
+        p.bias = bias.data_ptr() if bias is not None else None
+        p.rowbias = rowbias.data_ptr() if rowbias is not None else None
+        p.residual = residual.data_ptr() if residual is not None else None
+        p.N, p.H, p.W, p.Cin, p.Cout = N, H, W, Cin, Cout
+        p.stride, p.upsample2x, p.frames_per_group, p.dtype = stride, int(upsample2x), frames_per_group, self.dt
+        need = self.lib.mmgt_conv3x3_workspace_bytes(self.h, C.byref(p))
+        ws = None
+        if need > 0:
+            if self._conv_ws is None or self._conv_ws.numel() < need:
+                self._conv_ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+            ws = self._conv_ws
+        ev = self._t0()
+        check(self.lib.mmgt_conv3x3(self.h, C.byref(p), _p(ws), need if need > 0 else 0, _stream()), "mmgt_conv3x3")
+        self._t1(ev, ("conv3x3", Cin, Cout, stride, int(upsample2x)), 2.0 * N * Ho * Wo * 9 * Cin * Cout,
+                 (x.numel() + w_krsc.numel() + out.numel() * (2 if residual is not None else 1)) * x.element_size())
+        return out
+
+    # ------------------------------------------------------------------ attention
+    def attention(self, q, k, v, heads: int, k2=None, v2=None, seg2_index=None, kv_batch_stride: int = 0):
+        """q: (N, Lq, C) view (last dim contiguous); k, v: (N, Lk, C) views; k2, v2: (B2, Lk2, C) views."""
+        N, Lq, Cc = q.shape
+        d = Cc // heads
+        out = self.empty(N, Lq, Cc)
+        p = AttentionParams()
+        p.q, p.k, p.v, p.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+        p.ldq, p.ldk, p.ldv, p.ldo = q.stride(1), k.stride(1), v.stride(1), Cc
+        p.kv_batch_stride = kv_batch_stride if kv_batch_stride else k.stride(0)
+        p.N, p.Lq, p.Lk, p.heads, p.d = N, Lq, k.shape[1], heads, d
+        if k2 is not None:
+            p.k2, p.v2 = k2.data_ptr(), v2.data_ptr()
+            p.ldk2, p.ldv2, p.Lk2 = k2.stride(1), v2.stride(1), k2.shape[1]
+            p.seg2_index = seg2_index.data_ptr() if seg2_index is not None else None
+        p.scale = float(d) ** -0.5
+        p.dtype = self.dt
+        ev = self._t0()
+        check(self.lib.mmgt_attention(self.h, C.byref(p), _stream()), "mmgt_attention")
+        lk_tot = k.shape[1] + (k2.shape[1] if k2 is not None else 0)   # upper bound: frames without segment 2 do less
+        self._t1(ev, ("attention", d, k.shape[1], k2 is not None), 4.0 * N * heads * Lq * lk_tot * d,
+                 (2 * q.numel() + 2 * N * lk_tot * Cc) * q.element_size())
+        return out
+
+    def temporal_attention(self, qkv, B: int, F: int, T: int, heads: int):
+        Cc = qkv.shape[-1] // 3
+        d = Cc // heads
+        out = self.empty(B * F * T, Cc)
+        ev = self._t0()
+        check(self.lib.mmgt_temporal_attention(self.h, _p(qkv), _p(out), B, F, T, heads, d, float(d) ** -0.5, self.dt,
+                                                _stream()), "mmgt_temporal_attention")
+        self._t1(ev, ("temporal_attention", d), 4.0 * B * T * heads * F * F * d, (qkv.numel() + out.numel()) * out.element_size())
+        return out
+
+    # ------------------------------------------------------------------ small pieces
+    def timestep_embedding(self, t_f32, dim: int, flip: bool, shift: float):
+        B = t_f32.numel()
+        out = torch.empty((B, dim), device=self.device, dtype=torch.float32)
+        check(self.lib.mmgt_timestep_embedding(self.h, _p(t_f32), _p(out), B, dim, int(flip), float(shift), _stream()),
+              "mmgt_timestep_embedding")
+        return out
+
+    def silu_f32(self, x):
+        out = torch.empty_like(x)
+        check(self.lib.mmgt_silu_f32(self.h, _p(x), _p(out), x.numel(), _stream()), "mmgt_silu_f32")
+        return out
+
+    def upsample_nearest2x(self, x):
+        N, H, W, Cc = x.shape
+        out = self.empty(N, 2 * H, 2 * W, Cc)
+        check(self.lib.mmgt_upsample_nearest2x(self.h, _p(x), _p(out), N, H, W, Cc, self.dt, _stream()),
+              "mmgt_upsample_nearest2x")
+        return out
+
+    def gather_rows(self, src, idx_i32, out=None):
+        """out[i] = src[idx[i]] along dim 0 (rows must be multiples of 16 bytes)."""
+        n_out = idx_i32.numel()
+        row_bytes = src[0].numel() * src.element_size()
+        if out is None:
+            out = torch.empty((n_out,) + tuple(src.shape[1:]), device=self.device, dtype=src.dtype)
+        check(self.lib.mmgt_gather_rows(self.h, _p(src), _p(idx_i32), _p(out), n_out, row_bytes, _stream()), "mmgt_gather_rows")
+        return out
+
+    def window_accumulate(self, noise_acc, pred, frames_i32, b0: int):
+        Bp, Cc, Fw, H, W = pred.shape
+        L = noise_acc.shape[2]
+        check(self.lib.mmgt_window_accumulate(self.h, _p(noise_acc), _p(pred), _p(frames_i32), Bp, b0, Cc, L, Fw, H * W,
+                                               dt_code(pred.dtype), _stream()), "mmgt_window_accumulate")
+
+    def cfg_ddim_step(self, latents, noise_acc, inv_count, cfg: bool, guidance: float, cx: float, cv: float):
+        _, Cc, L, H, W = latents.shape
+        check(self.lib.mmgt_cfg_ddim_step(self.h, _p(latents), _p(noise_acc), _p(inv_count), Cc, L, H * W, int(cfg),
+                                           float(guidance), float(cx), float(cv), _stream()), "mmgt_cfg_ddim_step")
+
+    def mask_resize(self, src_u8, S: int, offset: float = 0.0, want_u8: bool = False):
+        L, Hs, Ws = src_u8.shape
+        tmp = torch.empty((L, Hs, S), device=self.device, dtype=torch.uint8)
+        out_f = torch.empty((L, S * S), device=self.device, dtype=torch.float32)
+        out_u = torch.empty((L, S, S), device=self.device, dtype=torch.uint8) if want_u8 else None
+        check(self.lib.mmgt_mask_resize(self.h, _p(src_u8), _p(tmp), _p(out_u), _p(out_f), L, Hs, Ws, S, float(offset),
+                                         _stream()), "mmgt_mask_resize")
+        return (out_f, out_u) if want_u8 else out_f
+
+
+_engines = {}
+
+
+def get_engine(device: torch.device, dtype: torch.dtype) -> Engine:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), dtype)
+    if key not in _engines:
+        _engines[key] = Engine(torch.device(key[0], key[1]), dtype)
+    return _engines[key]

@@ -1,0 +1,231 @@
+"""Host mirror of src/pipelines/pipeline_pose2vid_long.py.
+
+``DenoiseLoop`` is the hot loop (:491-646): per DDIM step, one UNet forward per 12-frame context window with
+CFG, overlap-averaged, CFG-combined and DDIM-updated -- everything on the sm_100a kernels.
+``Pose2VideoPipeline`` keeps the reference's constructor and ``__call__`` signature; the one-shot conditioning
+passes (CLIP, VAE, ReferenceNet write pass, pose guider) remain the caller's PyTorch modules.
+
+Multi-GPU (one process per GPU): the (window, CFG-branch) forwards of a step are independent
+ and are dealt round-robin to the ranks; the only exchange is one all-reduce of the
+overlap-accumulated prediction (2*4*L*h*w float32) per step.
+"""
+import math
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Union
+
+import torch
+
+from .context import get_context_scheduler
+from .kernels import Engine
+from .mutual_self_attention import ReferenceAttentionControl
+from .scheduling_ddim import DDIMSchedule
+
+
+@dataclass
+class Pose2VideoPipelineOutput:
+    videos: Union[torch.Tensor, "object"]
+
+
+class DenoiseLoop:
+    def __init__(self, unet, schedule: DDIMSchedule, num_inference_steps: int, guidance_scale: float,
+                 context_frames: int = 12, context_stride: int = 1, context_overlap: int = 4,
+                 context_schedule: str = "uniform", motion_scale: Optional[Sequence[float]] = None,
+                 rank: int = 0, world_size: int = 1, process_group=None):
+        self.unet = unet
+        self.schedule = schedule
+        self.n_steps = num_inference_steps
+        self.guidance = float(guidance_scale)
+        self.cfg = guidance_scale > 1.0
+        self.ctx_args = (context_frames, context_stride, context_overlap)
+        self.context_scheduler = get_context_scheduler(context_schedule)
+        self.motion_scale = motion_scale
+        self.rank, self.world, self.group = rank, world_size, process_group
+        self.timesteps = schedule.timesteps(num_inference_steps)
+        self._graph = None
+
+    # ------------------------------------------------------------------ one-off preparation per video
+    def prepare(self, latents, pose_fea, audio, full_mask, face_mask, lip_mask, encoder_hidden_states):
+        """latents (1,4,L,h,w); pose_fea (1,320,L,h,w); audio (nb,L,M,768); *_mask: 4 x (nb*L, T_l);
+        encoder_hidden_states (nb,1,768) with nb = 2 under CFG ([uncond; cond]) else 1."""
+        u = self.unet
+        dev = latents.device
+        eng: Engine = u._engine(dev)
+        self.eng = eng
+        nb = 2 if self.cfg else 1
+        _, C, L, h, w = latents.shape
+        self.L, self.C, self.h, self.w, self.nb = L, C, h, w, nb
+        self.latents = latents.to(torch.float32).contiguous().clone()
+        cf, cs, co = self.ctx_args
+        self.windows = [list(map(int, c)) for c in self.context_scheduler(0, self.n_steps, L, cf, cs, co)]
+        # (window, branch) units of this rank
+        units = [(wi, b) for wi in range(len(self.windows)) for b in range(nb)]
+        self.units = units[self.rank::self.world]
+        counts = torch.zeros(L, dtype=torch.float32)
+        for c in self.windows:
+            for f in c:
+                counts[f] += 1
+        self.inv_count = (1.0 / counts).to(dev)
+        self.noise_acc = torch.zeros((nb, C, L, h, w), device=dev, dtype=torch.float32)
+        self.t_dev = torch.zeros(1, device=dev, dtype=torch.float32)
+        # whole-video constants in kernel layout
+        pose_tok = eng.ncfhw_to_tokens(pose_fea) if pose_fea is not None else None      # (L,h,w,320)
+        audio_all = audio.to(device=dev, dtype=eng.dtype).contiguous()                   # (nb,L,M,768)
+        ehs = encoder_hidden_states.to(dev)
+        masks = [[m.to(device=dev, dtype=torch.float32).contiguous() for m in ms] for ms in (full_mask, face_mask, lip_mask)]
+        self.win = []
+        for c in self.windows:
+            idx = torch.tensor(c, dtype=torch.int32, device=dev)
+            entry = dict(idx=idx, pose=eng.gather_rows(pose_tok, idx) if pose_tok is not None else None, per_branch=[])
+            for b in range(nb):
+                rows = idx + b * L
+                aud = eng.gather_rows(audio_all.view(nb * L, -1), rows).view(1, len(c), audio_all.shape[2], audio_all.shape[3])
+                mk = [[eng.gather_rows(_pad16(m), rows)[:, : m.shape[1]].contiguous() for m in ms] for ms in masks]
+                entry["per_branch"].append(dict(audio=aud, masks=mk, ehs=ehs[b:b + 1]))
+            self.win.append(entry)
+        return self
+
+    # ------------------------------------------------------------------ the hot loop
+    def _forward_units(self, lat_tok):
+        eng, u = self.eng, self.unet
+        F_ = None
+        for wi, b in self.units:
+            e = self.win[wi]
+            pb = e["per_branch"][b]
+            F_ = e["idx"].numel()
+            x = eng.gather_rows(lat_tok, e["idx"])
+            ref = [None] if (self.cfg and b == 0) else [b]
+            out = u.forward_tokens(eng, x, self.t_dev, pb["ehs"], pb["audio"], e["pose"], pb["masks"][0], pb["masks"][1],
+                                   pb["masks"][2], self.motion_scale, 1, F_, ref_index=ref)
+            pred = eng.tokens_to_ncfhw(out, 1, F_, torch.float32)
+            eng.window_accumulate(self.noise_acc, pred, e["idx"], b)
+
+    def step(self, i: int):
+        """One DDIM step over the whole video (all context windows, both CFG branches)."""
+        eng = self.eng
+        t = self.timesteps[i]
+        self.t_dev.fill_(float(t))
+        self.noise_acc.zero_()
+        lat_tok = eng.ncfhw_to_tokens(self.latents)[: self.L]          # (L,h,w,4) run dtype
+        self._forward_units(lat_tok)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.noise_acc, group=self.group)
+        cx, cv = self.schedule.step_coefficients(t, self.n_steps)
+        eng.cfg_ddim_step(self.latents, self.noise_acc, self.inv_count, self.cfg, self.guidance, cx, cv)
+        return self.latents
+
+    def run(self, callback: Optional[Callable] = None, callback_steps: int = 1):
+        for i in range(len(self.timesteps)):
+            self.step(i)
+            if callback is not None and i % callback_steps == 0:
+                callback(i, self.timesteps[i], self.latents)
+        return self.latents
+
+
+def _pad16(m: torch.Tensor) -> torch.Tensor:
+    """Rows must be multiples of 16 bytes for mmgt_gather_rows (the 8x8 level has 64 floats: fine; 4x4 not)."""
+    cols = m.shape[1]
+    pad = (-cols) % 4
+    if pad == 0:
+        return m
+    out = torch.zeros((m.shape[0], cols + pad), device=m.device, dtype=m.dtype)
+    out[:, :cols] = m
+    return out
+
+
+class Pose2VideoPipeline:
+    """Same constructor / ``__call__`` signature as the reference (pipeline_pose2vid_long.py:38-56,337-366)."""
+
+    def __init__(self, vae, image_encoder, reference_unet, denoising_unet, pose_guider, scheduler, image_proj_model=None,
+                 tokenizer=None, text_encoder=None):
+        self.vae, self.image_encoder, self.reference_unet = vae, image_encoder, reference_unet
+        self.denoising_unet, self.pose_guider, self.scheduler = denoising_unet, pose_guider, scheduler
+        self.image_proj_model, self.tokenizer, self.text_encoder = image_proj_model, tokenizer, text_encoder
+        self.vae_scale_factor = 8
+        self.rank, self.world_size, self.process_group = 0, 1, None
+
+    def to(self, *a, **k):
+        for m in (self.vae, self.image_encoder, self.reference_unet, self.denoising_unet, self.pose_guider):
+            if m is not None and hasattr(m, "to"):
+                m.to(*a, **k)
+        return self
+
+    @property
+    def _execution_device(self):
+        return self.denoising_unet.device
+
+    def prepare_latents(self, batch_size, num_channels_latents, width, height, video_length, dtype, device, generator,
+                        latents=None):
+        shape = (batch_size, num_channels_latents, video_length, height // self.vae_scale_factor,
+                 width // self.vae_scale_factor)
+        if latents is None:
+            gdev = generator.device if generator is not None else torch.device("cpu")
+            latents = torch.randn(shape, generator=generator, device=gdev, dtype=torch.float32).to(device)
+        return latents * 1.0   # init_noise_sigma == 1 for DDIM
+
+    def decode_latents(self, latents):
+        """Frame-by-frame VAE decode, as pipeline_pose2vid_long.py:112-125 (PyTorch; out of the timed path)."""
+        video_length = latents.shape[2]
+        latents = 1 / 0.18215 * latents
+        frames = []
+        for f in range(video_length):
+            frames.append(self.vae.decode(latents[:, :, f].to(self.vae.dtype)).sample)
+        video = torch.stack(frames, dim=2)
+        return ((video / 2 + 0.5).clamp(0, 1)).cpu().float().numpy()
+
+    @torch.no_grad()
+    def __call__(self, ref_image, pose_images, audio_tensor, pixel_values_full_mask, pixel_values_face_mask,
+                 pixel_values_lip_mask, width, height, video_length, num_inference_steps, guidance_scale,
+                 num_images_per_prompt=1, eta: float = 0.0, motion_scale=None, generator=None, output_type="tensor",
+                 return_dict: bool = True, callback=None, callback_steps=1, context_schedule="uniform", context_frames=12,
+                 context_stride=1, context_overlap=4, context_batch_size=1, interpolation_factor=1, **kwargs):
+        if eta != 0.0:
+            raise NotImplementedError("eta != 0")
+        device = self._execution_device
+        cfg = guidance_scale > 1.0
+        # --- one-shot conditioning: the reference's own modules (PyTorch), or precomputed tensors via kwargs
+        clip_embeds = kwargs.get("clip_image_embeds")
+        if clip_embeds is None:
+            from transformers import CLIPImageProcessor
+            clip_image = CLIPImageProcessor().preprocess(ref_image.resize((224, 224)), return_tensors="pt").pixel_values
+            clip_embeds = self.image_encoder(clip_image.to(device, dtype=self.image_encoder.dtype)).image_embeds
+        ehs = clip_embeds.unsqueeze(1) if clip_embeds.dim() == 2 else clip_embeds
+        if cfg:
+            ehs = torch.cat([torch.zeros_like(ehs), ehs], dim=0)
+        reader = ReferenceAttentionControl(self.denoising_unet, do_classifier_free_guidance=cfg, mode="read", batch_size=1,
+                                           fusion_blocks="full")
+        latents = self.prepare_latents(num_images_per_prompt, self.denoising_unet.in_channels, width, height, video_length,
+                                       torch.float32, device, generator, kwargs.get("latents"))
+        banks = kwargs.get("reference_banks")
+        if banks is not None:
+            reader.set_banks(banks)
+        else:
+            writer = kwargs.get("reference_control_writer")
+            if writer is None:
+                raise ValueError("pass reference_banks=[...] or reference_control_writer=<the reference's writer control> "
+                                 "(the ReferenceNet write pass is the reference's PyTorch)")
+            ref_latents = kwargs["ref_image_latents"]
+            self.reference_unet(ref_latents.repeat(2 if cfg else 1, 1, 1, 1), torch.zeros((), device=device),
+                                encoder_hidden_states=ehs.to(ref_latents.dtype), return_dict=False)
+            reader.update(writer)
+        pose_fea = kwargs.get("pose_fea")
+        if pose_fea is None:
+            pose_fea = self.pose_guider(pose_images.to(device=device, dtype=self.pose_guider.dtype))
+        dup = (lambda ms: [torch.cat([m] * 2) for m in ms]) if cfg else (lambda ms: list(ms))
+        audio = audio_tensor.to(device)
+        if cfg:
+            audio = torch.cat([torch.zeros_like(audio), audio], dim=0)
+        sched = self.scheduler if isinstance(self.scheduler, DDIMSchedule) else DDIMSchedule.from_scheduler(self.scheduler)
+        loop = DenoiseLoop(self.denoising_unet, sched, num_inference_steps, guidance_scale, context_frames, context_stride,
+                           context_overlap, context_schedule, motion_scale, self.rank, self.world_size, self.process_group)
+        loop.prepare(latents, pose_fea, audio, dup(pixel_values_full_mask), dup(pixel_values_face_mask),
+                     dup(pixel_values_lip_mask), ehs)
+        latents = loop.run(callback, callback_steps)
+        reader.clear()
+        if output_type == "latent" or self.vae is None:
+            images = latents
+        else:
+            images = torch.from_numpy(self.decode_latents(latents))
+        if not return_dict:
+            return images
+        return Pose2VideoPipelineOutput(videos=images)

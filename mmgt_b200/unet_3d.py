@@ -1,0 +1,382 @@
+"""Host mirror of src/models/unet_3d.py: ``UNet3DConditionModel`` with the reference's constructor
+arguments, state-dict keys / shapes and ``forward`` signature, executing on the sm_100a kernels.
+
+Differences that are deliberate (and invisible through the reference API):
+  * activations live channels-last as (N = B*F, H, W, C); NCFHW only exists at the boundary;
+  * the reference-feature (bank) K/V projections are cached per video, the CFG "uncond re-do" is a
+    per-frame key-length switch inside one attention launch, CLIP cross-attention (1 token) is a vector add;
+  * compute dtype is float32 or bfloat16 (the reference's fp16 maps to bf16); parameters may stay float32
+    while kernels run in bf16 (``set_compute_dtype``).
+"""
+import json
+import os
+from dataclasses import dataclass
+from pathlib import Path
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from .kernels import Engine, get_engine
+from .packing import Pack, f32
+from .resnet import InflatedConv3d, InflatedGroupNorm
+from .unet_3d_blocks import (CrossAttnDownBlock3D, StepInputs, UNetMidBlock3DCrossAttn, get_down_block, get_up_block)
+
+
+class FrozenConfig(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+@dataclass
+class UNet3DConditionOutput:
+    sample: torch.Tensor
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]
+
+
+class Timesteps(nn.Module):
+    """Parameter-free sinusoidal projection (diffusers Timesteps); evaluated by mmgt_timestep_embedding."""
+
+    def __init__(self, num_channels, flip_sin_to_cos, downscale_freq_shift):
+        super().__init__()
+        self.num_channels, self.flip_sin_to_cos, self.downscale_freq_shift = num_channels, flip_sin_to_cos, downscale_freq_shift
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, in_channels, time_embed_dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_channels, time_embed_dim)
+        self.act = nn.SiLU()
+        self.linear_2 = nn.Linear(time_embed_dim, time_embed_dim)
+        self._pack = Pack()
+
+    def run(self, eng: Engine, t_emb):
+        w1, b1, w2, b2 = self._pack.get(
+            eng, [self.linear_1.weight, self.linear_1.bias, self.linear_2.weight, self.linear_2.bias],
+            lambda: (f32(self.linear_1.weight, eng), f32(self.linear_1.bias, eng), f32(self.linear_2.weight, eng),
+                     f32(self.linear_2.bias, eng)))
+        h = eng.silu_f32(eng.gemm(t_emb, w1, bias=b1, dtype=torch.float32))
+        return eng.gemm(h, w2, bias=b2, dtype=torch.float32)
+
+
+_INIT_DEFAULTS = dict(
+    sample_size=None, in_channels=4, out_channels=4, flip_sin_to_cos=True, freq_shift=0,
+    down_block_types=("CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "DownBlock3D"),
+    mid_block_type="UNetMidBlock3DCrossAttn",
+    up_block_types=("UpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D"),
+    only_cross_attention=False, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, downsample_padding=1,
+    mid_block_scale_factor=1, act_fn="silu", norm_num_groups=32, norm_eps=1e-5, cross_attention_dim=1280,
+    attention_head_dim=8, dual_cross_attention=False, use_linear_projection=False, class_embed_type=None,
+    num_class_embeds=None, upcast_attention=False, resnet_time_scale_shift="default", use_inflated_groupnorm=False,
+    task_type="action", mode=None, use_motion_module=False, motion_module_resolutions=(1, 2, 4, 8),
+    motion_module_mid_block=False, motion_module_decoder_only=False, motion_module_type=None, motion_module_kwargs={},
+    unet_use_cross_frame_attention=None, unet_use_temporal_attention=None, use_audio_module=False,
+    audio_attention_dim=768, stack_enable_blocks_name=None, stack_enable_blocks_depth=None)
+
+
+class UNet3DConditionModel(nn.Module):
+    """Same constructor keywords as the reference (unet_3d.py:37-90)."""
+
+    _supports_gradient_checkpointing = True
+    config_name = "config.json"
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        unknown = set(kwargs) - set(_INIT_DEFAULTS)
+        if unknown:
+            raise TypeError(f"unexpected arguments {sorted(unknown)}")
+        cfg = dict(_INIT_DEFAULTS)
+        cfg.update(kwargs)
+        self._internal_dict = FrozenConfig(cfg)
+        c = self._internal_dict
+        if c.dual_cross_attention or c.use_linear_projection or c.class_embed_type is not None \
+                or c.num_class_embeds is not None or c.resnet_time_scale_shift != "default" or c.mid_block_scale_factor != 1:
+            raise NotImplementedError("configuration outside the SD-1.5 / animation.yaml hot path")
+        if not c.use_inflated_groupnorm:
+            raise NotImplementedError("use_inflated_groupnorm=False (animation.yaml:48 sets it true)")
+        boc = list(c.block_out_channels)
+        self.sample_size = c.sample_size
+        time_embed_dim = boc[0] * 4
+        self.conv_in = InflatedConv3d(c.in_channels, boc[0], kernel_size=3, padding=(1, 1))
+        self.time_proj = Timesteps(boc[0], c.flip_sin_to_cos, c.freq_shift)
+        self.time_embedding = TimestepEmbedding(boc[0], time_embed_dim)
+        self.class_embedding = None
+        self.down_blocks = nn.ModuleList([])
+        self.mid_block = None          # plain attribute for now: keeps the reference's module order down->up->mid
+        self.up_blocks = nn.ModuleList([])
+        heads = c.attention_head_dim
+        heads = (heads,) * len(c.down_block_types) if isinstance(heads, int) else tuple(heads)
+
+        out_c = boc[0]
+        for i, btype in enumerate(c.down_block_types):
+            in_c, out_c = out_c, boc[i]
+            res = 2 ** i
+            self.down_blocks.append(get_down_block(
+                btype, num_layers=c.layers_per_block, in_channels=in_c, out_channels=out_c, temb_channels=time_embed_dim,
+                add_downsample=i != len(boc) - 1, resnet_eps=c.norm_eps, resnet_act_fn=c.act_fn,
+                resnet_groups=c.norm_num_groups, cross_attention_dim=c.cross_attention_dim,
+                attn_num_head_channels=heads[i], downsample_padding=c.downsample_padding,
+                use_motion_module=c.use_motion_module and (res in c.motion_module_resolutions)
+                and (not c.motion_module_decoder_only),
+                motion_module_type=c.motion_module_type, motion_module_kwargs=c.motion_module_kwargs,
+                use_audio_module=c.use_audio_module, audio_attention_dim=c.audio_attention_dim, depth=i,
+                stack_enable_blocks_name=c.stack_enable_blocks_name, stack_enable_blocks_depth=c.stack_enable_blocks_depth,
+                name_index=None if c.task_type == "action" else i))
+
+        if c.mid_block_type != "UNetMidBlock3DCrossAttn":
+            raise ValueError(f"unknown mid_block_type : {c.mid_block_type}")
+        self.mid_block = UNetMidBlock3DCrossAttn(
+            in_channels=boc[-1], temb_channels=time_embed_dim, resnet_eps=c.norm_eps, resnet_groups=c.norm_num_groups,
+            attn_num_head_channels=heads[-1], cross_attention_dim=c.cross_attention_dim,
+            use_motion_module=c.use_motion_module and c.motion_module_mid_block, motion_module_type=c.motion_module_type,
+            motion_module_kwargs=c.motion_module_kwargs, name=None if c.task_type == "action" else "MidBlock")
+
+        self.num_upsamplers = 0
+        rboc, rheads = list(reversed(boc)), list(reversed(heads))
+        out_c = rboc[0]
+        for i, btype in enumerate(c.up_block_types):
+            res = 2 ** (3 - i)
+            prev_c, out_c = out_c, rboc[i]
+            in_c = rboc[min(i + 1, len(boc) - 1)]
+            add_up = i != len(boc) - 1
+            self.num_upsamplers += int(add_up)
+            self.up_blocks.append(get_up_block(
+                btype, num_layers=c.layers_per_block + 1, in_channels=in_c, out_channels=out_c, prev_output_channel=prev_c,
+                temb_channels=time_embed_dim, add_upsample=add_up, resnet_eps=c.norm_eps, resnet_act_fn=c.act_fn,
+                resnet_groups=c.norm_num_groups, cross_attention_dim=c.cross_attention_dim,
+                attn_num_head_channels=rheads[i],
+                use_motion_module=c.use_motion_module and (res in c.motion_module_resolutions),
+                motion_module_type=c.motion_module_type, motion_module_kwargs=c.motion_module_kwargs,
+                name_index=None if c.task_type == "action" else i))
+
+        self.conv_norm_out = InflatedGroupNorm(num_channels=boc[0], num_groups=c.norm_num_groups, eps=c.norm_eps)
+        self.conv_act = nn.SiLU()
+        self.conv_out = InflatedConv3d(boc[0], c.out_channels, kernel_size=3, padding=1)
+        self.mode = c.mode
+        self.compute_dtype: Optional[torch.dtype] = None   # None => follow the parameter dtype
+        # None => the reference's accidental rule (fact 4): motion_scale reaches MM-HAA only when
+        # `self.training and gradient_checkpointing`; True/False force it.
+        self.apply_motion_scale: Optional[bool] = None
+        self._idx_cache = {}
+
+    # ------------------------------------------------------------------ diffusers-style plumbing
+    @property
+    def config(self):
+        return self._internal_dict
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            d = self.__dict__.get("_internal_dict")
+            if d is not None and name in d:
+                return d[name]
+            raise
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        cfg = {k: v for k, v in dict(config).items() if not k.startswith("_")}
+        cfg.update(kwargs)
+        model = cls(**{k: v for k, v in cfg.items() if k in _INIT_DEFAULTS})
+        extra = {k: v for k, v in cfg.items() if k not in _INIT_DEFAULTS}
+        extra.setdefault("center_input_sample", False)
+        model._internal_dict = FrozenConfig({**model._internal_dict, **extra})
+        return model
+
+    @classmethod
+    def load_config(cls, path):
+        with open(path) as f:
+            return json.load(f)
+
+    def _set_gradient_checkpointing(self, module, value=False):
+        if hasattr(module, "gradient_checkpointing"):
+            module.gradient_checkpointing = value
+
+    def enable_gradient_checkpointing(self):
+        for m in self.modules():
+            self._set_gradient_checkpointing(m, True)
+
+    def disable_gradient_checkpointing(self):
+        for m in self.modules():
+            self._set_gradient_checkpointing(m, False)
+
+    @property
+    def attn_processors(self):
+        return {}
+
+    def set_attn_processor(self, processor):
+        return None
+
+    def set_attention_slice(self, slice_size):
+        return None
+
+    def set_compute_dtype(self, dtype: Optional[torch.dtype]):
+        """Run the kernels in ``dtype`` (float32 / bfloat16) regardless of the parameter dtype."""
+        self.compute_dtype = dtype
+        return self
+
+    @classmethod
+    def from_pretrained_2d(cls, pretrained_model_path, motion_module_path, subfolder=None, unet_additional_kwargs=None,
+                           mm_zero_proj_out=False):
+        """Same contract as unet_3d.py:627-718: SD-1.5 2-D weights + motion-module checkpoint, strict=False."""
+        pretrained_model_path = Path(pretrained_model_path)
+        motion_module_path = Path(motion_module_path)
+        if subfolder is not None:
+            pretrained_model_path = pretrained_model_path.joinpath(subfolder)
+        config_file = pretrained_model_path / "config.json"
+        if not (config_file.exists() and config_file.is_file()):
+            raise RuntimeError(f"{config_file} does not exist or is not a file")
+        unet_config = cls.load_config(config_file)
+        unet_config["down_block_types"] = ["CrossAttnDownBlock3D"] * 3 + ["DownBlock3D"]
+        unet_config["up_block_types"] = ["UpBlock3D"] + ["CrossAttnUpBlock3D"] * 3
+        unet_config["mid_block_type"] = "UNetMidBlock3DCrossAttn"
+        model = cls.from_config(unet_config, **(unet_additional_kwargs or {}))
+        st_file = pretrained_model_path / "diffusion_pytorch_model.safetensors"
+        bin_file = pretrained_model_path / "diffusion_pytorch_model.bin"
+        if st_file.exists():
+            from safetensors.torch import load_file
+            state_dict = load_file(str(st_file), device="cpu")
+        elif bin_file.exists():
+            state_dict = torch.load(bin_file, map_location="cpu", weights_only=True)
+        else:
+            raise FileNotFoundError(f"no weights file found in {pretrained_model_path}")
+        if motion_module_path.exists() and motion_module_path.is_file():
+            if motion_module_path.suffix.lower() in (".pth", ".pt", ".ckpt"):
+                motion_sd = torch.load(motion_module_path, map_location="cpu", weights_only=True)
+            elif motion_module_path.suffix.lower() == ".safetensors":
+                from safetensors.torch import load_file
+                motion_sd = load_file(str(motion_module_path), device="cpu")
+            else:
+                raise RuntimeError(f"unknown file format for motion module weights: {motion_module_path.suffix}")
+            if mm_zero_proj_out:
+                motion_sd = {k: v for k, v in motion_sd.items() if "proj_out" not in k}
+            state_dict.update(motion_sd)
+        model.load_state_dict(state_dict, strict=False)
+        return model
+
+    # ------------------------------------------------------------------ helpers
+    def _engine(self, device) -> Engine:
+        dt = self.compute_dtype or self.dtype
+        if dt == torch.float16:
+            dt = torch.bfloat16
+        return get_engine(device, dt)
+
+    def spatial_blocks(self):
+        """The 16 spatial transformer blocks in module order (what torch_dfs + isinstance finds)."""
+        from .attention import TemporalBasicTransformerBlock
+        return [m for m in self.modules() if isinstance(m, TemporalBasicTransformerBlock)]
+
+    def _seg2_index(self, eng, B, F, ref_index):
+        key = (str(eng.device), B, F, tuple(-1 if r is None else int(r) for r in ref_index))
+        if key not in self._idx_cache:
+            idx = torch.tensor([v for v in key[3] for _ in range(F)], dtype=torch.int32, device=eng.device)
+            self._idx_cache[key] = idx
+        return self._idx_cache[key]
+
+    def _motion_scale_reaches_audio(self) -> bool:
+        if self.apply_motion_scale is not None:
+            return bool(self.apply_motion_scale)
+        blk = next((b for b in self.down_blocks if isinstance(b, CrossAttnDownBlock3D)), None)
+        return bool(self.training and blk is not None and blk.gradient_checkpointing)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, sample, timestep, encoder_hidden_states, audio_embedding=None, class_labels=None,
+                mask_cond_fea=None, pose_cond_fea=None, attention_mask=None, full_mask=None, face_mask=None,
+                body_mask=None, motion_scale=None, down_block_additional_residuals=None,
+                mid_block_additional_residual=None, return_dict: bool = True, ref_index: Optional[Sequence] = None):
+        """Reference signature (unet_3d.py:425-443) plus ``ref_index``: per batch sample, the row of the
+        reference bank its frames attend to, or None for plain self-attention.  Default = what
+        ReferenceAttentionControl configured (CFG: first half None, second half its own row)."""
+        if attention_mask is not None or down_block_additional_residuals is not None \
+                or mid_block_additional_residual is not None or class_labels is not None:
+            raise NotImplementedError("attention_mask / additional residuals / class labels are not on the hot path")
+        if sample.dim() != 5:
+            raise ValueError(f"Expected sample to have ndim=5, but got ndim={sample.dim()}")
+        B, Cin, F, H, W = sample.shape
+        eng = self._engine(sample.device)
+        if self.config.get("center_input_sample", False):
+            sample = 2 * sample - 1.0
+        x = eng.ncfhw_to_tokens(sample)
+        pose = eng.ncfhw_to_tokens(pose_cond_fea) if pose_cond_fea is not None else None
+        out = self.forward_tokens(eng, x, timestep, encoder_hidden_states, audio_embedding, pose, full_mask, face_mask,
+                                  body_mask, motion_scale, B, F, ref_index)
+        res = eng.tokens_to_ncfhw(out, B, F, sample.dtype if sample.dtype in (torch.float32, torch.bfloat16) else torch.float32)
+        if res.dtype != sample.dtype:
+            res = res.to(sample.dtype)
+        if not return_dict:
+            return (res,)
+        return UNet3DConditionOutput(sample=res)
+
+    def forward_tokens(self, eng: Engine, x, timestep, encoder_hidden_states, audio_embedding, pose, full_mask, face_mask,
+                       body_mask, motion_scale, B: int, F: int, ref_index=None):
+        """Channels-last core: x (N,H,W,4), pose (N,H,W,320) or None -> (N,H,W,4) in the run dtype."""
+        N, H, W, _ = x.shape
+        dev = eng.device
+        # --- time embedding (unet_3d.py:481-502), float32 end to end
+        if torch.is_tensor(timestep):
+            t = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
+        else:
+            t = torch.tensor([float(timestep)], device=dev, dtype=torch.float32)
+        if t.numel() == 1:
+            t = t.expand(B).contiguous()
+        tp = self.time_proj
+        emb = self.time_embedding.run(eng, eng.timestep_embedding(t, tp.num_channels, tp.flip_sin_to_cos,
+                                                                  tp.downscale_freq_shift))
+        temb_silu = eng.silu_f32(emb)
+        # --- conditioning
+        if ref_index is None:
+            ctl = getattr(self, "_reference_control", None)
+            if ctl is not None and ctl.get("do_classifier_free_guidance", False):
+                ref_index = [None] * (B // 2) + list(range(B // 2, B))
+            else:
+                ref_index = list(range(B))
+        have_bank = any(len(b.bank) > 0 for b in self.spatial_blocks())
+        if have_bank:
+            nb = next(b.bank[0].shape[0] for b in self.spatial_blocks() if b.bank)
+            ref_index = [None if r is None else min(int(r), nb - 1) for r in ref_index]
+        seg2 = self._seg2_index(eng, B, F, ref_index) if have_bank else None
+        clip = encoder_hidden_states.to(dev)
+        if clip.shape[0] != B:
+            raise ValueError("encoder_hidden_states batch must match sample batch")
+        audio_rows, masks = None, None
+        if self.config.use_audio_module:
+            if audio_embedding is None or full_mask is None or face_mask is None or body_mask is None:
+                raise ValueError("use_audio_module=True needs audio_embedding and the full/face/body masks")
+            audio_rows = audio_embedding.to(device=dev, dtype=eng.dtype).reshape(N * audio_embedding.shape[2], -1).contiguous()
+            masks = []
+            for lvl in range(len(full_mask)):
+                masks.append(tuple(m[lvl].to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+                                   for m in (full_mask, face_mask, body_mask)))
+        scale = tuple(float(s) for s in motion_scale) if motion_scale is not None else (1.0, 1.0, 1.0)
+        si = StepInputs(frames=F, temb_silu=temb_silu, clip=clip, seg2_index=seg2, audio_rows=audio_rows, masks=masks,
+                        scale=scale)
+        reaches = self._motion_scale_reaches_audio()
+
+        # --- pre-process: conv_in (+ pose features fused as the residual) (unet_3d.py:517-519)
+        x = self.conv_in.run(eng, x, residual=pose)
+        skips = [x]
+        for blk in self.down_blocks:
+            if isinstance(blk, CrossAttnDownBlock3D):
+                x, outs = blk.run(eng, x, si, reaches)
+            else:
+                x, outs = blk.run(eng, x, si)
+            skips += outs
+        x = self.mid_block.run(eng, x, si)
+        for blk in self.up_blocks:
+            x = blk.run(eng, x, skips, si)
+        x = self.conv_norm_out.run(eng, x, None, silu=True)
+        return self.conv_out.run(eng, x)

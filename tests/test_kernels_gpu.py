@@ -1,0 +1,297 @@
+"""GPU: every C-ABI operator against the oracle primitives (plain torch fp32 / numpy integer code) on the
+same seeded inputs.  Integer work (mask pyramid, gathers) must be bit-exact; float32 kernels 1e-5-ish;
+bf16 kernels are compared against the float32 result computed from the same bf16-rounded inputs."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from helpers import rel_l2  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device("cuda", 0)
+
+
+def eng_for(dev, dtype):
+    from mmgt_b200.kernels import get_engine
+    return get_engine(dev, dtype)
+
+
+def rnd(*shape, dev, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(device=dev, dtype=dtype)
+
+
+TOL = {torch.float32: 2e-5, torch.bfloat16: 1.2e-2}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layout_roundtrip_and_add(dev, dtype):
+    eng = eng_for(dev, dtype)
+    x = rnd(2, 5, 3, 6, 7, dev=dev, seed=1)
+    a = rnd(2, 5, 3, 6, 7, dev=dev, seed=2)
+    tok = eng.ncfhw_to_tokens(x, add=a)
+    ref = (x + a).permute(0, 2, 3, 4, 1).reshape(6, 6, 7, 5)
+    assert rel_l2(tok.float(), ref) < TOL[dtype]
+    back = eng.tokens_to_ncfhw(tok, 2, 3, torch.float32)
+    assert torch.equal(back, tok.float().reshape(2, 3, 6, 7, 5).permute(0, 4, 1, 2, 3))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 16, 64, 0), (2, 64, 320, 0), (2, 16, 1280, 640), (4, 256, 128, 64), (2, 9, 1280, 1280)])
+def test_groupnorm_with_virtual_concat_and_silu(dev, dtype, shape):
+    N, T, C1, C2 = shape
+    eng = eng_for(dev, dtype)
+    x1 = rnd(N, T, C1, dev=dev, dtype=dtype, seed=3) * 2 + 0.5
+    x2 = rnd(N, T, C2, dev=dev, dtype=dtype, seed=4) if C2 else None
+    C = C1 + C2
+    g, b = rnd(C, dev=dev, seed=5) * 0.1 + 1, rnd(C, dev=dev, seed=6) * 0.1
+    for silu, eps in ((True, 1e-5), (False, 1e-6)):
+        y = eng.groupnorm(x1, x2, g, b, 32, eps, silu)
+        cat = torch.cat([x1, x2], -1) if C2 else x1
+        ref = F.group_norm(cat.float().permute(0, 2, 1), 32, g, b, eps).permute(0, 2, 1)
+        ref = F.silu(ref) if silu else ref
+        assert y.shape == (N, T, C)
+        assert rel_l2(y.float(), ref) < (2e-5 if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C", [64, 320, 640, 1280])
+def test_layernorm_and_positional_encoding(dev, dtype, C):
+    eng = eng_for(dev, dtype)
+    Fr, T = 3, 5
+    x = rnd(2 * Fr * T, C, dev=dev, dtype=dtype, seed=7) * 3 + 1
+    g, b = rnd(C, dev=dev, seed=8) * 0.1 + 1, rnd(C, dev=dev, seed=9) * 0.1
+    pe = rnd(32, C, dev=dev, seed=10)
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
+    assert rel_l2(eng.layernorm(x, g, b).float(), ref) < (2e-6 if dtype == torch.float32 else 5e-3)
+    frame = (torch.arange(2 * Fr * T, device=dev) // T) % Fr
+    assert rel_l2(eng.layernorm(x, g, b, pe=pe, T=T, F=Fr).float(), ref + pe[frame]) < (2e-6 if dtype == torch.float32 else 5e-3)
+
+
+def _gemm_ref(A, W, bias, rowscale, rowbias, rpg, residual, alpha, geglu):
+    acc = A.float() @ W.float().t()
+    if bias is not None:
+        acc = acc + bias
+    if geglu:
+        n = acc.shape[1] // 2
+        acc = acc[:, :n] * F.gelu(acc[:, n:])
+    if rowscale is not None:
+        acc = acc * rowscale[:, None]
+    acc = acc * alpha
+    if rowbias is not None:
+        acc = acc + rowbias[torch.arange(A.shape[0], device=A.device) // rpg]
+    if residual is not None:
+        acc = acc + residual.float()
+    return acc
+
+
+GEMM_SHAPES = [(2, 1280, 320), (257, 320, 320), (1000, 960, 320), (384, 64, 2880), (130, 160, 72), (96, 4, 64),
+               (300, 640, 1280), (128, 256, 64), (513, 192, 64), (64, 1920, 768)]
+
+
+@pytest.mark.parametrize("dtype,tc", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)],
+                         ids=["f32", "bf16simt", "bf16tc"])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_full_epilogue(dev, dtype, tc, M, N, K):
+    eng = eng_for(dev, dtype)
+    eng.ctx.set_tensor_cores(tc)
+    try:
+        A = rnd(M, K, dev=dev, dtype=dtype, seed=11)
+        W = rnd(N, K, dev=dev, dtype=dtype, seed=12, scale=K ** -0.5)
+        bias, rs = rnd(N, dev=dev, seed=13), rnd(M, dev=dev, seed=14).abs() + 0.5
+        rpg = 37
+        rb = rnd((M + rpg - 1) // rpg, N, dev=dev, seed=15)
+        res = rnd(M, N, dev=dev, dtype=dtype, seed=16)
+        tol = 1e-5 if dtype == torch.float32 else 8e-3
+        assert rel_l2(eng.gemm(A, W).float(), _gemm_ref(A, W, None, None, None, 1, None, 1.0, False)) < tol
+        out = eng.gemm(A, W, bias=bias, rowscale=rs, rowbias=rb, rows_per_group=rpg, residual=res, alpha=0.7)
+        assert rel_l2(out.float(), _gemm_ref(A, W, bias, rs, rb, rpg, res, 0.7, False)) < tol
+        # in-place accumulate (residual aliases the output), as the split-K shortcut / MM-HAA sum use it
+        acc = res.clone()
+        eng.gemm(A, W, bias=bias, residual=acc, out=acc, alpha=2.0)
+        assert rel_l2(acc.float(), _gemm_ref(A, W, bias, None, None, 1, res, 2.0, False)) < tol
+    finally:
+        eng.ctx.set_tensor_cores(True)
+
+
+@pytest.mark.parametrize("dtype,tc", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)],
+                         ids=["f32", "bf16simt", "bf16tc"])
+@pytest.mark.parametrize("M,C", [(300, 64), (1000, 320), (257, 640)])
+def test_gemm_geglu(dev, dtype, tc, M, C):
+    from mmgt_b200.packing import geglu_interleave
+    eng = eng_for(dev, dtype)
+    eng.ctx.set_tensor_cores(tc)
+    try:
+        A = rnd(M, C, dev=dev, dtype=dtype, seed=21)
+        W = rnd(8 * C, C, dev=dev, dtype=dtype, seed=22, scale=C ** -0.5)
+        bias = rnd(8 * C, dev=dev, seed=23)
+        gb = eng.geglu_block(8 * C)
+        Wi, bi = geglu_interleave(W, bias, gb)
+        out = eng.gemm(A, Wi.contiguous(), bias=bi.contiguous(), geglu_block=gb)
+        assert out.shape == (M, 4 * C)
+        assert rel_l2(out.float(), _gemm_ref(A, W, bias, None, None, 1, None, 1.0, True)) < (1e-5 if dtype == torch.float32 else 8e-3)
+    finally:
+        eng.ctx.set_tensor_cores(True)
+
+
+def test_gemm_strided_views_and_f32_vectors(dev):
+    eng = eng_for(dev, torch.bfloat16)
+    buf = rnd(500, 960, dev=dev, dtype=torch.bfloat16, seed=31)
+    W = rnd(320, 320, dev=dev, dtype=torch.bfloat16, seed=32, scale=0.05)
+    out = eng.gemm(buf[:, 320:640], W)                       # strided A (lda = 960)
+    assert rel_l2(out.float(), buf[:, 320:640].float() @ W.float().t()) < 8e-3
+    Wbig = rnd(640, 960, dev=dev, dtype=torch.bfloat16, seed=33, scale=0.03)
+    out2 = eng.gemm(buf[:, :320].contiguous(), Wbig[:, 640:])  # strided W (ldw = 960): split-K shortcut
+    assert rel_l2(out2.float(), buf[:, :320].float() @ Wbig[:, 640:].float().t()) < 8e-3
+    v = rnd(2, 1280, dev=dev, seed=34)
+    Wf = rnd(320, 1280, dev=dev, seed=35, scale=0.03)
+    o = eng.gemm(v, Wf, bias=rnd(320, dev=dev, seed=36), dtype=torch.float32)
+    assert o.dtype == torch.float32 and rel_l2(o, v @ Wf.t() + rnd(320, dev=dev, seed=36)) < 1e-5
+
+
+CONV_CASES = [  # N, H, W, Cin, Cout, stride, upsample
+    (3, 16, 16, 64, 64, 1, 0), (2, 8, 8, 128, 256, 1, 0), (5, 4, 4, 256, 256, 1, 0), (2, 32, 32, 64, 128, 1, 0),
+    (2, 64, 64, 64, 64, 1, 0), (3, 2, 2, 256, 256, 1, 0), (2, 16, 16, 64, 64, 2, 0), (2, 8, 8, 128, 128, 1, 1),
+    (2, 16, 16, 4, 64, 1, 0), (2, 16, 16, 64, 4, 1, 0), (3, 16, 16, 320, 320, 1, 0), (2, 8, 8, 1920, 640, 1, 0)]
+
+
+@pytest.mark.parametrize("dtype,tc", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)],
+                         ids=["f32", "bf16simt", "bf16tc"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3x3_fused_epilogue(dev, dtype, tc, case):
+    N, H, W, Cin, Cout, stride, up = case
+    eng = eng_for(dev, dtype)
+    eng.ctx.set_tensor_cores(tc)
+    try:
+        x = rnd(N, H, W, Cin, dev=dev, dtype=dtype, seed=41)
+        w = rnd(Cout, Cin, 3, 3, dev=dev, dtype=dtype, seed=42, scale=(9 * Cin) ** -0.5)
+        bias = rnd(Cout, dev=dev, seed=43)
+        fpg = 1 if N % 2 else 2
+        rb = rnd(N // fpg, Cout, dev=dev, seed=44)
+        xin = x.float().permute(0, 3, 1, 2)
+        if up:
+            xin = F.interpolate(xin, scale_factor=2.0, mode="nearest")
+        ref = F.conv2d(xin, w.float(), bias, stride=stride, padding=1)
+        ref = ref + rb.repeat_interleave(fpg, 0)[:, :, None, None]
+        res = rnd(*ref.permute(0, 2, 3, 1).shape, dev=dev, dtype=dtype, seed=45)
+        ref = ref.permute(0, 2, 3, 1) + res.float()
+        out = eng.conv3x3(x, w.permute(0, 2, 3, 1).contiguous(), bias=bias, rowbias=rb, frames_per_group=fpg, residual=res,
+                          stride=stride, upsample2x=bool(up))
+        assert out.shape == ref.shape
+        assert rel_l2(out.float(), ref) < (1e-5 if dtype == torch.float32 else 8e-3)
+    finally:
+        eng.ctx.set_tensor_cores(True)
+
+
+def _attn_ref(q, k, v, heads):
+    n, lq, c = q.shape
+    d = c // heads
+    qh, kh, vh = (t.float().view(n, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    s = (qh @ kh.transpose(-1, -2)) * d ** -0.5
+    return (s.softmax(-1) @ vh).transpose(1, 2).reshape(n, lq, c)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,Lq,Lk,Lk2,heads,d", [(4, 64, 64, 64, 8, 40), (3, 100, 100, 100, 8, 8), (2, 256, 256, 0, 8, 80),
+                                                 (2, 70, 32, 0, 8, 40), (2, 64, 64, 64, 8, 160), (6, 16, 16, 16, 8, 32)])
+def test_attention_two_segments(dev, dtype, N, Lq, Lk, Lk2, heads, d):
+    eng = eng_for(dev, dtype)
+    C = heads * d
+    qkv = rnd(N, Lq if Lq == Lk else max(Lq, Lk), 3 * C, dev=dev, dtype=dtype, seed=51)
+    q, k, v = qkv[:, :Lq, :C], qkv[:, :Lk, C:2 * C], qkv[:, :Lk, 2 * C:]
+    if Lk2:
+        bank = rnd(2, Lk2, 2 * C, dev=dev, dtype=dtype, seed=52)
+        k2, v2 = bank[:, :, :C], bank[:, :, C:]
+        idx = torch.tensor([(-1 if i % 3 == 0 else i % 2) for i in range(N)], dtype=torch.int32, device=dev)
+        out = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
+        refs = []
+        for n in range(N):
+            kk, vv = k[n:n + 1], v[n:n + 1]
+            if idx[n] >= 0:
+                kk = torch.cat([kk, k2[idx[n]:idx[n] + 1]], 1)
+                vv = torch.cat([vv, v2[idx[n]:idx[n] + 1]], 1)
+            refs.append(_attn_ref(q[n:n + 1], kk, vv, heads))
+        ref = torch.cat(refs)
+    else:
+        out = eng.attention(q, k, v, heads)
+        ref = _attn_ref(q, k, v, heads)
+    assert rel_l2(out.float(), ref) < (2e-5 if dtype == torch.float32 else 8e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,Fr,T,heads,d", [(2, 12, 16, 8, 40), (1, 8, 64, 8, 8), (2, 4, 9, 8, 160), (1, 32, 4, 8, 80)])
+def test_temporal_attention(dev, dtype, B, Fr, T, heads, d):
+    eng = eng_for(dev, dtype)
+    C = heads * d
+    qkv = rnd(B * Fr * T, 3 * C, dev=dev, dtype=dtype, seed=61)
+    out = eng.temporal_attention(qkv, B, Fr, T, heads)
+    x = qkv.float().view(B, Fr, T, 3 * C).permute(0, 2, 1, 3).reshape(B * T, Fr, 3 * C)   # (b d) f c
+    ref = _attn_ref(x[:, :, :C], x[:, :, C:2 * C], x[:, :, 2 * C:], heads)
+    ref = ref.view(B, T, Fr, C).permute(0, 2, 1, 3).reshape(B * Fr * T, C)
+    assert rel_l2(out.float(), ref) < (2e-5 if dtype == torch.float32 else 8e-3)
+
+
+def test_mask_pyramid_bit_exact(dev):
+    from mmgt_b200.image_processor import MaskPyramid
+    from oracle.mask_pyramid import full_mask_from_lips, mask_pyramid_u8, preprocess_mov_mask
+    from oracle.synthetic import synthetic_masks_u8
+    face, lips = synthetic_masks_u8(7)
+    noise = np.random.default_rng(5).integers(0, 256, (3, 64, 64), dtype=np.uint8)
+    for image_size in (512, 256, 768):
+        mp = MaskPyramid(image_size, dev)
+        f_gpu, l_gpu = mp.preprocess_mov_mask(list(face), list(lips))
+        f_ref, l_ref = preprocess_mov_mask(face, lips, image_size)
+        full_gpu, full_ref = mp.full_mask_from_lips(list(lips)), full_mask_from_lips(l_ref)
+        for k in range(4):
+            assert torch.equal(f_gpu[k].cpu(), torch.from_numpy(f_ref[k])), (image_size, k)
+            assert torch.equal(l_gpu[k].cpu(), torch.from_numpy(l_ref[k])), (image_size, k)
+            assert torch.equal(full_gpu[k].cpu(), torch.from_numpy(full_ref[k])), (image_size, k)
+    eng = eng_for(dev, torch.float32)
+    for s, ref in zip((64, 32, 16, 8), mask_pyramid_u8(noise, 512)):
+        _, u8 = eng.mask_resize(torch.from_numpy(noise).to(dev), s, want_u8=True)
+        assert torch.equal(u8.cpu(), torch.from_numpy(ref))
+
+
+def test_small_pieces(dev):
+    eng = eng_for(dev, torch.float32)
+    t = torch.tensor([500.0, 999.0, 32.0], device=dev)
+    emb = eng.timestep_embedding(t, 320, True, 0.0)
+    half = 160
+    freq = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=dev) / half)
+    arg = t[:, None] * freq[None]
+    assert torch.allclose(emb, torch.cat([arg.cos(), arg.sin()], -1), atol=2e-4)
+    x = rnd(3, 1280, dev=dev, seed=71)
+    assert torch.allclose(eng.silu_f32(x), F.silu(x), atol=1e-6)
+    src = rnd(10, 24, dev=dev, seed=72)
+    idx = torch.tensor([9, 0, 3, 3, 7], dtype=torch.int32, device=dev)
+    assert torch.equal(eng.gather_rows(src, idx), src[idx.long()])
+    up = rnd(2, 3, 5, 8, dev=dev, seed=73)
+    ref = F.interpolate(up.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(eng.upsample_nearest2x(up), ref)
+    # window accumulate + CFG / DDIM update
+    L, Fw = 9, 4
+    acc = torch.zeros(2, 4, L, 3, 3, device=dev)
+    pred = rnd(1, 4, Fw, 3, 3, dev=dev, seed=74)
+    frames = torch.tensor([7, 8, 0, 1], dtype=torch.int32, device=dev)
+    eng.window_accumulate(acc, pred, frames, 1)
+    eng.window_accumulate(acc, pred, frames, 1)
+    ref_acc = torch.zeros_like(acc)
+    ref_acc[1, :, frames.long()] = 2 * pred[0]
+    assert torch.allclose(acc, ref_acc)
+    lat = rnd(1, 4, L, 3, 3, dev=dev, seed=75)
+    noise = rnd(2, 4, L, 3, 3, dev=dev, seed=76)
+    inv = 1.0 / torch.tensor([1, 2, 1, 1, 2, 2, 1, 1, 2], dtype=torch.float32, device=dev)
+    u, c = (noise * inv.view(1, 1, L, 1, 1)).chunk(2)
+    want = 0.9 * lat + (-0.3) * (u + 3.5 * (c - u))
+    eng.cfg_ddim_step(lat, noise, inv, True, 3.5, 0.9, -0.3)
+    assert torch.allclose(lat, want, atol=1e-5)

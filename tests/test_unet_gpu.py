@@ -1,0 +1,150 @@
+"""GPU parity of the whole hot path, called through the reference-shaped host API -> C ABI.
+
+Tolerances are the ones BASELINE.json's north_star states: rel-L2 <= 1e-4 in float32 mode, <= 1e-2 in bf16,
+against (a) the golden outputs of the reference's own modules and (b) the oracle on fresh seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import (FULL, GOLD, TINY, attach_banks, build_cuda_unet, rel_l2, run_cuda_unet, synthetic_state_dict,  # noqa: E402
+                     to_dev)
+from oracle.sampler import DDIM, denoise_step, uniform_windows  # noqa: E402
+from oracle.synthetic import make_banks, make_inputs, window_inputs  # noqa: E402
+from oracle.unet3d import UNetSpec, unet3d_forward  # noqa: E402
+
+TOL_F32, TOL_BF16 = 1e-4, 1e-2
+
+
+def _golden(tag):
+    return np.load(os.path.join(GOLD, f"unet_{tag}.npz"))
+
+
+def _setup(tag, boc, compute_dtype, sd=None):
+    g = _golden(tag)
+    latent, frames, t = int(g["latent"]), int(g["frames"]), int(g["timestep"])
+    spec = UNetSpec(block_out_channels=tuple(boc))
+    sd = sd if sd is not None else synthetic_state_dict("tiny" if tag == "tiny" else "full")
+    unet = build_cuda_unet(boc, sd, compute_dtype=compute_dtype)
+    inp = make_inputs(spec, frames, latent)
+    banks = make_banks(spec, latent)
+    win = window_inputs(inp, list(range(frames)))
+    return g, spec, sd, unet, banks, win, frames, t
+
+
+@pytest.mark.parametrize("compute_dtype,tc,tol", [(torch.float32, False, TOL_F32), (torch.bfloat16, False, TOL_BF16),
+                                                   (torch.bfloat16, True, TOL_BF16)], ids=["f32", "bf16simt", "bf16tc"])
+def test_tiny_unet_matches_reference_golden(compute_dtype, tc, tol):
+    g, spec, sd, unet, banks, win, frames, t = _setup("tiny", TINY, compute_dtype)
+    unet._engine(torch.device("cuda", 0)).ctx.set_tensor_cores(tc)
+    try:
+        attach_banks(unet, spec, banks, cfg=True)
+        # scripts' branch: train mode + gradient checkpointing => motion_scale reaches MM-HAA (fact 4)
+        unet.train()
+        unet.enable_gradient_checkpointing()
+        out = run_cuda_unet(unet, win, t)
+        assert out.shape == tuple(g["out_scripts"].shape)
+        e_scripts = rel_l2(out, torch.from_numpy(g["out_scripts"]))
+        unet.eval()
+        e_eval = rel_l2(run_cuda_unet(unet, win, t), torch.from_numpy(g["out_eval"]))
+        # no-CFG reader: every frame attends to [self ; bank row 0]
+        ctl = attach_banks(unet, spec, banks, cfg=False)
+        unet.train()
+        w1 = {k: (v[1:2] if torch.is_tensor(v) and v.shape[0] == 2 else v) for k, v in win.items()}
+        for k in ("full_mask", "face_mask", "body_mask"):
+            w1[k] = [m[frames:] for m in win[k]]
+        e_nocfg = rel_l2(run_cuda_unet(unet, w1, t), torch.from_numpy(g["out_nocfg"]))
+        print(f"tiny {compute_dtype} tc={tc}: scripts {e_scripts:.3e} eval {e_eval:.3e} nocfg {e_nocfg:.3e}")
+        assert e_scripts < tol and e_eval < tol and e_nocfg < tol
+        ctl.clear()
+    finally:
+        unet._engine(torch.device("cuda", 0)).ctx.set_tensor_cores(True)
+
+
+def test_tiny_unet_float32_vs_oracle_fresh_seed_and_ragged_window():
+    """Oracle on the CPU vs CUDA on a different seed, 5 frames (ragged vs the 4-frame golden), timestep 999."""
+    spec = UNetSpec(block_out_channels=TINY)
+    sd = synthetic_state_dict("tiny", seed=3)
+    unet = build_cuda_unet(TINY, sd, compute_dtype=torch.float32)
+    unet.train()
+    unet.enable_gradient_checkpointing()
+    inp = make_inputs(spec, 7, 16, seed=99)
+    banks = make_banks(spec, 16, seed=5)
+    attach_banks(unet, spec, banks, cfg=True)
+    win = window_inputs(inp, [6, 0, 1, 2, 3])       # wrapped window, like the closed-loop scheduler produces
+    with torch.no_grad():
+        ref = unet3d_forward(sd, spec, win["sample"], 999, win["encoder_hidden_states"], win["audio_embedding"],
+                             win["pose_cond_fea"], win["full_mask"], win["face_mask"], win["body_mask"], win["motion_scale"],
+                             banks, ref_index=[None, 1], apply_motion_scale=True)
+    out = run_cuda_unet(unet, win, 999)
+    assert rel_l2(out, ref) < TOL_F32
+    # the B=1 CFG-split forwards used by the multi-GPU loop must reproduce the two halves of the B=2 forward
+    w = to_dev(win, "cuda")
+    halves = []
+    for b, ref_idx in ((0, [None]), (1, [1])):
+        sl = slice(b, b + 1)
+        Fr = win["sample"].shape[2]
+        halves.append(unet(w["sample"][sl], torch.tensor(999), encoder_hidden_states=w["encoder_hidden_states"][sl],
+                           audio_embedding=w["audio_embedding"][sl], pose_cond_fea=w["pose_cond_fea"][sl],
+                           full_mask=[m[b * Fr:(b + 1) * Fr] for m in w["full_mask"]],
+                           face_mask=[m[b * Fr:(b + 1) * Fr] for m in w["face_mask"]],
+                           body_mask=[m[b * Fr:(b + 1) * Fr] for m in w["body_mask"]], motion_scale=w["motion_scale"],
+                           return_dict=False, ref_index=ref_idx)[0])
+    assert rel_l2(torch.cat(halves), out) < 1e-5
+
+
+@pytest.mark.parametrize("compute_dtype,tol", [(torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)], ids=["f32", "bf16tc"])
+def test_full_width_unet_config1_matches_reference_golden(compute_dtype, tol):
+    """BASELINE config 1: 256x256 (32x32 latent), 8 frames, CFG, full-width weights (1.4 G parameters)."""
+    g, spec, sd, unet, banks, win, frames, t = _setup("full_cfg1", FULL, compute_dtype)
+    attach_banks(unet, spec, banks, cfg=True)
+    unet.train()
+    unet.enable_gradient_checkpointing()
+    out = run_cuda_unet(unet, win, t)
+    err = rel_l2(out, torch.from_numpy(g["out_scripts"]))
+    print(f"full cfg1 {compute_dtype}: rel-L2 {err:.3e}")
+    assert err < tol
+    del unet
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("compute_dtype,tol", [(torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)], ids=["f32", "bf16tc"])
+def test_denoise_step_matches_oracle(compute_dtype, tol):
+    """One full DDIM step (3 overlapping windows, CFG combine, overlap average, DDIM update) on 20 frames."""
+    from mmgt_b200.pipeline_pose2vid_long import DenoiseLoop
+    from mmgt_b200.scheduling_ddim import DDIMSchedule
+    spec = UNetSpec(block_out_channels=TINY)
+    sd = synthetic_state_dict("tiny")
+    unet = build_cuda_unet(TINY, sd, compute_dtype=compute_dtype)
+    unet.train()
+    unet.enable_gradient_checkpointing()
+    L, latent, n_steps = 20, 16, 30
+    inp = make_inputs(spec, L, latent, seed=11)
+    banks = make_banks(spec, latent)
+    attach_banks(unet, spec, banks, cfg=True)
+    windows = uniform_windows(0, L)
+    assert len(windows) == 3
+
+    def unet_fn(sample, t, ehs, aud, pose, full, face, lip, ms):
+        with torch.no_grad():
+            return unet3d_forward(sd, spec, sample, t, ehs, aud, pose, full, face, lip, ms, banks, ref_index=[None, 1],
+                                  apply_motion_scale=True)
+    ddim = DDIM()
+    lat_ref = inp["latents"].clone()
+    for t in ddim.timesteps(n_steps)[:2]:
+        lat_ref, v_ref = denoise_step(unet_fn, lat_ref, t, n_steps, ddim, 3.5, windows, inp["pose_fea"], inp["audio"],
+                                      inp["full_mask"], inp["face_mask"], inp["lip_mask"], inp["encoder_hidden_states"],
+                                      inp["motion_scale"])
+    d = to_dev(inp, "cuda")
+    loop = DenoiseLoop(unet, DDIMSchedule.from_config(), n_steps, 3.5, motion_scale=inp["motion_scale"])
+    loop.prepare(d["latents"], d["pose_fea"], d["audio"], d["full_mask"], d["face_mask"], d["lip_mask"],
+                 d["encoder_hidden_states"])
+    assert loop.windows == windows
+    loop.step(0)
+    lat = loop.step(1)
+    err = rel_l2(lat, lat_ref)
+    print(f"denoise 2 steps {compute_dtype}: latents rel-L2 {err:.3e}")
+    assert err < tol
