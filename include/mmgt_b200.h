@@ -137,6 +137,7 @@ typedef struct {
   int64_t ldq, ldk, ldv, ldk2, ldv2, ldo;
   int64_t kv_batch_stride; /* elements between consecutive frames of k/v (0 = Lk*ldk) */
   int N, Lq, Lk, Lk2, heads, d;
+  int B2;         /* rows (batch) of k2 / v2 */
   float scale;    /* d^-0.5 */
   int dtype;
 } mmgt_attention_params;

@@ -34,7 +34,7 @@ class AttentionParams(C.Structure):
                 ("seg2_index", c_void_p), ("out", c_void_p),
                 ("ldq", c_int64), ("ldk", c_int64), ("ldv", c_int64), ("ldk2", c_int64), ("ldv2", c_int64),
                 ("ldo", c_int64), ("kv_batch_stride", c_int64),
-                ("N", c_int), ("Lq", c_int), ("Lk", c_int), ("Lk2", c_int), ("heads", c_int), ("d", c_int),
+                ("N", c_int), ("Lq", c_int), ("Lk", c_int), ("Lk2", c_int), ("heads", c_int), ("d", c_int), ("B2", c_int),
                 ("scale", c_float), ("dtype", c_int)]
 
 

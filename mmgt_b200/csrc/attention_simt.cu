@@ -226,6 +226,7 @@ extern "C" int mmgt_attention(mmgt_ctx* ctx, const mmgt_attention_params* p, voi
   MMGT_CHECK_ARG(p->q && p->k && p->v && p->out && p->N > 0 && p->Lq > 0 && p->Lk > 0 && p->heads > 0 && p->d > 0,
                  MMGT_E_INVALID, "attention: bad args");
   MMGT_CHECK_ARG(!p->k2 || (p->v2 && p->Lk2 > 0), MMGT_E_INVALID, "attention: second segment incomplete");
+  if (ctx->use_tc && mmgt_attention_tc_supported(ctx, p)) return mmgt_attention_tc(ctx, p, st);
   MMGT_CHECK_ARG(p->d % 4 == 0 && p->d <= 160, MMGT_E_UNSUPPORTED, "attention: head dim %d (need multiple of 4, <= 160)", p->d);
   const int ev = p->dtype == MMGT_F32 ? 16 : 8;
   MMGT_CHECK_ARG(p->ldq % 4 == 0 && p->ldk % 4 == 0 && p->ldv % 4 == 0 && (!p->k2 || (p->ldk2 % 4 == 0 && p->ldv2 % 4 == 0)) &&

@@ -1,0 +1,450 @@
+// Flash-style attention on tcgen05 / TMEM, fed by TMA (bf16 operands, fp32 softmax and accumulation).
+//
+//   out[n, q, h, :] = softmax_k( q . k * scale ) v     over keys [ per-frame segment ; optional shared segment ]
+//
+// One CTA = one (frame, head, 128-query tile).  Warp roles:
+//   warp 0 (one lane)  TMA producer: Q once, then K / V tiles through two smem rings
+//   warp 1 (one lane)  MMA issuer:   S[j&1] = Q K_j^T   (128 x BN x d_pad, accumulator in TMEM, double buffered)
+//                                    O     += P_j V_j   (128 x d_pad x BN, P from smem, V MN-major)
+//   warps 2..5         softmax: one thread per query row (= TMEM lane): tcgen05.ld S -> online max / exp2 ->
+//                      bf16 P into 128B-swizzled smem; lazy rescale of O in TMEM (only when the running max
+//                      moved by > 2^8); final 1/l scaling and the global store of O.
+// Head dims that are not multiples of 64 (40, 80, 160) need no padded tensors: Q/K/V are described to TMA as
+// (d, heads, rows) and a 64-wide box on the d axis is zero-filled past d, which pads every head to 64/128/192.
+// The second key segment implements ReferenceNet feature injection: frames whose seg2 index is -1 (the CFG
+// "uncond" half, mutual_self_attention.py:168-188) simply stop after the first segment.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BQ = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int KV_STAGES = 2;
+constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
+
+struct AttnArgs {
+  int N, Lq, Lk, Lk2, heads, d;
+  const int32_t* seg2_index;
+  int has_seg2;
+  bf16* out;
+  int64_t ldo;
+  float scale_log2e;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major operand, 128B swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// MN-major operand (V: keys x d, d contiguous), 128B swizzle: 64-element d chunks `lbo_bytes` apart,
+// 8-key groups 1024 B apart
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t lbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int n, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major ? (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BQ >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// DCH = ceil(d / 64) head-dim chunks (d_pad = 64 * DCH); BN = keys per tile
+template <int DCH, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
+                    const __grid_constant__ CUtensorMap tmV2, const AttnArgs args) {
+  constexpr int DPAD = 64 * DCH;
+  constexpr int Q_BYTES = BQ * DPAD * 2;
+  constexpr int KV_BYTES = BN * DPAD * 2;        // one K (or V) stage
+  constexpr int KV_CHUNK = BN * 128;             // bytes of one 64-wide d chunk of a K/V stage
+  constexpr int P_BYTES = BQ * BN * 2;
+  constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256;
+  constexpr uint32_t IDESC_QK = idesc_bf16(BN, false);
+  constexpr uint32_t IDESC_PV = idesc_bf16(DPAD, true);
+  static_assert(TM_O + DPAD <= 512, "TMEM budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;
+  uint8_t* sV = sK + KV_STAGES * KV_BYTES;
+  uint8_t* sP = sV + KV_STAGES * KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* q_full = bars;                     // 1
+  uint64_t* k_full = bars + 1;                 // KV_STAGES
+  uint64_t* k_empty = k_full + KV_STAGES;
+  uint64_t* v_full = k_empty + KV_STAGES;
+  uint64_t* v_empty = v_full + KV_STAGES;
+  uint64_t* s_full = v_empty + KV_STAGES;      // 2
+  uint64_t* s_empty = s_full + 2;              // 2
+  uint64_t* p_full = s_empty + 2;              // 1
+  uint64_t* p_empty = p_full + 1;              // 1  (== "PV_j retired": P buffer free and O stable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+
+  int seg2 = -1;
+  if (args.has_seg2) seg2 = args.seg2_index ? args.seg2_index[n] : 0;
+  const int tiles1 = (args.Lk + BN - 1) / BN;
+  const int tiles2 = seg2 >= 0 ? (args.Lk2 + BN - 1) / BN : 0;
+  const int num_tiles = tiles1 + tiles2;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    mbar_init(&s_empty[0], 4); mbar_init(&s_empty[1], 4);
+    mbar_init(p_full, 128);
+    mbar_init(p_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    // ===================== TMA producer =====================
+    mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+    for (int c = 0; c < DCH; ++c) tma_load_3d(sQ + c * (BQ * 128), &tmQ, q_full, c * 64, h, n * args.Lq + q0);
+    for (int j = 0; j < num_tiles; ++j) {
+      const int st = j % KV_STAGES;
+      const uint32_t ph = (j / KV_STAGES) & 1;
+      const bool second = j >= tiles1;
+      const int row = second ? seg2 * args.Lk2 + (j - tiles1) * BN : n * args.Lk + j * BN;
+      mbar_wait(&k_empty[st], ph ^ 1);
+      mbar_expect_tx(&k_full[st], KV_BYTES);
+#pragma unroll
+      for (int c = 0; c < DCH; ++c)
+        tma_load_3d(sK + st * KV_BYTES + c * KV_CHUNK, second ? &tmK2 : &tmK, &k_full[st], c * 64, h, row);
+      mbar_wait(&v_empty[st], ph ^ 1);
+      mbar_expect_tx(&v_full[st], KV_BYTES);
+#pragma unroll
+      for (int c = 0; c < DCH; ++c)
+        tma_load_3d(sV + st * KV_BYTES + c * KV_CHUNK, second ? &tmV2 : &tmV, &v_full[st], c * 64, h, row);
+    }
+  } else if (threadIdx.x == 32) {
+    // ===================== MMA issuer =====================
+    auto issue_qk = [&](int j) {
+      const int st = j % KV_STAGES;
+      mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
+      mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tS = tmem_base + ((j & 1) ? TM_S1 : TM_S0);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + st * KV_BYTES);
+#pragma unroll
+      for (int k = 0; k < DPAD / 16; ++k) {
+        const uint32_t offq = (k / 4) * (BQ * 128) + (k % 4) * 32, offk = (k / 4) * KV_CHUNK + (k % 4) * 32;
+        umma(tS, desc_kmajor(aQ + offq), desc_kmajor(aK + offk), IDESC_QK, k != 0);
+      }
+      umma_commit(&k_empty[st]);
+      umma_commit(&s_full[j & 1]);
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < num_tiles; ++j) {
+      if (j + 1 < num_tiles) issue_qk(j + 1);
+      const int st = j % KV_STAGES;
+      mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      const uint32_t aP = smem_u32(sP), aV = smem_u32(sV + st * KV_BYTES);
+#pragma unroll
+      for (int k = 0; k < BN / 16; ++k) {
+        // A = P: K-major, 64-key chunks of (128 rows x 128 B); B = V: MN-major, 16 keys = 2 x 1024 B per step
+        const uint32_t offp = (k / 4) * (BQ * 128) + (k % 4) * 32;
+        umma(tmem_base + TM_O, desc_kmajor(aP + offp), desc_mnmajor(aV + k * 2048, KV_CHUNK), IDESC_PV, (j | k) != 0);
+      }
+      umma_commit(&v_empty[st]);
+      umma_commit(p_empty);
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax / correction / epilogue =====================
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;            // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
+    const float c = args.scale_log2e;
+    float m_ref = -INFINITY;   // reference maximum the stored O / l are relative to (raw score units)
+    float l_run = 0.f;
+    uint8_t* prow = sP + row * 128;
+    const int sw = row & 7;
+
+    for (int j = 0; j < num_tiles; ++j) {
+      const bool second = j >= tiles1;
+      const int seg_len = second ? args.Lk2 : args.Lk;
+      const int k0 = (second ? (j - tiles1) : j) * BN;
+      const int valid = min(BN, seg_len - k0);       // keys of this tile that exist
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[BN];
+      const uint32_t tS = tmem_base + ((j & 1) ? TM_S1 : TM_S0) + lane_addr;
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) tmem_ld32(tS + i * 32, s + i * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[j & 1]);
+
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < BN; ++i) {
+        float v = __uint_as_float(s[i]);
+        if (i >= valid) { v = -INFINITY; s[i] = __float_as_uint(v); }
+        mx = fmaxf(mx, v);
+      }
+      // lazy rescale: keep the old reference unless the maximum moved by more than 2^THRESHOLD
+      float alpha = 1.f;
+      const bool need = (mx - m_ref) * c > RESCALE_THRESHOLD;     // true on the first tile (m_ref = -inf)
+      if (need) {
+        alpha = exp2f((m_ref - mx) * c);                          // 0 on the first tile
+        m_ref = mx;
+      }
+      const float mc = m_ref * c;
+      float lsum = 0.f;
+      uint32_t pk[BN / 2];
+#pragma unroll
+      for (int i = 0; i < BN; i += 2) {
+        float p0 = exp2f(fmaf(__uint_as_float(s[i]), c, -mc));
+        float p1 = exp2f(fmaf(__uint_as_float(s[i + 1]), c, -mc));
+        pk[i / 2] = pack_bf16(p0, p1);
+        // accumulate the row sum from the bf16-rounded values that the PV MMA will actually use
+        __nv_bfloat162 hb = *reinterpret_cast<__nv_bfloat162*>(&pk[i / 2]);
+        float2 f = __bfloat1622float2(hb);
+        lsum += f.x + f.y;
+      }
+      l_run = l_run * alpha + lsum;
+
+      if (j > 0) {
+        mbar_wait(p_empty, (j - 1) & 1);   // PV_{j-1} retired: P buffer reusable, O stable
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+          for (int cc = 0; cc < DPAD / 32; ++cc) {
+            uint32_t o[32];
+            tmem_ld32(tmem_base + TM_O + lane_addr + cc * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_base + TM_O + lane_addr + cc * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // P -> smem, K-major 128B swizzle: 16-byte unit u of row r lands at unit (u ^ (r & 7)) of its 128-byte row
+#pragma unroll
+      for (int u = 0; u < BN / 8; ++u) {
+        const int chunk = u >> 3, uu = u & 7;
+        uint4 val = make_uint4(pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
+        *reinterpret_cast<uint4*>(prow + chunk * (BQ * 128) + ((uu ^ sw) << 4)) = val;
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+
+    // ---- epilogue: O / l -> global (only the first d columns are real)
+    mbar_wait(p_empty, (num_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    const int q = q0 + row;
+    bf16* orow = args.out + ((int64_t)n * args.Lq + q) * args.ldo + h * args.d;
+#pragma unroll
+    for (int cc = 0; cc < DPAD / 32; ++cc) {
+      uint32_t o[32];
+      tmem_ld32(tmem_base + TM_O + lane_addr + cc * 32, o);
+      tmem_ld_wait();
+      if (q < args.Lq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = cc * 32 + g * 8;
+          if (col < args.d) {
+            uint4 val;
+            val.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+            val.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+            val.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+            val.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + col) = val;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_qkv_map(mmgt_ctx* ctx, CUtensorMap* map, const void* base, int d, int heads, int64_t rows, int64_t ld, int box_rows) {
+  if (!ctx->encode_tiled) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+      mmgt_set_error("cuTensorMapEncodeTiled not available (%s)", cudaGetErrorString(e));
+      return MMGT_E_NODRIVER;
+    }
+    ctx->encode_tiled = p;
+  }
+  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+  cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)rows};
+  cuuint64_t strides[2] = {(cuuint64_t)d * 2, (cuuint64_t)ld * 2};
+  cuuint32_t box[3] = {64, 1, (cuuint32_t)box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mmgt_set_error("attention: cuTensorMapEncodeTiled failed (%d) d=%d heads=%d rows=%lld ld=%lld", (int)r, d, heads,
+                   (long long)rows, (long long)ld);
+    return MMGT_E_INVALID;
+  }
+  return 0;
+}
+
+template <int DCH, int BN>
+int launch_attn(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaStream_t st) {
+  constexpr int smem = BQ * 64 * DCH * 2 + 2 * KV_STAGES * BN * 64 * DCH * 2 + BQ * BN * 2 + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    MMGT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<DCH, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((a.Lq + BQ - 1) / BQ, a.heads, a.N);
+  attention_tc_kernel<DCH, BN><<<grid, NUM_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], a);
+  MMGT_LAUNCH_OK(ctx);
+  return 0;
+}
+
+}  // namespace
+
+bool mmgt_attention_tc_supported(const mmgt_ctx* ctx, const mmgt_attention_params* p) {
+  (void)ctx;
+  if (p->dtype != MMGT_BF16) return false;
+  if (p->d % 8 || p->d > 192 || p->d < 8) return false;
+  if (p->Lq < 64 || p->N > 65535 || p->heads > 65535) return false;
+  if (p->ldq % 8 || p->ldk % 8 || p->ldv % 8 || p->ldo % 8) return false;
+  if (p->kv_batch_stride && (p->kv_batch_stride != (int64_t)p->Lk * p->ldk || p->ldk != p->ldv)) return false;
+  if (!aligned16(p->q) || !aligned16(p->k) || !aligned16(p->v) || !aligned16(p->out)) return false;
+  if (p->k2 && (p->ldk2 % 8 || p->ldv2 % 8 || !aligned16(p->k2) || !aligned16(p->v2) || p->B2 < 1)) return false;
+  return true;
+}
+
+int mmgt_attention_tc(mmgt_ctx* ctx, const mmgt_attention_params* p, cudaStream_t st) {
+  const int dch = (p->d + 63) / 64;
+  const int bn = dch == 3 ? 64 : 128;
+  CUtensorMap maps[5];
+  int rc;
+  if ((rc = encode_qkv_map(ctx, &maps[0], p->q, p->d, p->heads, (int64_t)p->N * p->Lq, p->ldq, BQ))) return rc;
+  if ((rc = encode_qkv_map(ctx, &maps[1], p->k, p->d, p->heads, (int64_t)p->N * p->Lk, p->ldk, bn))) return rc;
+  if ((rc = encode_qkv_map(ctx, &maps[2], p->v, p->d, p->heads, (int64_t)p->N * p->Lk, p->ldv, bn))) return rc;
+  const void* k2 = p->k2 ? p->k2 : p->k;
+  const void* v2 = p->k2 ? p->v2 : p->v;
+  const int64_t rows2 = p->k2 ? (int64_t)p->B2 * p->Lk2 : (int64_t)p->N * p->Lk;
+  if ((rc = encode_qkv_map(ctx, &maps[3], k2, p->d, p->heads, rows2, p->k2 ? p->ldk2 : p->ldk, bn))) return rc;
+  if ((rc = encode_qkv_map(ctx, &maps[4], v2, p->d, p->heads, rows2, p->k2 ? p->ldv2 : p->ldv, bn))) return rc;
+  AttnArgs a{};
+  a.N = p->N; a.Lq = p->Lq; a.Lk = p->Lk; a.Lk2 = p->k2 ? p->Lk2 : 0; a.heads = p->heads; a.d = p->d;
+  a.seg2_index = p->seg2_index; a.has_seg2 = p->k2 != nullptr;
+  a.out = (bf16*)p->out; a.ldo = p->ldo;
+  a.scale_log2e = p->scale * 1.4426950408889634f;
+  if (dch == 1) return launch_attn<1, 128>(ctx, maps, a, st);
+  if (dch == 2) return launch_attn<2, 128>(ctx, maps, a, st);
+  return launch_attn<3, 64>(ctx, maps, a, st);
+}

@@ -85,3 +85,6 @@ int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st);
 bool mmgt_gemm_tc_supported(const mmgt_ctx* ctx, const mmgt_gemm_params* p);
 int mmgt_conv3x3_tc(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, cudaStream_t st);
 bool mmgt_conv3x3_tc_supported(const mmgt_ctx* ctx, const mmgt_conv3x3_params* p);
+// attention_tc.cu
+int mmgt_attention_tc(mmgt_ctx* ctx, const mmgt_attention_params* p, cudaStream_t st);
+bool mmgt_attention_tc_supported(const mmgt_ctx* ctx, const mmgt_attention_params* p);

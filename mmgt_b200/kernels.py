@@ -198,7 +198,7 @@ class Engine:
         p.N, p.Lq, p.Lk, p.heads, p.d = N, Lq, k.shape[1], heads, d
         if k2 is not None:
             p.k2, p.v2 = k2.data_ptr(), v2.data_ptr()
-            p.ldk2, p.ldv2, p.Lk2 = k2.stride(1), v2.stride(1), k2.shape[1]
+            p.ldk2, p.ldv2, p.Lk2, p.B2 = k2.stride(1), v2.stride(1), k2.shape[1], k2.shape[0]
             p.seg2_index = seg2_index.data_ptr() if seg2_index is not None else None
         p.scale = float(d) ** -0.5
         p.dtype = self.dt

@@ -76,8 +76,7 @@ def sdpa(q, k, v, heads):
     qh = q.view(n, lq, heads, d).transpose(1, 2)
     kh = k.view(n, -1, heads, d).transpose(1, 2)
     vh = v.view(n, -1, heads, d).transpose(1, 2)
-    s = torch.matmul(qh, kh.transpose(-1, -2)) * (d ** -0.5)
-    o = torch.matmul(s.softmax(dim=-1), vh)
+    o = F.scaled_dot_product_attention(qh, kh, vh)   # softmax(q k^T / sqrt(d)) v, what AttnProcessor2_0 calls
     return o.transpose(1, 2).reshape(n, lq, c)
 
 
@@ -153,12 +152,14 @@ def spatial_transformer(spec: UNetSpec, p: _SD, x, clip_n, bank_n: Optional[torc
     tok = _tokens_in(p, x, spec.norm_num_groups)
     b = p.sub("transformer_blocks.0")
     n1 = layer_norm(b.sub("norm1"), tok)
-    a_self = attention(b.sub("attn1"), n1, n1, spec.heads)
     if bank_n is not None and bool(use_ref.any()):
-        a_ref = attention(b.sub("attn1"), n1, torch.cat([n1, bank_n], dim=1), spec.heads)
-        a1 = torch.where(use_ref[:, None, None], a_ref, a_self)
+        a1 = torch.empty_like(n1)
+        ref_rows, self_rows = use_ref.nonzero().flatten(), (~use_ref).nonzero().flatten()
+        a1[ref_rows] = attention(b.sub("attn1"), n1[ref_rows], torch.cat([n1[ref_rows], bank_n[ref_rows]], dim=1), spec.heads)
+        if self_rows.numel():
+            a1[self_rows] = attention(b.sub("attn1"), n1[self_rows], n1[self_rows], spec.heads)
     else:
-        a1 = a_self
+        a1 = attention(b.sub("attn1"), n1, n1, spec.heads)
     tok = a1 + tok
     tok = attention(b.sub("attn2"), layer_norm(b.sub("norm2"), tok), clip_n, spec.heads) + tok
     tok = feed_forward(b.sub("ff"), layer_norm(b.sub("norm3"), tok)) + tok

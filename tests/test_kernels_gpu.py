@@ -201,31 +201,43 @@ def _attn_ref(q, k, v, heads):
     return (s.softmax(-1) @ vh).transpose(1, 2).reshape(n, lq, c)
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("N,Lq,Lk,Lk2,heads,d", [(4, 64, 64, 64, 8, 40), (3, 100, 100, 100, 8, 8), (2, 256, 256, 0, 8, 80),
-                                                 (2, 70, 32, 0, 8, 40), (2, 64, 64, 64, 8, 160), (6, 16, 16, 16, 8, 32)])
-def test_attention_two_segments(dev, dtype, N, Lq, Lk, Lk2, heads, d):
+ATTN_CASES = [(4, 64, 64, 64, 8, 40), (3, 100, 100, 100, 8, 8), (2, 256, 256, 0, 8, 80), (2, 70, 32, 0, 8, 40),
+              (2, 64, 64, 64, 8, 160), (6, 16, 16, 16, 8, 32), (3, 1024, 1024, 1024, 8, 40), (2, 4096, 4096, 4096, 8, 40),
+              (2, 300, 300, 300, 8, 80), (2, 256, 256, 256, 8, 160), (2, 1024, 32, 0, 8, 80), (3, 200, 136, 72, 8, 16)]
+
+
+@pytest.mark.parametrize("dtype,tc", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)],
+                         ids=["f32", "bf16simt", "bf16tc"])
+@pytest.mark.parametrize("N,Lq,Lk,Lk2,heads,d", ATTN_CASES)
+def test_attention_two_segments(dev, dtype, tc, N, Lq, Lk, Lk2, heads, d):
     eng = eng_for(dev, dtype)
-    C = heads * d
-    qkv = rnd(N, Lq if Lq == Lk else max(Lq, Lk), 3 * C, dev=dev, dtype=dtype, seed=51)
-    q, k, v = qkv[:, :Lq, :C], qkv[:, :Lk, C:2 * C], qkv[:, :Lk, 2 * C:]
-    if Lk2:
-        bank = rnd(2, Lk2, 2 * C, dev=dev, dtype=dtype, seed=52)
-        k2, v2 = bank[:, :, :C], bank[:, :, C:]
-        idx = torch.tensor([(-1 if i % 3 == 0 else i % 2) for i in range(N)], dtype=torch.int32, device=dev)
-        out = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
-        refs = []
-        for n in range(N):
-            kk, vv = k[n:n + 1], v[n:n + 1]
-            if idx[n] >= 0:
-                kk = torch.cat([kk, k2[idx[n]:idx[n] + 1]], 1)
-                vv = torch.cat([vv, v2[idx[n]:idx[n] + 1]], 1)
-            refs.append(_attn_ref(q[n:n + 1], kk, vv, heads))
-        ref = torch.cat(refs)
-    else:
-        out = eng.attention(q, k, v, heads)
-        ref = _attn_ref(q, k, v, heads)
-    assert rel_l2(out.float(), ref) < (2e-5 if dtype == torch.float32 else 8e-3)
+    eng.ctx.set_tensor_cores(tc)
+    try:
+        C = heads * d
+        qkv = rnd(N, max(Lq, Lk), 3 * C, dev=dev, dtype=dtype, seed=51)
+        q = qkv[:, :Lq, :C]
+        # keys / values of a frame must be Lk consecutive rows (row stride 3C), frames Lk rows apart
+        kvbuf = rnd(N, Lk, 3 * C, dev=dev, dtype=dtype, seed=53)
+        k, v = kvbuf[:, :, C:2 * C], kvbuf[:, :, 2 * C:]
+        if Lk2:
+            bank = rnd(2, Lk2, 2 * C, dev=dev, dtype=dtype, seed=52)
+            k2, v2 = bank[:, :, :C], bank[:, :, C:]
+            idx = torch.tensor([(-1 if i % 3 == 0 else i % 2) for i in range(N)], dtype=torch.int32, device=dev)
+            out = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
+            refs = []
+            for n in range(N):
+                kk, vv = k[n:n + 1], v[n:n + 1]
+                if idx[n] >= 0:
+                    kk = torch.cat([kk, k2[idx[n]:idx[n] + 1]], 1)
+                    vv = torch.cat([vv, v2[idx[n]:idx[n] + 1]], 1)
+                refs.append(_attn_ref(q[n:n + 1], kk, vv, heads))
+            ref = torch.cat(refs)
+        else:
+            out = eng.attention(q, k, v, heads)
+            ref = _attn_ref(q, k, v, heads)
+        assert rel_l2(out.float(), ref) < (2e-5 if dtype == torch.float32 else 8e-3)
+    finally:
+        eng.ctx.set_tensor_cores(True)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
