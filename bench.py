@@ -175,6 +175,10 @@ def run_ours(args):
     eng = loop.eng
     if args.no_tc:
         eng.ctx.set_tensor_cores(False)
+    if not args.no_graph:
+        t0 = time.time()
+        loop.capture_graph()
+        log(f"[rank {rank}] CUDA graph of one step captured in {time.time() - t0:.1f}s ({loop.graph_launches} kernel launches)")
 
     def barrier():
         if world > 1:
@@ -195,7 +199,7 @@ def run_ours(args):
     e1.record()
     barrier()
     clocks = sampler.stop()
-    launches = eng.ctx.launches() - n0
+    launches = eng.ctx.launches() - n0 + (loop.graph_launches * args.steps if loop._graph is not None else 0)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -208,6 +212,8 @@ def run_ours(args):
     t_prep0 = time.perf_counter()
     d2 = to_device(host, dev)
     loop2 = make_loop(d2)
+    if not args.no_graph:
+        loop2.capture_graph()
     torch.cuda.synchronize()
     prep_s = time.perf_counter() - t_prep0
     lat_host = host["latents"]
@@ -232,7 +238,9 @@ def run_ours(args):
     roof = None
     if rank == 0:
         eng.prof = {}
+        graph, loop._graph = loop._graph, None        # per-launch events need eager launches
         loop.step(0)
+        loop._graph = graph
         torch.cuda.synchronize()
         prof, eng.prof = eng.prof, None
         rows = []
@@ -243,7 +251,7 @@ def run_ours(args):
         tot = sum(x[0] for x in rows)
         pk = peaks()
         log(f"--- per-operator time over one step (event-timed, {tot:.1f} ms in instrumented ops) ---")
-        for tms, key, r in rows[:14]:
+        for tms, key, r in rows[:40]:
             tf = r["flops"] / (tms * 1e-3) / 1e12 if tms > 0 else 0
             gb = r["bytes"] / (tms * 1e-3) / 1e9 if tms > 0 else 0
             log(f"{tms:9.2f} ms {100 * tms / tot:5.1f}%  calls {r['calls']:5d}  {tf:8.1f} TFLOP/s {gb:8.1f} GB/s  {key}")
@@ -352,6 +360,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--frames", type=int, default=VIDEO_LENGTH)
     ap.add_argument("--no-tc", action="store_true", help="debug: CUDA-core kernels only")
+    ap.add_argument("--no-graph", action="store_true", help="debug: eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=150.0)
     args = ap.parse_args()

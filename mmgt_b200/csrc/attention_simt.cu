@@ -242,7 +242,12 @@ extern "C" int mmgt_attention(mmgt_ctx* ctx, const mmgt_attention_params* p, voi
   const int dpl = (p->d + 31) / 32;
 #define LAUNCH(TT, DPL)                                                                                            \
   do {                                                                                                             \
-    MMGT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<TT, DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    static bool configured = false; /* once per instantiation: keeps the call out of CUDA-graph capture */        \
+    if (!configured) {                                                                                             \
+      MMGT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<TT, DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                        ctx->max_smem_optin));                                                     \
+      configured = true;                                                                                           \
+    }                                                                                                              \
     attention_kernel<TT, DPL><<<grid, AWARPS * 32, smem, st>>>(*p);                                                \
   } while (0)
   MMGT_DISPATCH_DTYPE(p->dtype, T_, {
@@ -270,7 +275,12 @@ extern "C" int mmgt_temporal_attention(mmgt_ctx* ctx, const void* qkv, void* out
   const int64_t total = (int64_t)B * T * heads;
   int blocks = (int)std::min<int64_t>((total + TW - 1) / TW, (int64_t)ctx->num_sms * 32);
   MMGT_DISPATCH_DTYPE(dtype, T_, {
-    MMGT_CUDA_OK(cudaFuncSetAttribute(temporal_attention_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool configured = false;
+    if (!configured) {
+      MMGT_CUDA_OK(cudaFuncSetAttribute(temporal_attention_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        ctx->max_smem_optin));
+      configured = true;
+    }
     temporal_attention_kernel<T_><<<blocks, TW * 32, smem, st>>>((const T_*)qkv, (T_*)out, B, F, T, heads, d, scale);
   });
   MMGT_LAUNCH_OK(ctx);

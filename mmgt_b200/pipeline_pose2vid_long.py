@@ -42,6 +42,7 @@ class DenoiseLoop:
         self.rank, self.world, self.group = rank, world_size, process_group
         self.timesteps = schedule.timesteps(num_inference_steps)
         self._graph = None
+        self.graph_launches = 0
 
     # ------------------------------------------------------------------ one-off preparation per video
     def prepare(self, latents, pose_fea, audio, full_mask, face_mask, lip_mask, encoder_hidden_states):
@@ -99,14 +100,39 @@ class DenoiseLoop:
             pred = eng.tokens_to_ncfhw(out, 1, F_, torch.float32)
             eng.window_accumulate(self.noise_acc, pred, e["idx"], b)
 
+    def _units_body(self):
+        """Everything of a step that does not depend on host scalars: zero the accumulator, re-layout the latents,
+        run this rank's (window, branch) forwards and scatter-add their predictions."""
+        self.noise_acc.zero_()
+        lat_tok = self.eng.ncfhw_to_tokens(self.latents)[: self.L]      # (L,h,w,4) run dtype
+        self._forward_units(lat_tok)
+
+    def capture_graph(self):
+        """Capture ``_units_body`` (tens of thousands of launches) into one CUDA graph.  The timestep lives in a
+        device tensor and the DDIM coefficients stay outside the graph, so one graph serves all steps."""
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):       # eager warm-up: builds weight packs, bank K/V, scratch buffers
+            n0 = self.eng.ctx.launches()
+            self._units_body()
+            self.graph_launches = self.eng.ctx.launches() - n0
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._units_body()
+        return self
+
     def step(self, i: int):
         """One DDIM step over the whole video (all context windows, both CFG branches)."""
         eng = self.eng
         t = self.timesteps[i]
         self.t_dev.fill_(float(t))
-        self.noise_acc.zero_()
-        lat_tok = eng.ncfhw_to_tokens(self.latents)[: self.L]          # (L,h,w,4) run dtype
-        self._forward_units(lat_tok)
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._units_body()
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.noise_acc, group=self.group)

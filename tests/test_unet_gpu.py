@@ -147,6 +147,8 @@ def test_denoise_step_matches_oracle(compute_dtype, tol):
     loop.prepare(d["latents"], d["pose_fea"], d["audio"], d["full_mask"], d["face_mask"], d["lip_mask"],
                  d["encoder_hidden_states"])
     assert loop.windows == windows
+    if compute_dtype == torch.bfloat16:
+        loop.capture_graph()          # the bf16 case also covers CUDA-graph replay of the step
     loop.step(0)
     lat = loop.step(1)
     err = rel_l2(lat, lat_ref)
