@@ -218,6 +218,136 @@ temporal_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int B,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// bf16 temporal attention on warp-level tensor-core MMAs (m16n8k16): one warp owns one (b, t, head); the
+// F <= 16 frames form one 16-row tile.  S = Q K^T (16 x 16 x d), softmax on the accumulator fragments,
+// O = P V (16 x d x 16).  This operator is HBM-bound (reads 3*C, writes C per row, ~0.03 % of the FLOPs), so
+// the point of the MMAs is only to get the arithmetic out of the way of the memory pipeline.
+constexpr int TMW = 4;  // warps per block
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// DK = head dim rounded up to 16 (k extent of Q K^T); row stride DP = DK + 8 elements keeps ldmatrix conflict-free
+template <int DK>
+__global__ void __launch_bounds__(TMW * 32)
+temporal_attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B, int F, int T_tok, int heads, int d,
+                              float scale_log2e) {
+  constexpr int DP = DK + 8;
+  extern __shared__ __align__(16) uint8_t smem_u8[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bf16* Qs = reinterpret_cast<bf16*>(smem_u8) + (size_t)warp * 3 * 16 * DP;
+  bf16* Ks = Qs + 16 * DP;
+  bf16* Vs = Ks + 16 * DP;
+  // zero once: rows >= F and columns >= d are never written again
+  for (int i = lane; i < 3 * 16 * DP / 8; i += 32) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  const int C = heads * d, dv = d >> 3;   // 16-byte vectors per row
+  const int64_t total = (int64_t)B * T_tok * heads;
+  const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(Qs), k_addr = (uint32_t)__cvta_generic_to_shared(Ks),
+                 v_addr = (uint32_t)__cvta_generic_to_shared(Vs);
+  const int qrow = lane >> 2, qcol = (lane & 3) * 2;   // accumulator fragment coordinates
+  for (int64_t w = (int64_t)blockIdx.x * TMW + warp; w < total; w += (int64_t)gridDim.x * TMW) {
+    const int h = w % heads;
+    const int64_t bt = w / heads;
+    const int t = bt % T_tok, b = bt / T_tok;
+    for (int i = lane; i < F * dv; i += 32) {
+      const int f = i / dv, c = (i - f * dv) * 8;
+      const bf16* row = qkv + (((int64_t)b * F + f) * T_tok + t) * (3 * C) + h * d + c;
+      *reinterpret_cast<uint4*>(Qs + f * DP + c) = *reinterpret_cast<const uint4*>(row);
+      *reinterpret_cast<uint4*>(Ks + f * DP + c) = *reinterpret_cast<const uint4*>(row + C);
+      *reinterpret_cast<uint4*>(Vs + f * DP + c) = *reinterpret_cast<const uint4*>(row + 2 * C);
+    }
+    __syncwarp();
+    // ---- S = Q K^T : two 16x8 accumulator tiles (keys 0-7, 8-15)
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < DK / 16; ++ks) {
+      uint32_t a[4], bb[4];
+      ldsm_x4(q_addr + (((lane & 7) + ((lane >> 3) & 1) * 8) * DP + ks * 16 + (lane >> 4) * 8) * 2, a);
+      ldsm_x4(k_addr + (((lane & 7) + (lane >> 4) * 8) * DP + ks * 16 + ((lane >> 3) & 1) * 8) * 2, bb);
+      mma_bf16_16816(s0, a, bb[0], bb[1]);
+      mma_bf16_16816(s1, a, bb[2], bb[3]);
+    }
+    // ---- softmax over keys (columns); this lane holds rows qrow, qrow+8 and key columns qcol,+1 (+8)
+    float p[8] = {s0[0], s0[1], s1[0], s1[1], s0[2], s0[3], s1[2], s1[3]};  // [row lo: k0,k1,k8,k9 | row hi: ...]
+    const int kc[4] = {qcol, qcol + 1, qcol + 8, qcol + 9};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (kc[j] >= F) p[r * 4 + j] = -INFINITY;
+        mx = fmaxf(mx, p[r * 4 + j]);
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        p[r * 4 + j] = exp2f((p[r * 4 + j] - mx) * scale_log2e);
+        sum += p[r * 4 + j];
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p[r * 4 + j] *= inv;
+    }
+    // accumulator layout of S == A-operand layout of P (16 x 16)
+    const uint32_t pa[4] = {pack2(p[0], p[1]), pack2(p[4], p[5]), pack2(p[2], p[3]), pack2(p[6], p[7])};
+    __syncwarp();   // everyone is done reading Qs before it receives O
+    // ---- O = P V, 16 d-columns per step (two n-tiles)
+    for (int n0 = 0; n0 < d; n0 += 16) {
+      uint32_t vb[4];
+      ldsm_x4_trans(v_addr + (((lane & 7) + ((lane >> 3) & 1) * 8) * DP + n0 + (lane >> 4) * 8) * 2, vb);
+      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(o0, pa, vb[0], vb[1]);
+      mma_bf16_16816(o1, pa, vb[2], vb[3]);
+      // rows qrow / qrow+8, columns n0 + qcol (+8 for the second tile) -> staged in Qs
+      *reinterpret_cast<uint32_t*>(Qs + qrow * DP + n0 + qcol) = pack2(o0[0], o0[1]);
+      *reinterpret_cast<uint32_t*>(Qs + (qrow + 8) * DP + n0 + qcol) = pack2(o0[2], o0[3]);
+      if (n0 + 8 < d) {
+        *reinterpret_cast<uint32_t*>(Qs + qrow * DP + n0 + 8 + qcol) = pack2(o1[0], o1[1]);
+        *reinterpret_cast<uint32_t*>(Qs + (qrow + 8) * DP + n0 + 8 + qcol) = pack2(o1[2], o1[3]);
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < F * dv; i += 32) {
+      const int f = i / dv, c = (i - f * dv) * 8;
+      *reinterpret_cast<uint4*>(out + (((int64_t)b * F + f) * T_tok + t) * C + h * d + c) =
+          *reinterpret_cast<const uint4*>(Qs + f * DP + c);
+    }
+    __syncwarp();
+    // rows >= F of Qs received garbage-free zeros only if F >= 8 rows hi part unused; re-zero what O staging touched
+    if (F < 16) {
+      for (int i = lane; i < (16 - F) * (DP / 8); i += 32) {
+        const int r = F + i / (DP / 8), c = (i % (DP / 8)) * 8;
+        *reinterpret_cast<uint4*>(Qs + r * DP + c) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    if (d < DK) {   // columns [d, DK) of the rows O staging wrote (d % 16 == 8 case writes none beyond d; keep exact)
+      for (int i = lane; i < F; i += 32) *reinterpret_cast<uint4*>(Qs + i * DP + d) = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 extern "C" int mmgt_attention(mmgt_ctx* ctx, const mmgt_attention_params* p, void* stream) {
@@ -269,6 +399,38 @@ extern "C" int mmgt_temporal_attention(mmgt_ctx* ctx, const void* qkv, void* out
   MMGT_CHECK_ARG(F <= 32, MMGT_E_UNSUPPORTED, "temporal_attention: F=%d > 32 (positional table max_len is 32)", F);
   MMGT_CHECK_ARG(d % 4 == 0, MMGT_E_UNSUPPORTED, "temporal_attention: head dim must be a multiple of 4");
   MMGT_CHECK_ARG(aligned16(qkv), MMGT_E_ALIGN, "temporal_attention: qkv must be 16B aligned");
+  if (dtype == MMGT_BF16 && ctx->use_tc && F <= 16 && d % 8 == 0 && d <= 160) {
+    const int DK = (d + 15) / 16 * 16;
+    const size_t smem = (size_t)TMW * 3 * 16 * (DK + 8) * 2;
+    const int64_t total = (int64_t)B * T * heads;
+    int blocks = (int)std::min<int64_t>((total + TMW - 1) / TMW, (int64_t)ctx->num_sms * 32);
+    const float sl2 = scale * 1.4426950408889634f;
+#define TLAUNCH(DK_)                                                                                                   \
+  do {                                                                                                                 \
+    static bool configured = false;                                                                                    \
+    if (!configured) {                                                                                                 \
+      MMGT_CUDA_OK(cudaFuncSetAttribute(temporal_attention_mma_kernel<DK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        ctx->max_smem_optin));                                                         \
+      configured = true;                                                                                               \
+    }                                                                                                                  \
+    temporal_attention_mma_kernel<DK_><<<blocks, TMW * 32, smem, st>>>((const bf16*)qkv, (bf16*)out, B, F, T, heads, d, sl2); \
+  } while (0)
+    switch (DK) {
+      case 16: TLAUNCH(16); break;
+      case 32: TLAUNCH(32); break;
+      case 48: TLAUNCH(48); break;
+      case 64: TLAUNCH(64); break;
+      case 80: TLAUNCH(80); break;
+      case 96: TLAUNCH(96); break;
+      case 112: TLAUNCH(112); break;
+      case 128: TLAUNCH(128); break;
+      case 144: TLAUNCH(144); break;
+      default: TLAUNCH(160); break;
+    }
+#undef TLAUNCH
+    MMGT_LAUNCH_OK(ctx);
+    return 0;
+  }
   const int S = padded_stride(d);
   const size_t smem = sizeof(float) * (size_t)TW * 3 * F * S;
   MMGT_CHECK_ARG((int)smem <= ctx->max_smem_optin, MMGT_E_UNSUPPORTED, "temporal_attention: smem %zu too large", smem);

@@ -151,6 +151,41 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ Wt, TD* __restri
   }
 }
 
+// Batch-sized float32 vectors (time embedding, per-resnet time projections, CLIP value/out vectors): M <= 8 rows.
+// One warp per output column, lanes stride over K with float4 loads, warp-shuffle reduction.
+constexpr int GEMV_MAX_M = 8;
+__global__ void __launch_bounds__(256)
+gemv_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ D, const float* __restrict__ bias,
+                int M, int N, int K, int64_t lda, int64_t ldw, int64_t ldd, float alpha) {
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int n = warp; n < N; n += nwarps) {
+    float acc[GEMV_MAX_M];
+#pragma unroll
+    for (int m = 0; m < GEMV_MAX_M; ++m) acc[m] = 0.f;
+    const float* w = W + (int64_t)n * ldw;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 wv = *reinterpret_cast<const float4*>(w + k);
+#pragma unroll
+      for (int m = 0; m < GEMV_MAX_M; ++m) {
+        if (m < M) {
+          const float4 av = *reinterpret_cast<const float4*>(A + (int64_t)m * lda + k);
+          acc[m] = fmaf(av.x, wv.x, acc[m]); acc[m] = fmaf(av.y, wv.y, acc[m]);
+          acc[m] = fmaf(av.z, wv.z, acc[m]); acc[m] = fmaf(av.w, wv.w, acc[m]);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < GEMV_MAX_M; ++m) {
+      if (m < M) {
+        float v = warp_sum(acc[m]);
+        if (lane == 0) D[(int64_t)m * ldd + n] = alpha * (v + (bias ? bias[n] : 0.f));
+      }
+    }
+  }
+}
+
 template <typename T, typename TD, bool CONV>
 int launch(mmgt_ctx* ctx, const void* A, const void* W, void* D, int M, int N, int K, int64_t lda, int64_t ldw,
            int64_t ldd, const Epi& ep, int gb, const ConvGeom& cg, cudaStream_t st) {
@@ -183,6 +218,14 @@ extern "C" int mmgt_gemm(mmgt_ctx* ctx, const mmgt_gemm_params* p, void* stream)
   }
   MMGT_CHECK_ARG(p->ldd >= (p->geglu_block ? p->N / 2 : p->N), MMGT_E_INVALID, "gemm: ldd too small");
   if (p->dtype == MMGT_BF16 && !p->out_f32 && ctx->use_tc && mmgt_gemm_tc_supported(ctx, p)) return mmgt_gemm_tc(ctx, p, st);
+  if (p->dtype == MMGT_F32 && p->M <= GEMV_MAX_M && !p->geglu_block && !p->rowscale && !p->rowbias && !p->residual &&
+      p->K % 4 == 0 && p->lda % 4 == 0 && p->ldw % 4 == 0 && aligned16(p->A) && aligned16(p->W)) {
+    int blocks = std::min((p->N + 7) / 8, ctx->num_sms * 8);
+    gemv_f32_kernel<<<blocks, 256, 0, st>>>((const float*)p->A, (const float*)p->W, (float*)p->D, p->bias, p->M, p->N, p->K,
+                                           p->lda, p->ldw, p->ldd, p->alpha);
+    MMGT_LAUNCH_OK(ctx);
+    return 0;
+  }
   Epi ep{p->bias, p->rowscale, p->rowbias, p->residual, p->ldr, p->rows_per_group, p->alpha};
   ConvGeom cg{};
   if (p->dtype == MMGT_F32) return launch<float, float, false>(ctx, p->A, p->W, p->D, p->M, p->N, p->K, p->lda, p->ldw, p->ldd, ep, p->geglu_block, cg, st);

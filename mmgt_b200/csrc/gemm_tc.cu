@@ -5,7 +5,7 @@
 // One persistent CTA per SM, warp-specialised:
 //   warp 0 (one lane)  TMA producer: A / W tiles -> 128B-swizzled shared memory, mbarrier complete_tx
 //   warp 1 (one lane)  tcgen05.mma issuer: 128 x BN x 16 UMMAs into a double-buffered TMEM accumulator
-//   warps 2..5         epilogue: tcgen05.ld -> bias / row-scale / row-bias / residual / GEGLU -> global stores
+//   warps 2..9         epilogue: tcgen05.ld -> bias / row-scale / row-bias / residual / GEGLU -> global stores
 // Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty pair (MMA <-> epilogue), so the epilogue
 // of tile i overlaps the main loop of tile i+1.
 //
@@ -21,7 +21,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;             // 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;            // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 __host__ __device__ constexpr int acc_stride(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
@@ -169,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);
+    mbar_init(&tmem_empty[0], 8); mbar_init(&tmem_empty[1], 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -239,63 +239,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
     }
   } else if (warp >= 2) {
-    // ===================== epilogue =====================
-    const int lane_grp = warp & 3;                 // TMEM lanes this warp may touch: 32*(warp % 4) ..
+    // ===================== epilogue (8 warps) =====================
+    // Warp w may only touch TMEM lanes 32*(w % 4)..; two warps share each lane group and split the tile's
+    // 16-column chunks between them.  The residual of the whole row segment is prefetched before the
+    // accumulator is waited for, so its global-load latency hides behind the main loop of this tile.
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = lane_grp * 32 + lane;
+    constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
+    constexpr int NCH = OUT_COLS / 16;
+    constexpr int CH0 = (NCH + 1) / 2;               // chunks of half 0; half 1 takes the rest
+    const int c_begin = half ? CH0 : 0;
+    const int c_count = half ? (NCH - CH0) : CH0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / args.num_n_tiles, n_blk = tile % args.num_n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int m = m_blk * BM + row_in_tile;
+      const bool m_ok = m < args.M;
+      const int n_out0 = n_blk * OUT_COLS;
+      uint4 resv[CH0][2];
+      const bool has_res = args.residual != nullptr && m_ok;
+      if (has_res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(args.residual + (int64_t)m * args.ldr + n_out0 + c_begin * 16);
+#pragma unroll
+        for (int i = 0; i < CH0; ++i) {
+          if (i < c_count) { resv[i][0] = rp[2 * i]; resv[i][1] = rp[2 * i + 1]; }
+        }
+      }
+      const float rs = (args.rowscale && m_ok ? args.rowscale[m] : 1.f) * args.alpha;
+      const float* rb = (args.rowbias && m_ok) ? args.rowbias + (int64_t)(m / args.rows_per_group) * args.N_out : nullptr;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(lane_grp * 32) << 16);
-      const int m = m_blk * BM + row_in_tile;
-      const bool m_ok = m < args.M;
-      const float rs = (args.rowscale && m_ok ? args.rowscale[m] : 1.f) * args.alpha;
-      const float* rb = (args.rowbias && m_ok) ? args.rowbias + (int64_t)(m / args.rows_per_group) * args.N_out : nullptr;
-      constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
-      const int n_out0 = n_blk * OUT_COLS;
-#pragma unroll 1
-      for (int c = 0; c < OUT_COLS; c += 16) {
-        uint32_t r[16];
-        float v[16];
-        tmem_ld_x16(taddr + c, r);
-        if (GEGLU) {
-          uint32_t g[16];
-          tmem_ld_x16(taddr + BN / 2 + c, g);
-          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float val = __uint_as_float(r[i]), gate = __uint_as_float(g[i]);
-            if (args.bias) {
-              val += __ldg(args.bias + n_blk * BN + c + i);
-              gate += __ldg(args.bias + n_blk * BN + BN / 2 + c + i);
+      for (int i = 0; i < CH0; ++i) {
+        if (i < c_count) {
+          const int c = (c_begin + i) * 16;
+          uint32_t r[16];
+          float v[16];
+          tmem_ld_x16(taddr + c, r);
+          if (GEGLU) {
+            uint32_t g[16];
+            tmem_ld_x16(taddr + BN / 2 + c, g);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              float val = __uint_as_float(r[e]), gate = __uint_as_float(g[e]);
+              if (args.bias) {
+                val += __ldg(args.bias + n_blk * BN + c + e);
+                gate += __ldg(args.bias + n_blk * BN + BN / 2 + c + e);
+              }
+              v[e] = val * gelu_erf_f(gate);
             }
-            v[i] = val * gelu_erf_f(gate);
-          }
-        } else {
-          tmem_ld_wait();
+          } else {
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = __uint_as_float(r[i]);
-            if (args.bias) v[i] += __ldg(args.bias + n_out0 + c + i);
+            for (int e = 0; e < 16; ++e) {
+              v[e] = __uint_as_float(r[e]);
+              if (args.bias) v[e] += __ldg(args.bias + n_out0 + c + e);
+            }
           }
-        }
-        if (m_ok) {
+          if (m_ok) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= rs;
-          if (rb) {
+            for (int e = 0; e < 16; ++e) v[e] *= rs;
+            if (rb) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __ldg(rb + n_out0 + c + i);
+              for (int e = 0; e < 16; ++e) v[e] += __ldg(rb + n_out0 + c + e);
+            }
+            if (has_res) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&resv[i][0]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float2 f = __bfloat1622float2(h[e]);
+                v[2 * e] += f.x; v[2 * e + 1] += f.y;
+              }
+            }
+            store16_bf16(args.D + (int64_t)m * args.ldd + n_out0 + c, v);
           }
-          if (args.residual) {
-            float res[16];
-            load16_bf16(args.residual + (int64_t)m * args.ldr + n_out0 + c, res);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += res[i];
-          }
-          store16_bf16(args.D + (int64_t)m * args.ldd + n_out0 + c, v);
         }
       }
       tcgen05_fence_before();
