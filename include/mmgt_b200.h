@@ -58,9 +58,10 @@ MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);
  * Replaces the rearranges at resnet.py:13, transformer_3d.py:158 and the pose add unet_3d.py:517-519. */
 MMGT_API int mmgt_ncfhw_to_tokens(mmgt_ctx*, const void* src, const void* add_or_null, void* dst, int B, int C, int F,
                          int H, int W, int src_dtype, int dst_dtype, void* stream);
-/* (B*F, H*W, C) -> (B,C,F,H,W); inverse of the above (resnet.py:15, transformer_3d.py:264). */
-MMGT_API int mmgt_tokens_to_ncfhw(mmgt_ctx*, const void* src, void* dst, int B, int C, int F, int H, int W, int src_dtype,
-                         int dst_dtype, void* stream);
+/* (B*F, H*W, src_ld >= C) -> (B,C,F,H,W); inverse of the above (resnet.py:15, transformer_3d.py:264).
+ * src_ld is the channel stride of the token tensor (0 = C); conv_out is computed with padded output channels. */
+MMGT_API int mmgt_tokens_to_ncfhw(mmgt_ctx*, const void* src, void* dst, int B, int C, int F, int H, int W, int src_ld,
+                         int src_dtype, int dst_dtype, void* stream);
 
 /* Normalisation ------------------------------------------------------------------------------ */
 /* GroupNorm over (T, C/groups) per frame on a channels-last tensor, optional fused SiLU.  The input may
@@ -101,8 +102,8 @@ typedef struct {
  * FeedForward; transformer_3d.py:176,253; resnet.py:226,243; attention.py:730-767;
  * motion_module.py:161,172). */
 MMGT_API int mmgt_gemm(mmgt_ctx*, const mmgt_gemm_params*, void* stream);
-/* N-tile width the tensor-core kernel uses for a weight with N rows (0 = none divides N).  A GEGLU weight
- * must be row-interleaved with geglu_block = mmgt_gemm_tc_block_n(N) / 2 to take the tensor-core path. */
+/* Widest N tile of the tensor-core kernel that divides N (0 = none: such weights run on the CUDA-core kernel).
+ * A GEGLU weight must be row-interleaved with geglu_block = 16 to take the tensor-core path. */
 MMGT_API int mmgt_gemm_tc_block_n(int N);
 
 typedef struct {

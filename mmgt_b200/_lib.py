@@ -46,7 +46,7 @@ SIGNATURES = {
     "mmgt_last_error": (C.c_char_p, []),
     "mmgt_ctx_flag": (c_int64, [c_void_p, c_int, c_int64]),
     "mmgt_ncfhw_to_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
-    "mmgt_tokens_to_ncfhw": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "mmgt_tokens_to_ncfhw": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "mmgt_groupnorm": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_float, c_int, c_int, c_void_p]),
     "mmgt_layernorm": (c_int, [c_void_p] * 6 + [c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "mmgt_gemm": (c_int, [c_void_p, C.POINTER(GemmParams), c_void_p]),

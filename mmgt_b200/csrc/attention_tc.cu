@@ -122,6 +122,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float ex2_approx(float x) {   // single MUFU.EX2, flush-to-zero (exp2f adds denormal fix-ups)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -273,33 +278,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[j & 1]);
 
+      if (valid < BN) {   // partial last tile of a segment: mask the keys that do not exist (warp-uniform branch)
+#pragma unroll
+        for (int i = 0; i < BN; ++i)
+          if (i >= valid) s[i] = 0xff800000u;   // -inf
+      }
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < BN; ++i) {
-        float v = __uint_as_float(s[i]);
-        if (i >= valid) { v = -INFINITY; s[i] = __float_as_uint(v); }
-        mx = fmaxf(mx, v);
-      }
+      for (int i = 0; i < BN; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
       // lazy rescale: keep the old reference unless the maximum moved by more than 2^THRESHOLD
       float alpha = 1.f;
       const bool need = (mx - m_ref) * c > RESCALE_THRESHOLD;     // true on the first tile (m_ref = -inf)
       if (need) {
-        alpha = exp2f((m_ref - mx) * c);                          // 0 on the first tile
+        alpha = ex2_approx((m_ref - mx) * c);                     // 0 on the first tile
         m_ref = mx;
       }
       const float mc = m_ref * c;
-      float lsum = 0.f;
+      float lsum0 = 0.f, lsum1 = 0.f;
       uint32_t pk[BN / 2];
 #pragma unroll
       for (int i = 0; i < BN; i += 2) {
-        float p0 = exp2f(fmaf(__uint_as_float(s[i]), c, -mc));
-        float p1 = exp2f(fmaf(__uint_as_float(s[i + 1]), c, -mc));
+        const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), c, -mc));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, -mc));
         pk[i / 2] = pack_bf16(p0, p1);
-        // accumulate the row sum from the bf16-rounded values that the PV MMA will actually use
-        __nv_bfloat162 hb = *reinterpret_cast<__nv_bfloat162*>(&pk[i / 2]);
-        float2 f = __bfloat1622float2(hb);
-        lsum += f.x + f.y;
+        lsum0 += p0;
+        lsum1 += p1;
       }
+      const float lsum = lsum0 + lsum1;
       l_run = l_run * alpha + lsum;
 
       if (j > 0) {

@@ -3,9 +3,10 @@
 
 // ---------------------------------------------------------------- NCFHW <-> tokens (tiled transpose)
 // For each (b, f): a (C x HW) matrix in src becomes (HW x C) in dst.
+// tok_ld = channel stride of the token tensor (>= C; > C when the producer padded its output channels)
 template <typename TS, typename TD, bool kToTokens>
 __global__ void ncfhw_tokens_kernel(const TS* __restrict__ src, const TS* __restrict__ add, TD* __restrict__ dst,
-                                    int B, int C, int F, int HW) {
+                                    int B, int C, int F, int HW, int tok_ld) {
   __shared__ float tile[32][33];
   const int bf = blockIdx.z;
   const int b = bf / F, f = bf % F;
@@ -26,13 +27,13 @@ __global__ void ncfhw_tokens_kernel(const TS* __restrict__ src, const TS* __rest
 #pragma unroll
     for (int i = 0; i < 32; i += 8) {
       int t = t0 + ty + i, c = c0 + tx;
-      if (c < C && t < HW) dst[((size_t)bf * HW + t) * C + c] = from_f32<TD>(tile[tx][ty + i]);
+      if (c < C && t < HW) dst[((size_t)bf * HW + t) * tok_ld + c] = from_f32<TD>(tile[tx][ty + i]);
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 32; i += 8) {
       int t = t0 + ty + i, c = c0 + tx;
-      if (c < C && t < HW) tile[ty + i][tx] = to_f32(src[((size_t)bf * HW + t) * C + c]);
+      if (c < C && t < HW) tile[ty + i][tx] = to_f32(src[((size_t)bf * HW + t) * tok_ld + c]);
     }
     __syncthreads();
 #pragma unroll
@@ -45,12 +46,14 @@ __global__ void ncfhw_tokens_kernel(const TS* __restrict__ src, const TS* __rest
 
 template <bool kToTokens>
 static int launch_layout(mmgt_ctx* ctx, const void* src, const void* add, void* dst, int B, int C, int F, int H,
-                         int W, int sdt, int ddt, cudaStream_t st) {
+                         int W, int sdt, int ddt, int tok_ld, cudaStream_t st) {
   MMGT_CHECK_ARG(src && dst && B > 0 && C > 0 && F > 0 && H > 0 && W > 0, MMGT_E_INVALID, "layout: bad args");
   MMGT_CHECK_ARG((size_t)B * F <= 65535, MMGT_E_INVALID, "layout: B*F too large");
+  if (tok_ld <= 0) tok_ld = C;
+  MMGT_CHECK_ARG(tok_ld >= C, MMGT_E_INVALID, "layout: token channel stride %d < C=%d", tok_ld, C);
   int HW = H * W;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B * F), block(32, 8);
-#define L(TS, TD) ncfhw_tokens_kernel<TS, TD, kToTokens><<<grid, block, 0, st>>>((const TS*)src, (const TS*)add, (TD*)dst, B, C, F, HW)
+#define L(TS, TD) ncfhw_tokens_kernel<TS, TD, kToTokens><<<grid, block, 0, st>>>((const TS*)src, (const TS*)add, (TD*)dst, B, C, F, HW, tok_ld)
   if (sdt == MMGT_F32 && ddt == MMGT_F32) L(float, float);
   else if (sdt == MMGT_F32 && ddt == MMGT_BF16) L(float, bf16);
   else if (sdt == MMGT_BF16 && ddt == MMGT_F32) L(bf16, float);
@@ -63,11 +66,11 @@ static int launch_layout(mmgt_ctx* ctx, const void* src, const void* add, void* 
 
 extern "C" int mmgt_ncfhw_to_tokens(mmgt_ctx* ctx, const void* src, const void* add, void* dst, int B, int C, int F,
                                     int H, int W, int sdt, int ddt, void* stream) {
-  return launch_layout<true>(ctx, src, add, dst, B, C, F, H, W, sdt, ddt, (cudaStream_t)stream);
+  return launch_layout<true>(ctx, src, add, dst, B, C, F, H, W, sdt, ddt, C, (cudaStream_t)stream);
 }
 extern "C" int mmgt_tokens_to_ncfhw(mmgt_ctx* ctx, const void* src, void* dst, int B, int C, int F, int H, int W,
-                                    int sdt, int ddt, void* stream) {
-  return launch_layout<false>(ctx, src, nullptr, dst, B, C, F, H, W, sdt, ddt, (cudaStream_t)stream);
+                                    int src_ld, int sdt, int ddt, void* stream) {
+  return launch_layout<false>(ctx, src, nullptr, dst, B, C, F, H, W, sdt, ddt, src_ld, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- nearest x2 upsample, channels-last

@@ -246,6 +246,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lane_grp = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row_in_tile = lane_grp * 32 + lane;
+    // GEGLU weights are row-interleaved in blocks of 16: tile columns [32p, 32p+16) hold "value" and
+    // [32p+16, 32p+32) the matching "gate" columns of output columns [16p, 16p+16) of this tile.
     constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
     constexpr int NCH = OUT_COLS / 16;
     constexpr int CH0 = (NCH + 1) / 2;               // chunks of half 0; half 1 takes the rest
@@ -279,17 +281,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int c = (c_begin + i) * 16;
           uint32_t r[16];
           float v[16];
-          tmem_ld_x16(taddr + c, r);
+          tmem_ld_x16(taddr + (GEGLU ? 2 * c : c), r);
           if (GEGLU) {
             uint32_t g[16];
-            tmem_ld_x16(taddr + BN / 2 + c, g);
+            tmem_ld_x16(taddr + 2 * c + 16, g);
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               float val = __uint_as_float(r[e]), gate = __uint_as_float(g[e]);
               if (args.bias) {
-                val += __ldg(args.bias + n_blk * BN + c + e);
-                gate += __ldg(args.bias + n_blk * BN + BN / 2 + c + e);
+                val += __ldg(args.bias + n_blk * BN + 2 * c + e);
+                gate += __ldg(args.bias + n_blk * BN + 2 * c + 16 + e);
               }
               v[e] = val * gelu_erf_f(gate);
             }
@@ -377,6 +379,20 @@ int pick_bn(int N) {
     if (N % cand[i] == 0) return cand[i];
   return 0;
 }
+// Largest tile width dividing N that still yields at least one tile per SM; small-M layers (16x16 / 8x8 latents)
+// otherwise leave most of the 148 SMs idle.  Falls back to the width with the most tiles.
+int pick_bn_for(int N, int M, int num_sms) {
+  const int cand[5] = {256, 160, 128, 64, 32};
+  const int m_tiles = (M + BM - 1) / BM;
+  int best = 0;
+  for (int i = 0; i < 5; ++i) {
+    if (N % cand[i]) continue;
+    best = cand[i];
+    if (m_tiles * (N / cand[i]) >= num_sms) return cand[i];
+    if (cand[i] <= 64) break;      // do not go below 64 just to add tiles (B-operand re-reads grow)
+  }
+  return best;
+}
 
 template <int BN, bool CONV, bool GEGLU>
 int launch_tc(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
@@ -422,7 +438,7 @@ bool mmgt_gemm_tc_supported(const mmgt_ctx* ctx, const mmgt_gemm_params* p) {
   if (p->dtype != MMGT_BF16 || p->out_f32) return false;
   const int bn = pick_bn(p->N);
   if (!bn) return false;
-  if (p->geglu_block && p->geglu_block * 2 != bn) return false;
+  if (p->geglu_block && p->geglu_block != 16) return false;
   if (p->K % 8 || p->lda % 8 || p->ldw % 8) return false;
   if (!aligned16(p->A) || !aligned16(p->W) || !aligned16(p->D)) return false;
   const int n_out = p->geglu_block ? p->N / 2 : p->N;
@@ -433,7 +449,7 @@ bool mmgt_gemm_tc_supported(const mmgt_ctx* ctx, const mmgt_gemm_params* p) {
 }
 
 int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
-  const int bn = pick_bn(p->N);
+  const int bn = pick_bn_for(p->N, p->M, ctx->num_sms);
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->M};
@@ -491,7 +507,7 @@ bool mmgt_conv3x3_tc_supported(const mmgt_ctx* ctx, const mmgt_conv3x3_params* p
 }
 
 int mmgt_conv3x3_tc(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, cudaStream_t st) {
-  const int bn = pick_bn(p->Cout);
+  const int bn = pick_bn_for(p->Cout, p->N * p->H * p->W, ctx->num_sms);
   uint32_t bw, bh, bf;
   conv_box(p, &bw, &bh, &bf);
   CUtensorMap tmA, tmB;

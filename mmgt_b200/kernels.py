@@ -76,9 +76,11 @@ class Engine:
         return self._stats_ws
 
     def geglu_block(self, n_rows: int) -> int:
-        """Row-interleave granularity a GEGLU weight with ``n_rows`` rows should be packed with."""
-        bn = self.lib.mmgt_gemm_tc_block_n(int(n_rows)) if self.dtype == torch.bfloat16 else 0
-        return bn // 2 if bn else n_rows // 2
+        """Row-interleave granularity a GEGLU weight with ``n_rows`` rows should be packed with: 16 for the
+        tensor-core kernel (any N-tile width then holds matching value / gate columns), else the natural halves."""
+        if self.dtype == torch.bfloat16 and n_rows % 32 == 0 and self.lib.mmgt_gemm_tc_block_n(int(n_rows)):
+            return 16
+        return n_rows // 2
 
     # ------------------------------------------------------------------ layout
     def ncfhw_to_tokens(self, x: torch.Tensor, add: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -94,10 +96,13 @@ class Engine:
         return out
 
     def tokens_to_ncfhw(self, x: torch.Tensor, B: int, F: int, out_dtype: torch.dtype) -> torch.Tensor:
+        """x: (N, H, W, C) tokens; the channel dim may be a slice of a wider (padded) buffer."""
         N, H, W, Cc = x.shape
+        ld = x.stride(2)
+        assert x.stride(3) == 1 and x.stride(1) == W * ld and x.stride(0) == H * W * ld
         out = torch.empty((B, Cc, F, H, W), device=self.device, dtype=out_dtype)
-        check(self.lib.mmgt_tokens_to_ncfhw(self.h, _p(x), _p(out), B, Cc, F, H, W, self.dt, dt_code(out_dtype), _stream()),
-              "mmgt_tokens_to_ncfhw")
+        check(self.lib.mmgt_tokens_to_ncfhw(self.h, _p(x), _p(out), B, Cc, F, H, W, ld, self.dt, dt_code(out_dtype),
+                                             _stream()), "mmgt_tokens_to_ncfhw")
         return out
 
     # ------------------------------------------------------------------ norms

@@ -58,8 +58,13 @@ class DenoiseLoop:
         self.latents = latents.to(torch.float32).contiguous().clone()
         cf, cs, co = self.ctx_args
         self.windows = [list(map(int, c)) for c in self.context_scheduler(0, self.n_steps, L, cf, cs, co)]
-        # (window, branch) units of this rank
-        units = [(wi, b) for wi in range(len(self.windows)) for b in range(nb)]
+        # Work units of this rank.  Whole windows (both CFG branches batched as one B=2 forward: larger GEMM M) when the
+        # windows divide evenly over the ranks, otherwise single (window, branch) forwards for a finer deal.
+        nw = len(self.windows)
+        if nb == 2 and nw % self.world == 0:
+            units = [(wi, (0, 1)) for wi in range(nw)]
+        else:
+            units = [(wi, (b,)) for wi in range(nw) for b in range(nb)]
         self.units = units[self.rank::self.world]
         counts = torch.zeros(L, dtype=torch.float32)
         for c in self.windows:
@@ -73,32 +78,33 @@ class DenoiseLoop:
         audio_all = audio.to(device=dev, dtype=eng.dtype).contiguous()                   # (nb,L,M,768)
         ehs = encoder_hidden_states.to(dev)
         masks = [[m.to(device=dev, dtype=torch.float32).contiguous() for m in ms] for ms in (full_mask, face_mask, lip_mask)]
-        self.win = []
-        for c in self.windows:
+        mask_pads = [[_pad16(m) for m in ms] for ms in masks]
+        self.prepared = []
+        for wi, branches in self.units:
+            c = self.windows[wi]
             idx = torch.tensor(c, dtype=torch.int32, device=dev)
-            entry = dict(idx=idx, pose=eng.gather_rows(pose_tok, idx) if pose_tok is not None else None, per_branch=[])
-            for b in range(nb):
-                rows = idx + b * L
-                aud = eng.gather_rows(audio_all.view(nb * L, -1), rows).view(1, len(c), audio_all.shape[2], audio_all.shape[3])
-                mk = [[eng.gather_rows(_pad16(m), rows)[:, : m.shape[1]].contiguous() for m in ms] for ms in masks]
-                entry["per_branch"].append(dict(audio=aud, masks=mk, ehs=ehs[b:b + 1]))
-            self.win.append(entry)
+            nbr = len(branches)
+            x_idx = idx.repeat(nbr)                                                      # latents / pose rows (frames)
+            rows = torch.cat([idx + b * L for b in branches])                            # rows of the (nb*L, ...) tensors
+            aud = eng.gather_rows(audio_all.view(nb * L, -1), rows).view(nbr, len(c), audio_all.shape[2], audio_all.shape[3])
+            mk = [[eng.gather_rows(mp, rows)[:, : m.shape[1]].contiguous() for mp, m in zip(mps, ms)]
+                  for mps, ms in zip(mask_pads, masks)]
+            ref = [None if (self.cfg and b == 0) else b for b in branches]
+            self.prepared.append(dict(idx=idx, x_idx=x_idx, frames=len(c), branches=branches,
+                                      pose=eng.gather_rows(pose_tok, x_idx) if pose_tok is not None else None,
+                                      audio=aud, masks=mk, ehs=ehs[list(branches)].contiguous(), ref=ref))
         return self
 
     # ------------------------------------------------------------------ the hot loop
     def _forward_units(self, lat_tok):
         eng, u = self.eng, self.unet
-        F_ = None
-        for wi, b in self.units:
-            e = self.win[wi]
-            pb = e["per_branch"][b]
-            F_ = e["idx"].numel()
-            x = eng.gather_rows(lat_tok, e["idx"])
-            ref = [None] if (self.cfg and b == 0) else [b]
-            out = u.forward_tokens(eng, x, self.t_dev, pb["ehs"], pb["audio"], e["pose"], pb["masks"][0], pb["masks"][1],
-                                   pb["masks"][2], self.motion_scale, 1, F_, ref_index=ref)
-            pred = eng.tokens_to_ncfhw(out, 1, F_, torch.float32)
-            eng.window_accumulate(self.noise_acc, pred, e["idx"], b)
+        for e in self.prepared:
+            x = eng.gather_rows(lat_tok, e["x_idx"])
+            nbr, F_ = len(e["branches"]), e["frames"]
+            out = u.forward_tokens(eng, x, self.t_dev, e["ehs"], e["audio"], e["pose"], e["masks"][0], e["masks"][1],
+                                   e["masks"][2], self.motion_scale, nbr, F_, ref_index=e["ref"])
+            pred = eng.tokens_to_ncfhw(out, nbr, F_, torch.float32)
+            eng.window_accumulate(self.noise_acc, pred, e["idx"], e["branches"][0])
 
     def _units_body(self):
         """Everything of a step that does not depend on host scalars: zero the accumulator, re-layout the latents,

@@ -29,11 +29,22 @@ class InflatedConv3d(nn.Conv2d):
 
     def packed(self, eng: Engine):
         def build():
+            b = f32(self.bias, eng) if self.bias is not None else None
             if self.kernel_size == (3, 3):
                 w = conv_krsc(self.weight, eng)
+                cout = w.shape[0]
+                if eng.dtype == torch.bfloat16 and cout < 32 and w.shape[-1] % 64 == 0:
+                    # conv_out (320 -> 4): pad the output channels to 32 so the tensor-core implicit GEMM takes it
+                    wp = torch.zeros((32,) + tuple(w.shape[1:]), device=w.device, dtype=w.dtype)
+                    wp[:cout] = w
+                    w = wp
+                    if b is not None:
+                        bp = torch.zeros(32, device=b.device, dtype=b.dtype)
+                        bp[:cout] = b
+                        b = bp
             else:
                 w = conv1x1(self.weight, eng)
-            return w, (f32(self.bias, eng) if self.bias is not None else None)
+            return w, b
         return self._pack.get(eng, [self.weight] + ([self.bias] if self.bias is not None else []), build)
 
     def run(self, eng: Engine, x, rowbias=None, frames_per_group=0, residual=None, upsample2x=False):
@@ -41,8 +52,10 @@ class InflatedConv3d(nn.Conv2d):
         if self.kernel_size == (3, 3):
             if self.padding != (1, 1):
                 raise NotImplementedError("InflatedConv3d: only padding=1 is implemented for 3x3 kernels")
-            return eng.conv3x3(x, w, bias=b, rowbias=rowbias, frames_per_group=frames_per_group, residual=residual,
-                               stride=self.stride[0], upsample2x=upsample2x)
+            y = eng.conv3x3(x, w, bias=b, rowbias=rowbias, frames_per_group=frames_per_group, residual=residual,
+                            stride=self.stride[0], upsample2x=upsample2x)
+            # padded output channels: return the real ones as a strided view (consumers take a channel stride)
+            return y if y.shape[-1] == self.out_channels else y[..., : self.out_channels]
         if self.kernel_size != (1, 1) or self.stride != (1, 1):
             raise NotImplementedError("InflatedConv3d: only 3x3 and 1x1 kernels are implemented")
         N, H, W, C = x.shape
