@@ -20,7 +20,7 @@
 namespace {
 
 constexpr int BQ = 128;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 2 x 4 softmax warps
 constexpr int KV_STAGES = 2;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 
@@ -132,7 +132,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// DCH = ceil(d / 64) head-dim chunks (d_pad = 64 * DCH); BN = keys per tile
+// DCH = ceil(d / 64) head-dim chunks (d_pad = 64 * DCH); BN = keys per tile.
+// Two independent softmax groups (warps 2-5 and 6-9) take alternate key tiles, each with its own running
+// maximum / row sum and its own O accumulator in TMEM (split-KV inside the CTA); the halves are merged in the
+// epilogue.  With two warps per scheduler the TMEM-load, MUFU and shared-store phases of the groups overlap.
 template <int DCH, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -142,11 +145,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr int Q_BYTES = BQ * DPAD * 2;
   constexpr int KV_BYTES = BN * DPAD * 2;        // one K (or V) stage
   constexpr int KV_CHUNK = BN * 128;             // bytes of one 64-wide d chunk of a K/V stage
-  constexpr int P_BYTES = BQ * BN * 2;
-  constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256;
+  constexpr int P_BYTES = BQ * BN * 2;           // one P buffer (per softmax group)
+  constexpr int TM_S = 0, TM_O = 2 * BN;         // S buffers at 0 / BN, O accumulators at 2BN / 2BN + DPAD
   constexpr uint32_t IDESC_QK = idesc_bf16(BN, false);
   constexpr uint32_t IDESC_PV = idesc_bf16(DPAD, true);
-  static_assert(TM_O + DPAD <= 512, "TMEM budget");
+  static_assert(TM_O + 2 * DPAD <= 512, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -154,17 +157,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sK = sQ + Q_BYTES;
   uint8_t* sV = sK + KV_STAGES * KV_BYTES;
   uint8_t* sP = sV + KV_STAGES * KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  float* stats = reinterpret_cast<float*>(sP + 2 * P_BYTES);          // [128][2]: (m_ref, l) of group 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 2 * BQ);
   uint64_t* q_full = bars;                     // 1
   uint64_t* k_full = bars + 1;                 // KV_STAGES
   uint64_t* k_empty = k_full + KV_STAGES;
   uint64_t* v_full = k_empty + KV_STAGES;
   uint64_t* v_empty = v_full + KV_STAGES;
-  uint64_t* s_full = v_empty + KV_STAGES;      // 2
+  uint64_t* s_full = v_empty + KV_STAGES;      // 2 (buffer == group == tile parity)
   uint64_t* s_empty = s_full + 2;              // 2
-  uint64_t* p_full = s_empty + 2;              // 1
-  uint64_t* p_empty = p_full + 1;              // 1  (== "PV_j retired": P buffer free and O stable)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 1);
+  uint64_t* p_full = s_empty + 2;              // 2
+  uint64_t* p_empty = p_full + 2;              // 2  ("PV of this group's tile retired": P buffer free, O_g stable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
@@ -180,10 +184,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
-    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-    mbar_init(&s_empty[0], 4); mbar_init(&s_empty[1], 4);
-    mbar_init(p_full, 128);
-    mbar_init(p_empty, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 4); mbar_init(&p_full[g], 4); mbar_init(&p_empty[g], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -219,11 +222,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else if (threadIdx.x == 32) {
     // ===================== MMA issuer =====================
     auto issue_qk = [&](int j) {
-      const int st = j % KV_STAGES;
+      const int st = j % KV_STAGES, g = j & 1;
       mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
-      mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+      mbar_wait(&s_empty[g], ((j >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t tS = tmem_base + ((j & 1) ? TM_S1 : TM_S0);
+      const uint32_t tS = tmem_base + TM_S + g * BN;
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + st * KV_BYTES);
 #pragma unroll
       for (int k = 0; k < DPAD / 16; ++k) {
@@ -231,61 +234,69 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         umma(tS, desc_kmajor(aQ + offq), desc_kmajor(aK + offk), IDESC_QK, k != 0);
       }
       umma_commit(&k_empty[st]);
-      umma_commit(&s_full[j & 1]);
+      umma_commit(&s_full[g]);
     };
     mbar_wait(q_full, 0);
     issue_qk(0);
     for (int j = 0; j < num_tiles; ++j) {
       if (j + 1 < num_tiles) issue_qk(j + 1);
-      const int st = j % KV_STAGES;
+      const int st = j % KV_STAGES, g = j & 1;
       mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
-      mbar_wait(p_full, j & 1);
+      mbar_wait(&p_full[g], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t aP = smem_u32(sP), aV = smem_u32(sV + st * KV_BYTES);
+      const uint32_t aP = smem_u32(sP + g * P_BYTES), aV = smem_u32(sV + st * KV_BYTES);
 #pragma unroll
       for (int k = 0; k < BN / 16; ++k) {
         // A = P: K-major, 64-key chunks of (128 rows x 128 B); B = V: MN-major, 16 keys = 2 x 1024 B per step
         const uint32_t offp = (k / 4) * (BQ * 128) + (k % 4) * 32;
-        umma(tmem_base + TM_O, desc_kmajor(aP + offp), desc_mnmajor(aV + k * 2048, KV_CHUNK), IDESC_PV, (j | k) != 0);
+        umma(tmem_base + TM_O + g * DPAD, desc_kmajor(aP + offp), desc_mnmajor(aV + k * 2048, KV_CHUNK), IDESC_PV,
+             ((j >> 1) | k) != 0);
       }
       umma_commit(&v_empty[st]);
-      umma_commit(p_empty);
+      umma_commit(&p_empty[g]);
     }
   } else if (warp >= 2) {
-    // ===================== softmax / correction / epilogue =====================
+    // ===================== softmax groups / merge / epilogue =====================
+    const int g = (warp - 2) >> 2;                   // softmax group: tiles j = g, g+2, ...
     const int lane_grp = warp & 3;
     const int row = lane_grp * 32 + lane;            // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
     const float c = args.scale_log2e;
-    float m_ref = -INFINITY;   // reference maximum the stored O / l are relative to (raw score units)
+    float m_ref = -INFINITY;   // reference maximum the stored O_g / l are relative to (raw score units)
     float l_run = 0.f;
-    uint8_t* prow = sP + row * 128;
+    uint8_t* prow = sP + g * P_BYTES + row * 128;
     const int sw = row & 7;
+    const uint32_t tO = tmem_base + TM_O + g * DPAD + lane_addr;
+    int it = 0;
 
-    for (int j = 0; j < num_tiles; ++j) {
+    for (int j = g; j < num_tiles; j += 2, ++it) {
       const bool second = j >= tiles1;
       const int seg_len = second ? args.Lk2 : args.Lk;
       const int k0 = (second ? (j - tiles1) : j) * BN;
       const int valid = min(BN, seg_len - k0);       // keys of this tile that exist
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[g], it & 1);
       tc_fence_after();
       uint32_t s[BN];
-      const uint32_t tS = tmem_base + ((j & 1) ? TM_S1 : TM_S0) + lane_addr;
+      const uint32_t tS = tmem_base + TM_S + g * BN + lane_addr;
 #pragma unroll
       for (int i = 0; i < BN / 32; ++i) tmem_ld32(tS + i * 32, s + i * 32);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[j & 1]);
+      if (lane == 0) mbar_arrive(&s_empty[g]);
 
       if (valid < BN) {   // partial last tile of a segment: mask the keys that do not exist (warp-uniform branch)
 #pragma unroll
         for (int i = 0; i < BN; ++i)
           if (i >= valid) s[i] = 0xff800000u;   // -inf
       }
-      float mx = -INFINITY;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains: no serial latency
 #pragma unroll
-      for (int i = 0; i < BN; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      for (int i = 0; i < BN; i += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(s[i + e]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       // lazy rescale: keep the old reference unless the maximum moved by more than 2^THRESHOLD
       float alpha = 1.f;
       const bool need = (mx - m_ref) * c > RESCALE_THRESHOLD;     // true on the first tile (m_ref = -inf)
@@ -294,31 +305,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         m_ref = mx;
       }
       const float mc = m_ref * c;
-      float lsum0 = 0.f, lsum1 = 0.f;
+      float lsum[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[BN / 2];
 #pragma unroll
-      for (int i = 0; i < BN; i += 2) {
+      for (int i = 0; i < BN; i += 4) {
         const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), c, -mc));
         const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, -mc));
+        const float p2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), c, -mc));
+        const float p3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), c, -mc));
         pk[i / 2] = pack_bf16(p0, p1);
-        lsum0 += p0;
-        lsum1 += p1;
+        pk[i / 2 + 1] = pack_bf16(p2, p3);
+        lsum[0] += p0; lsum[1] += p1; lsum[2] += p2; lsum[3] += p3;
       }
-      const float lsum = lsum0 + lsum1;
-      l_run = l_run * alpha + lsum;
+      l_run = l_run * alpha + ((lsum[0] + lsum[1]) + (lsum[2] + lsum[3]));
 
-      if (j > 0) {
-        mbar_wait(p_empty, (j - 1) & 1);   // PV_{j-1} retired: P buffer reusable, O stable
+      if (it > 0) {
+        mbar_wait(&p_empty[g], (it - 1) & 1);   // this group's previous PV retired: P buffer reusable, O_g stable
         tc_fence_after();
         if (__any_sync(0xffffffffu, need)) {
 #pragma unroll
           for (int cc = 0; cc < DPAD / 32; ++cc) {
             uint32_t o[32];
-            tmem_ld32(tmem_base + TM_O + lane_addr + cc * 32, o);
+            tmem_ld32(tO + cc * 32, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tmem_base + TM_O + lane_addr + cc * 32, o);
+            tmem_st32(tO + cc * 32, o);
           }
           tmem_st_wait();
         }
@@ -332,31 +344,54 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
     }
 
-    // ---- epilogue: O / l -> global (only the first d columns are real)
-    mbar_wait(p_empty, (num_tiles - 1) & 1);
+    // ---- merge the two groups and store O / l (only the first d columns are real)
+    if (it > 0) {
+      mbar_wait(&p_empty[g], (it - 1) & 1);
+      tc_fence_after();
+    }
+    if (g == 1) {
+      stats[2 * row] = m_ref;
+      stats[2 * row + 1] = l_run;
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 softmax warps
     tc_fence_after();
-    const float inv = 1.f / l_run;
-    const int q = q0 + row;
-    bf16* orow = args.out + ((int64_t)n * args.Lq + q) * args.ldo + h * args.d;
+    if (g == 0) {
+      const float m1 = stats[2 * row], l1 = stats[2 * row + 1];
+      const bool has1 = num_tiles > 1;                 // group 1 processed at least one tile (uniform)
+      const float m = has1 ? fmaxf(m_ref, m1) : m_ref;
+      const float a0 = ex2_approx((m_ref - m) * c);
+      const float a1 = has1 ? ex2_approx((m1 - m) * c) : 0.f;
+      const float inv = 1.f / (l_run * a0 + (has1 ? l1 * a1 : 0.f));
+      const float w0 = a0 * inv, w1 = a1 * inv;
+      const int q = q0 + row;
+      bf16* orow = args.out + ((int64_t)n * args.Lq + q) * args.ldo + h * args.d;
+      const uint32_t tO0 = tmem_base + TM_O + lane_addr, tO1 = tO0 + DPAD;
 #pragma unroll
-    for (int cc = 0; cc < DPAD / 32; ++cc) {
-      uint32_t o[32];
-      tmem_ld32(tmem_base + TM_O + lane_addr + cc * 32, o);
-      tmem_ld_wait();
-      if (q < args.Lq) {
+      for (int cc = 0; cc < DPAD / 32; ++cc) {
+        uint32_t o[32], o1[32];
+        tmem_ld32(tO0 + cc * 32, o);
+        if (has1) tmem_ld32(tO1 + cc * 32, o1);
+        tmem_ld_wait();
+        float f[32];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = cc * 32 + g * 8;
-          if (col < args.d) {
-            uint4 val;
-            val.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
-            val.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
-            val.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
-            val.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + col) = val;
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(o[i]) * w0 + (has1 ? __uint_as_float(o1[i]) * w1 : 0.f);
+        if (q < args.Lq) {
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            const int col = cc * 32 + gg * 8;
+            if (col < args.d) {
+              uint4 val;
+              val.x = pack_bf16(f[gg * 8 + 0], f[gg * 8 + 1]);
+              val.y = pack_bf16(f[gg * 8 + 2], f[gg * 8 + 3]);
+              val.z = pack_bf16(f[gg * 8 + 4], f[gg * 8 + 5]);
+              val.w = pack_bf16(f[gg * 8 + 6], f[gg * 8 + 7]);
+              *reinterpret_cast<uint4*>(orow + col) = val;
+            }
           }
         }
       }
@@ -405,7 +440,7 @@ int encode_qkv_map(mmgt_ctx* ctx, CUtensorMap* map, const void* base, int d, int
 
 template <int DCH, int BN>
 int launch_attn(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaStream_t st) {
-  constexpr int smem = BQ * 64 * DCH * 2 + 2 * KV_STAGES * BN * 64 * DCH * 2 + BQ * BN * 2 + 1024 + 256;
+  constexpr int smem = BQ * 64 * DCH * 2 + 2 * KV_STAGES * BN * 64 * DCH * 2 + 2 * BQ * BN * 2 + BQ * 8 + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     MMGT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<DCH, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
