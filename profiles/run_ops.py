@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Launch the hot kernels once each at BASELINE config-2 shapes (one B=2 window: 24 frames of 64x64 latent).
+
+Used under ncu (``--profile-from-start off``: only the region between cudaProfilerStart/Stop is captured):
+
+  ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -o gpurun_out/ops python profiles/run_ops.py [op ...]
+
+and standalone to event-time each op (``--time``), L2 flushed between repetitions.
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from mmgt_b200.kernels import get_engine  # noqa: E402
+from mmgt_b200.packing import geglu_interleave  # noqa: E402
+
+
+def make_ops(eng, dev):
+    bf = torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(0)
+
+    def rnd(*shape, dtype=bf, scale=1.0):
+        return (torch.randn(*shape, generator=g) * scale).to(device=dev, dtype=dtype)
+
+    ops = {}
+    N, T0 = 24, 4096
+    # ---- spatial attention, level 0 (d = 40), [self ; reference] keys for the cond half
+    for name, C, T in (("attn_d40", 320, 4096), ("attn_d80", 640, 1024), ("attn_d160", 1280, 256)):
+        qkv = rnd(N, T, 3 * C)
+        kv2 = rnd(2, T, 2 * C)
+        seg2 = torch.tensor([-1] * 12 + [1] * 12, dtype=torch.int32, device=dev)
+        ops[name] = (lambda qkv=qkv, kv2=kv2, seg2=seg2, C=C: eng.attention(
+            qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], 8, k2=kv2[:, :, :C], v2=kv2[:, :, C:], seg2_index=seg2),
+            4.0 * 8 * T * (12 * T + 12 * 2 * T) * (C // 8), 0.0)
+    qkv = rnd(N, T0, 960)
+    ops["attn_d40_self"] = (lambda: eng.attention(qkv[:, :, :320], qkv[:, :, 320:640], qkv[:, :, 640:], 8),
+                            4.0 * 8 * N * T0 * T0 * 40, 0.0)
+    # ---- MM-HAA audio cross attention (Lk = 32)
+    q3 = rnd(N, T0, 960)
+    kv6 = rnd(N, 32, 1920)
+    ops["attn_audio_d40"] = (lambda: eng.attention(q3[:, :, :320], kv6[:, :, :320], kv6[:, :, 320:640], 8),
+                             4.0 * 8 * N * T0 * 32 * 40, 2.0 * N * T0 * 320 * 2)
+    # ---- GEMMs (rows = 24 * 4096)
+    M = N * T0
+    a320 = rnd(M, 320)
+    res320 = rnd(M, 320)
+    w = rnd(320, 320, scale=0.05)
+    b = rnd(320, dtype=torch.float32)
+    ops["gemm_320x320_res"] = (lambda: eng.gemm(a320, w, bias=b, residual=res320), 2.0 * M * 320 * 320, 3.0 * M * 320 * 2)
+    wq = rnd(960, 320, scale=0.05)
+    ops["gemm_960x320"] = (lambda: eng.gemm(a320, wq), 2.0 * M * 960 * 320, (M * 320 + M * 960) * 2.0)
+    w1 = torch.randn(2560, 320, generator=g) * 0.05
+    b1 = torch.randn(2560, generator=g)
+    gb = eng.geglu_block(2560)
+    w1i, b1i = geglu_interleave(w1, b1, gb)
+    w1i, b1i = w1i.to(dev, bf).contiguous(), b1i.to(dev, torch.float32).contiguous()
+    ops["gemm_geglu_2560x320"] = (lambda: eng.gemm(a320, w1i, bias=b1i, geglu_block=gb), 2.0 * M * 2560 * 320,
+                                  (M * 320 + M * 1280) * 2.0)
+    a1280 = rnd(M, 1280)
+    w2 = rnd(320, 1280, scale=0.05)
+    ops["gemm_320x1280_res"] = (lambda: eng.gemm(a1280, w2, bias=b, residual=res320), 2.0 * M * 320 * 1280,
+                                (M * 1280 + 2 * M * 320) * 2.0)
+    M2 = N * 256
+    a2 = rnd(M2, 1280)
+    w3 = rnd(1280, 1280, scale=0.05)
+    b3 = rnd(1280, dtype=torch.float32)
+    r3 = rnd(M2, 1280)
+    ops["gemm_1280x1280_res_m6144"] = (lambda: eng.gemm(a2, w3, bias=b3, residual=r3), 2.0 * M2 * 1280 * 1280,
+                                       (3.0 * M2 * 1280 + 1280 * 1280) * 2)
+    # ---- norms
+    gam, bet = rnd(320, dtype=torch.float32), rnd(320, dtype=torch.float32)
+    ops["layernorm_320"] = (lambda: eng.layernorm(a320, gam, bet), 0.0, 2.0 * M * 320 * 2)
+    x4 = rnd(N, 64, 64, 320)
+    ops["groupnorm_320_silu"] = (lambda: eng.groupnorm(x4, None, gam, bet, 32, 1e-5, True), 0.0, 2.0 * M * 320 * 2)
+    x4b = rnd(N, 16, 16, 1280)
+    g2, be2 = rnd(1280, dtype=torch.float32), rnd(1280, dtype=torch.float32)
+    ops["groupnorm_1280_silu"] = (lambda: eng.groupnorm(x4b, None, g2, be2, 32, 1e-5, True), 0.0, 2.0 * M2 * 1280 * 2)
+    # ---- conv 3x3
+    wc = rnd(320, 3, 3, 320, scale=0.02)
+    ops["conv3x3_320_320"] = (lambda: eng.conv3x3(x4, wc, bias=b, residual=x4), 2.0 * M * 9 * 320 * 320,
+                              3.0 * M * 320 * 2)
+    wc2 = rnd(1280, 3, 3, 1280, scale=0.02)
+    ops["conv3x3_1280_1280"] = (lambda: eng.conv3x3(x4b, wc2, bias=b3, residual=x4b), 2.0 * M2 * 9 * 1280 * 1280,
+                                (3.0 * M2 * 1280 + 9 * 1280 * 1280) * 2)
+    # ---- temporal attention
+    tq = rnd(M, 960)
+    ops["temporal_attn_d40"] = (lambda: eng.temporal_attention(tq, 2, 12, T0, 8), 4.0 * 2 * T0 * 8 * 144 * 40,
+                                (M * 960 + M * 320) * 2.0)
+    return ops
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("ops", nargs="*")
+    ap.add_argument("--time", action="store_true")
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    eng = get_engine(dev, torch.bfloat16)
+    ops = make_ops(eng, dev)
+    names = args.ops or list(ops)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    for n in names:          # warm-up (cudaFuncSetAttribute, descriptor paths, allocator)
+        for _ in range(2):
+            ops[n][0]()
+    torch.cuda.synchronize()
+    if args.time:
+        for n in names:
+            fn, flops, nbytes = ops[n]
+            ts = []
+            for _ in range(args.reps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            ms = ts[len(ts) // 2]
+            print(f"{n:28s} {ms * 1e3:9.1f} us  {flops / ms / 1e9:8.1f} TFLOP/s  {nbytes / ms / 1e6:8.1f} GB/s", flush=True)
+        return
+    torch.cuda.cudart().cudaProfilerStart()
+    for n in names:
+        flush.zero_()
+        torch.cuda.nvtx.range_push(n)
+        ops[n][0]()
+        torch.cuda.nvtx.range_pop()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+
+
+if __name__ == "__main__":
+    main()
