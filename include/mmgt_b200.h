@@ -50,7 +50,8 @@ MMGT_API int mmgt_ctx_destroy(mmgt_ctx* ctx);
 /* Last error message of the calling thread (static storage, never NULL). */
 MMGT_API const char* mmgt_last_error(void);
 /* flag 0: enable (1) / disable (0) the tcgen05 tensor-core kernels for bf16 (default 1).
- * flag 1: number of kernels launched through this context since creation (read with value<0). */
+ * flag 1: number of kernels launched through this context since creation (read with value<0).
+ * flag 2: enable (1) / disable (0) the weight-stationary tensor-core GEMM variant for small K (default 1). */
 MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);
 
 /* Layout ------------------------------------------------------------------------------------- */
@@ -66,7 +67,8 @@ MMGT_API int mmgt_tokens_to_ncfhw(mmgt_ctx*, const void* src, void* dst, int B, 
 /* Normalisation ------------------------------------------------------------------------------ */
 /* GroupNorm over (T, C/groups) per frame on a channels-last tensor, optional fused SiLU.  The input may
  * be the virtual channel-concat [x1 (C1) || x2 (C2)] (x2 may be NULL, C2 = 0); the output is the
- * concatenated normalised tensor (N,T,C1+C2).  stats_ws: >= N*groups*2 doubles of scratch.
+ * concatenated normalised tensor (N,T,C1+C2).  stats_ws: >= N*groups*2 + ceil(N/2) doubles of scratch
+ * (per-group sums, then one 32-bit arrival counter per frame; zeroed by the call itself).
  * Replaces InflatedGroupNorm/nn.GroupNorm + F.silu (resnet.py:20-28,220-221,231-237;
  * transformer_3d.py:174; motion_module.py:156; unet_3d.py:618-619) and torch.cat
  * (unet_3d_blocks.py:894,1057). */

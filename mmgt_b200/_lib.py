@@ -119,5 +119,9 @@ class Context:
     def tensor_cores(self) -> bool:
         return bool(self.lib.mmgt_ctx_flag(self.handle, 0, -1))
 
+    def set_resident_weights(self, on: bool) -> bool:
+        """Weight-stationary GEMM variant (small K); on by default, switchable for A/B timing and tests."""
+        return bool(self.lib.mmgt_ctx_flag(self.handle, 2, 1 if on else 0))
+
     def launches(self) -> int:
         return int(self.lib.mmgt_ctx_flag(self.handle, 1, -1))

@@ -148,7 +148,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr int P_BYTES = BQ * BN * 2;           // one P buffer (per softmax group)
   constexpr int TM_S = 0, TM_O = 2 * BN;         // S buffers at 0 / BN, O accumulators at 2BN / 2BN + DPAD
   constexpr uint32_t IDESC_QK = idesc_bf16(BN, false);
-  constexpr uint32_t IDESC_PV = idesc_bf16(DPAD, true);
+  // Only ceil(d / 16) k-steps of Q K^T and round_up(d, 16) columns of P V are real: the rest of the 64-wide
+  // TMA box is zero fill (d = 40 -> 3 of 4 k-steps, N = 48 of 64).
+  const int qk_steps = (args.d + 15) >> 4;
+  const uint32_t IDESC_PV = idesc_bf16(qk_steps << 4, true);
   static_assert(TM_O + 2 * DPAD <= 512, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
@@ -203,21 +206,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
     for (int c = 0; c < DCH; ++c) tma_load_3d(sQ + c * (BQ * 128), &tmQ, q_full, c * 64, h, n * args.Lq + q0);
-    for (int j = 0; j < num_tiles; ++j) {
-      const int st = j % KV_STAGES;
-      const uint32_t ph = (j / KV_STAGES) & 1;
+    // K runs one tile further ahead than V: the MMA warp issues QK(j+2) before PV(j), and K(j+2) only needs QK(j)
+    // retired while V(j+1) needs PV(j-1) retired (a strict K, V, K, V order would gate K(j+2) behind PV(j-1) and put
+    // a full TMA round trip on the MMA warp's critical path).
+    auto tile_row = [&](int j) {
       const bool second = j >= tiles1;
-      const int row = second ? seg2 * args.Lk2 + (j - tiles1) * BN : n * args.Lk + j * BN;
-      mbar_wait(&k_empty[st], ph ^ 1);
+      return second ? seg2 * args.Lk2 + (j - tiles1) * BN : n * args.Lk + j * BN;
+    };
+    auto load_k = [&](int j) {
+      const int st = j % KV_STAGES;
+      const bool second = j >= tiles1;
+      mbar_wait(&k_empty[st], ((j / KV_STAGES) & 1) ^ 1);
       mbar_expect_tx(&k_full[st], KV_BYTES);
 #pragma unroll
       for (int c = 0; c < DCH; ++c)
-        tma_load_3d(sK + st * KV_BYTES + c * KV_CHUNK, second ? &tmK2 : &tmK, &k_full[st], c * 64, h, row);
-      mbar_wait(&v_empty[st], ph ^ 1);
+        tma_load_3d(sK + st * KV_BYTES + c * KV_CHUNK, second ? &tmK2 : &tmK, &k_full[st], c * 64, h, tile_row(j));
+    };
+    auto load_v = [&](int j) {
+      const int st = j % KV_STAGES;
+      const bool second = j >= tiles1;
+      mbar_wait(&v_empty[st], ((j / KV_STAGES) & 1) ^ 1);
       mbar_expect_tx(&v_full[st], KV_BYTES);
 #pragma unroll
       for (int c = 0; c < DCH; ++c)
-        tma_load_3d(sV + st * KV_BYTES + c * KV_CHUNK, second ? &tmV2 : &tmV, &v_full[st], c * 64, h, row);
+        tma_load_3d(sV + st * KV_BYTES + c * KV_CHUNK, second ? &tmV2 : &tmV, &v_full[st], c * 64, h, tile_row(j));
+    };
+    load_k(0);
+    if (num_tiles > 1) load_k(1);
+    load_v(0);
+    for (int j = 0; j < num_tiles; ++j) {
+      if (j + 2 < num_tiles) load_k(j + 2);
+      if (j + 1 < num_tiles) load_v(j + 1);
     }
   } else if (threadIdx.x == 32) {
     // ===================== MMA issuer =====================
@@ -230,16 +249,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + st * KV_BYTES);
 #pragma unroll
       for (int k = 0; k < DPAD / 16; ++k) {
-        const uint32_t offq = (k / 4) * (BQ * 128) + (k % 4) * 32, offk = (k / 4) * KV_CHUNK + (k % 4) * 32;
-        umma(tS, desc_kmajor(aQ + offq), desc_kmajor(aK + offk), IDESC_QK, k != 0);
+        if (k < qk_steps) {
+          const uint32_t offq = (k / 4) * (BQ * 128) + (k % 4) * 32, offk = (k / 4) * KV_CHUNK + (k % 4) * 32;
+          umma(tS, desc_kmajor(aQ + offq), desc_kmajor(aK + offk), IDESC_QK, k != 0);
+        }
       }
       umma_commit(&k_empty[st]);
       umma_commit(&s_full[g]);
     };
+    // Issue order: QK(0), QK(1), then per tile j: QK(j+2), PV(j).  QK(j+2) only needs group (j & 1) to have pulled
+    // S(j) out of TMEM, which happens at the start of its softmax of tile j, so S(j+2) is ready by the time the group
+    // finishes tile j (issuing it after PV(j) left every group idle for a PV + QK round trip per tile).
     mbar_wait(q_full, 0);
     issue_qk(0);
+    if (num_tiles > 1) issue_qk(1);
     for (int j = 0; j < num_tiles; ++j) {
-      if (j + 1 < num_tiles) issue_qk(j + 1);
+      if (j + 2 < num_tiles) issue_qk(j + 2);
       const int st = j % KV_STAGES, g = j & 1;
       mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
       mbar_wait(&p_full[g], (j >> 1) & 1);

@@ -12,6 +12,7 @@ struct mmgt_ctx {
   int num_sms;
   int max_smem_optin;
   int use_tc;                 // tcgen05 kernels enabled for bf16
+  int use_bres;               // weight-stationary GEMM variant enabled (small K)
   long long launches;         // kernels launched through this context
   void* encode_tiled;         // PFN of cuTensorMapEncodeTiled (resolved lazily through the runtime)
 };
@@ -71,6 +72,7 @@ __device__ __forceinline__ float warp_max(float v) {
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 // dtype dispatch: calls fn(T{}) with T = float or bf16
 #define MMGT_DISPATCH_DTYPE(dtype, T, ...)                          \

@@ -28,6 +28,7 @@ extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
   c->num_sms = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   c->use_tc = 1;
+  c->use_bres = 1;
   c->launches = 0;
   c->encode_tiled = nullptr;
   *out = c;
@@ -46,5 +47,9 @@ extern "C" int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value) {
     return ctx->use_tc;
   }
   if (flag == 1) return ctx->launches;
+  if (flag == 2) {
+    if (value >= 0) ctx->use_bres = value ? 1 : 0;
+    return ctx->use_bres;
+  }
   return MMGT_E_INVALID;
 }

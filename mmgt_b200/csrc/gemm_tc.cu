@@ -40,6 +40,9 @@ struct TcArgs {
   float alpha;
   // conv geometry (CONV only)
   int H, W, cin_blocks;
+  // BRES only: A ring depth (runtime: what is left of shared memory after the resident weight tile)
+  int stages;
+  int wide_io;   // D / residual rows are 32-byte aligned: 256-bit epilogue loads and stores
 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -143,31 +146,100 @@ __device__ __forceinline__ void load16_bf16(const bf16* src, float (&v)[16]) {
   }
 }
 
+
+// 32-byte (16 x bf16) global accesses.  sm_100 has 256-bit LDG / STG: one instruction (and one L1 tag look-up per
+// lane) instead of two -- the epilogue is row-per-thread, so every lane of a warp touches a different line and the
+// LSU, not the tensor pipe, paces small-K GEMMs.  `wide` needs 32-byte aligned addresses.
+struct Row32 { uint32_t w[8]; };
+__device__ __forceinline__ Row32 ld_row32(const bf16* p, bool wide) {
+  Row32 r;
+  if (wide) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p));
+  } else {
+    const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w; r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+  }
+  return r;
+}
+__device__ __forceinline__ void st_row32(bf16* p, const float (&v)[16], bool wide) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  if (wide) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                 "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+  } else {
+    reinterpret_cast<uint4*>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+__device__ __forceinline__ void load16_f32(const float* src, float (&v)[16]) {   // 64-byte aligned, warp-uniform address
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(src) + i);
+    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+  }
+}
+
+// erf-GELU for the tensor-core GEGLU epilogue: 0.5 x (1 + erf(x / sqrt 2)) with erfc(|z|) from Abramowitz-Stegun
+// 7.1.26 (|erf error| <= 1.5e-7, far below the bf16 output rounding) -- 2 MUFU + ~14 FP32 ops instead of the
+// ~35-instruction branchy erff(); the fp32 kernels keep erff().
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));   // exp(-x^2 / 2)
+  const float erfc_abs = p * t * e;                       // erfc(|x| / sqrt 2)
+  const float cdf2 = x < 0.f ? erfc_abs : 2.f - erfc_abs; // 1 + erf(x / sqrt 2)
+  return 0.5f * x * cdf2;
+}
+
 // ------------------------------------------------------------------------------------------- kernel
-template <int BN, bool CONV, bool GEGLU>
+// BRES ("weight-stationary"): for small K the whole (BN x K) weight tile of this CTA stays resident in shared
+// memory, every CTA keeps one n-block for its lifetime and only A tiles stream through the ring.  The
+// L2 -> SM fabric (~45 B/clk/SM), not the tensor pipe, bounds a 128 x BN tile that re-reads B per tile:
+// (128 + BN) * 128 B per k-block vs. 128 * 128 B with B resident.
+template <int BN, bool CONV, bool GEGLU, bool BRES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs args) {
-  constexpr int STAGES = num_stages(BN);
+  constexpr int MAX_STAGES = 8;
   constexpr int B_STAGE_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int STAGE_BYTES = BRES ? A_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr int ACC_STRIDE = acc_stride(BN);
   constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   constexpr uint32_t IDESC = make_idesc(BN);
   static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
+  static_assert(!(BRES && CONV), "resident weights are for small-K GEMMs");
+  const int STAGES = BRES ? args.stages : num_stages(BN);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem_base;                                                        // BRES: num_k_blocks weight tiles
+  uint8_t* smem = smem_base + (BRES ? args.num_k_blocks * B_STAGE_BYTES : 0);         // ring
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* b_full = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-#pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(b_full, 1);
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 8); mbar_init(&tmem_empty[1], 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,13 +254,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_tiles = args.num_m_tiles * args.num_n_tiles;
+  // Tile schedule.  Streaming: tile = blockIdx.x + i * gridDim.x, n fastest (the n-tiles of one m-block run on
+  // neighbouring SMs at the same time, so A is fetched from HBM once).  BRES: the n-block is fixed per CTA
+  // (gridDim.x is a multiple of num_n_tiles) and the CTA walks down the m-blocks.
+  auto tile_at = [&](int i, int& m_blk, int& n_blk) -> bool {
+    if (BRES) {
+      const int m_stride = gridDim.x / args.num_n_tiles;
+      n_blk = blockIdx.x % args.num_n_tiles;
+      m_blk = blockIdx.x / args.num_n_tiles + i * m_stride;
+      return m_blk < args.num_m_tiles;
+    }
+    const int tile = blockIdx.x + i * gridDim.x;
+    m_blk = tile / args.num_n_tiles;
+    n_blk = tile - m_blk * args.num_n_tiles;
+    return tile < num_tiles;
+  };
 
   if (threadIdx.x == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / args.num_n_tiles, n_blk = tile % args.num_n_tiles;
+    int m_blk, n_blk;
+    if (BRES && tile_at(0, m_blk, n_blk)) {
+      mbar_expect_tx(b_full, args.num_k_blocks * B_STAGE_BYTES);
+      for (int kb = 0; kb < args.num_k_blocks; ++kb) tma_load_2d(smem_b + kb * B_STAGE_BYTES, &tmB, b_full, kb * BK, n_blk * BN);
+    }
+    for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
       int cn = 0, ch = 0, cw = 0;
       if (CONV) {
         const int m0 = m_blk * BM, hw = args.H * args.W;
@@ -200,7 +291,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < args.num_k_blocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * STAGE_BYTES;
-        uint8_t* sb = sa + A_STAGE_BYTES;
         mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
         if (CONV) {
           const int tap = kb / args.cin_blocks, cb = kb - tap * args.cin_blocks;
@@ -208,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
         }
-        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+        if (!BRES) tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -216,8 +306,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer =====================
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    int m_blk, n_blk;
+    if (BRES && tile_at(0, m_blk, n_blk)) mbar_wait(b_full, 0);
+    for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -227,7 +318,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_STAGE_BYTES);
+        const uint32_t sb = BRES ? smem_u32(smem_b + kb * B_STAGE_BYTES) : sa + A_STAGE_BYTES;
+        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           // +32 bytes per UMMA_K step inside the 128B swizzle atom => +2 in the (addr >> 4) field
@@ -253,22 +345,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int CH0 = (NCH + 1) / 2;               // chunks of half 0; half 1 takes the rest
     const int c_begin = half ? CH0 : 0;
     const int c_count = half ? (NCH - CH0) : CH0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / args.num_n_tiles, n_blk = tile % args.num_n_tiles;
+    const bool wide = args.wide_io != 0;
+    // Residual prefetch, one tile ahead: chunk slot i is consumed for tile `it` and immediately refilled with the
+    // same chunk of tile `it + 1`, so every load has a whole tile period to land (for small K the epilogue, not the
+    // main loop, is the critical path and nothing else would cover the HBM latency of these loads).
+    Row32 resv[CH0];
+    int m_blk, n_blk;
+    if (args.residual != nullptr && tile_at(0, m_blk, n_blk) && m_blk * BM + row_in_tile < args.M) {
+      const bf16* rp = args.residual + (int64_t)(m_blk * BM + row_in_tile) * args.ldr + n_blk * OUT_COLS + c_begin * 16;
+#pragma unroll
+      for (int i = 0; i < CH0; ++i)
+        if (i < c_count) resv[i] = ld_row32(rp + 16 * i, wide);
+    }
+    for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m = m_blk * BM + row_in_tile;
       const bool m_ok = m < args.M;
       const int n_out0 = n_blk * OUT_COLS;
-      uint4 resv[CH0][2];
       const bool has_res = args.residual != nullptr && m_ok;
-      if (has_res) {
-        const uint4* rp = reinterpret_cast<const uint4*>(args.residual + (int64_t)m * args.ldr + n_out0 + c_begin * 16);
-#pragma unroll
-        for (int i = 0; i < CH0; ++i) {
-          if (i < c_count) { resv[i][0] = rp[2 * i]; resv[i][1] = rp[2 * i + 1]; }
-        }
+      const bf16* res_next = nullptr;
+      {
+        int mb2, nb2;
+        if (args.residual != nullptr && tile_at(it + 1, mb2, nb2) && mb2 * BM + row_in_tile < args.M)
+          res_next = args.residual + (int64_t)(mb2 * BM + row_in_tile) * args.ldr + nb2 * OUT_COLS + c_begin * 16;
       }
       const float rs = (args.rowscale && m_ok ? args.rowscale[m] : 1.f) * args.alpha;
       const float* rb = (args.rowbias && m_ok) ? args.rowbias + (int64_t)(m / args.rows_per_group) * args.N_out : nullptr;
@@ -285,41 +385,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (GEGLU) {
             uint32_t g[16];
             tmem_ld_x16(taddr + 2 * c + 16, g);
+            float bv[16], bg[16];
+            if (args.bias) {
+              load16_f32(args.bias + n_blk * BN + 2 * c, bv);
+              load16_f32(args.bias + n_blk * BN + 2 * c + 16, bg);
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               float val = __uint_as_float(r[e]), gate = __uint_as_float(g[e]);
-              if (args.bias) {
-                val += __ldg(args.bias + n_blk * BN + 2 * c + e);
-                gate += __ldg(args.bias + n_blk * BN + 2 * c + 16 + e);
-              }
-              v[e] = val * gelu_erf_f(gate);
+              if (args.bias) { val += bv[e]; gate += bg[e]; }
+              v[e] = val * gelu_erf_fast(gate);
             }
           } else {
+            float bv[16];
+            if (args.bias) load16_f32(args.bias + n_out0 + c, bv);
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               v[e] = __uint_as_float(r[e]);
-              if (args.bias) v[e] += __ldg(args.bias + n_out0 + c + e);
+              if (args.bias) v[e] += bv[e];
             }
           }
           if (m_ok) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] *= rs;
             if (rb) {
+              float rv[16];
+              load16_f32(rb + n_out0 + c, rv);
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] += __ldg(rb + n_out0 + c + e);
+              for (int e = 0; e < 16; ++e) v[e] += rv[e];
             }
             if (has_res) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&resv[i][0]);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&resv[i].w[0]);
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 float2 f = __bfloat1622float2(h[e]);
                 v[2 * e] += f.x; v[2 * e + 1] += f.y;
               }
             }
-            store16_bf16(args.D + (int64_t)m * args.ldd + n_out0 + c, v);
+            st_row32(args.D + (int64_t)m * args.ldd + n_out0 + c, v, wide);
           }
+          if (res_next) resv[i] = ld_row32(res_next + 16 * i, wide);
         }
       }
       tcgen05_fence_before();
@@ -400,12 +507,12 @@ int launch_tc(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, con
   constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    MMGT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MMGT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, GEGLU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int tiles = a.num_m_tiles * a.num_n_tiles;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  gemm_tc_kernel<BN, CONV, GEGLU><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a);
+  gemm_tc_kernel<BN, CONV, GEGLU, false><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a);
   MMGT_LAUNCH_OK(ctx);
   return 0;
 }
@@ -429,6 +536,66 @@ int dispatch_tc(mmgt_ctx* ctx, int bn, bool geglu, const CUtensorMap& tmA, const
   return MMGT_E_UNSUPPORTED;
 }
 
+// ---- weight-stationary plan (BRES kernels)
+constexpr int SMEM_OPTIN = 232448;          // 227 KB per CTA on sm_100
+constexpr int BRES_OVERHEAD = 1024 + 256;   // alignment slack + barriers
+
+struct BresPlan { int bn, stages, grid; };
+
+// Resident weights pay off when the (BN x K) tile fits next to >= 3 A stages, at least 90 % of the SMs get a CTA
+// (the grid must be a multiple of the n-tile count) and every CTA has a few m-tiles to amortise the weight load.
+bool plan_bres(int M, int N, int K, bool geglu, int num_sms, BresPlan* out) {
+  const int kblocks = (K + BK - 1) / BK;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int cand[4] = {256, 240, 160, 128};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cand[i];
+    if (N % bn || (geglu && bn % 32)) continue;
+    const int n_tiles = N / bn;
+    const int b_bytes = kblocks * bn * BK * 2;
+    int stages = (SMEM_OPTIN - BRES_OVERHEAD - b_bytes) / A_STAGE_BYTES;
+    if (stages > 8) stages = 8;
+    if (stages < 3 || n_tiles > num_sms) continue;
+    const int grid = (num_sms / n_tiles) * n_tiles;
+    if (grid * 10 < num_sms * 9) continue;
+    if (m_tiles < 4 * (grid / n_tiles)) continue;
+    out->bn = bn; out->stages = stages; out->grid = grid;
+    return true;
+  }
+  return false;
+}
+
+template <int BN, bool GEGLU>
+int launch_bres(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    MMGT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, false, GEGLU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SMEM_OPTIN));
+    configured = true;
+  }
+  const int smem = BRES_OVERHEAD + a.num_k_blocks * BN * BK * 2 + a.stages * A_STAGE_BYTES;
+  gemm_tc_kernel<BN, false, GEGLU, true><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a);
+  MMGT_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int dispatch_bres(mmgt_ctx* ctx, const BresPlan& pl, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a,
+                  cudaStream_t st) {
+#define CASE(BN_)                                                                    \
+  case BN_:                                                                          \
+    if (geglu) return launch_bres<BN_, true>(ctx, tmA, tmB, a, pl.grid, st);         \
+    return launch_bres<BN_, false>(ctx, tmA, tmB, a, pl.grid, st);
+  switch (pl.bn) {
+    CASE(256)
+    CASE(160)
+    CASE(128)
+    case 240: return launch_bres<240, false>(ctx, tmA, tmB, a, pl.grid, st);
+  }
+#undef CASE
+  mmgt_set_error("gemm_tc: no resident-weight kernel for BN=%d", pl.bn);
+  return MMGT_E_UNSUPPORTED;
+}
+
 }  // namespace
 
 extern "C" int mmgt_gemm_tc_block_n(int N) { return pick_bn(N); }
@@ -444,12 +611,15 @@ bool mmgt_gemm_tc_supported(const mmgt_ctx* ctx, const mmgt_gemm_params* p) {
   const int n_out = p->geglu_block ? p->N / 2 : p->N;
   if (n_out % 16 || p->ldd % 8) return false;
   if (p->residual && (!aligned16(p->residual) || p->ldr % 8)) return false;
+  if ((p->bias && !aligned16(p->bias)) || (p->rowbias && !aligned16(p->rowbias))) return false;   // float4 epilogue loads
   if (p->M < 1) return false;
   return true;
 }
 
 int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
-  const int bn = pick_bn_for(p->N, p->M, ctx->num_sms);
+  BresPlan pl{};
+  const bool bres = ctx->use_bres && plan_bres(p->M, p->N, p->K, p->geglu_block != 0, ctx->num_sms, &pl);
+  const int bn = bres ? pl.bn : pick_bn_for(p->N, p->M, ctx->num_sms);
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->M};
@@ -474,6 +644,11 @@ int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
   a.bias = p->bias; a.rowscale = p->rowscale; a.rowbias = p->rowbias;
   a.residual = (const bf16*)p->residual; a.D = (bf16*)p->D;
   a.ldd = p->ldd; a.ldr = p->ldr; a.rows_per_group = p->rows_per_group > 0 ? p->rows_per_group : 1; a.alpha = p->alpha;
+  a.wide_io = aligned32(p->D) && p->ldd % 16 == 0 && (!p->residual || (aligned32(p->residual) && p->ldr % 16 == 0));
+  if (bres) {
+    a.stages = pl.stages;
+    return dispatch_bres(ctx, pl, p->geglu_block != 0, tmA, tmB, a, st);
+  }
   return dispatch_tc<false>(ctx, bn, p->geglu_block != 0, tmA, tmB, a, st);
 }
 
@@ -503,6 +678,7 @@ bool mmgt_conv3x3_tc_supported(const mmgt_ctx* ctx, const mmgt_conv3x3_params* p
   uint32_t bw, bh, bf;
   if (!conv_box(p, &bw, &bh, &bf)) return false;
   if (!aligned16(p->x) || !aligned16(p->w) || !aligned16(p->y) || (p->residual && !aligned16(p->residual))) return false;
+  if ((p->bias && !aligned16(p->bias)) || (p->rowbias && !aligned16(p->rowbias))) return false;
   return true;
 }
 
@@ -535,6 +711,7 @@ int mmgt_conv3x3_tc(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, cudaStream_t st
   a.bias = p->bias; a.rowscale = nullptr; a.rowbias = p->rowbias;
   a.residual = (const bf16*)p->residual; a.D = (bf16*)p->y;
   a.ldd = p->Cout; a.ldr = p->Cout;
+  a.wide_io = aligned32(p->y) && p->Cout % 16 == 0 && (!p->residual || aligned32(p->residual));
   a.rows_per_group = p->rowbias ? p->frames_per_group * p->H * p->W : 1;
   a.alpha = 1.f;
   a.H = p->H; a.W = p->W;

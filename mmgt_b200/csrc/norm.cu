@@ -43,108 +43,171 @@ __device__ __forceinline__ void store_vec<bf16>(bf16* p, const float (&v)[8]) {
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAXNV = 3;  // channel vectors per thread when C/VEC > 256
 
-// stats[(n*G + g)*2 + {0,1}] += {sum, sumsq} over the block's token chunk
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// One kernel for statistics + normalise (+SiLU).  Work item = (frame n, token chunk); a block
+//   1. accumulates per-channel sum / sum-of-squares of its chunk in registers -> shared -> per-group doubles in global,
+//   2. bumps the frame's arrival counter and waits until all `chunks` items of the frame have arrived,
+//   3. re-reads its chunk (now L2-resident: a frame is at most a few MB) and writes the normalised output.
+// HBM traffic is one read + one write of the tensor instead of two reads + one write for the two-kernel form.
+// Items are frame-major and the grid never exceeds the number of co-resident blocks, so every item a block waits
+// for belongs to a block that is running (or has finished): no deadlock.
+// NV = channel vectors per thread (1 when C / VEC <= 256), UNR = tokens in flight per thread.
 template <typename T>
-__global__ void __launch_bounds__(GN_THREADS)
-gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __restrict__ stats, int T_tok, int C1,
-                int C2, int groups, int tok_per_block) {
-  constexpr int VEC = VecOf<T>::N;
-  extern __shared__ float chan[];  // [2][C] per-channel partial sums of this block
-  const int C = C1 + C2, Cv = C / VEC, C1v = C1 / VEC, cpg = C / groups;
-  const int n = blockIdx.y;
-  const int t0 = blockIdx.x * tok_per_block;
-  const int t1 = min(T_tok, t0 + tok_per_block);
-  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) chan[i] = 0.f;
-  __syncthreads();
-  const int lanes = Cv < GN_THREADS ? Cv : GN_THREADS;
-  const int rows_per_pass = GN_THREADS / lanes;
-  const int lane = threadIdx.x % lanes, rip = threadIdx.x / lanes;
-  float s[GN_MAXNV][VEC], ss[GN_MAXNV][VEC];
+__device__ __forceinline__ void unpack_vec(const typename VecOf<T>::type& raw, float (&v)[VecOf<T>::N]);
+template <>
+__device__ __forceinline__ void unpack_vec<float>(const float4& t, float (&v)[4]) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+template <>
+__device__ __forceinline__ void unpack_vec<bf16>(const uint4& t, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
-  for (int j = 0; j < GN_MAXNV; ++j)
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) s[j][e] = ss[j][e] = 0.f;
-  if (rip < rows_per_pass) {
-    for (int t = t0 + rip; t < t1; t += rows_per_pass) {
-      const size_t row = (size_t)n * T_tok + t;
-#pragma unroll
-      for (int j = 0; j < GN_MAXNV; ++j) {
-        int cv = lane + j * lanes;
-        if (cv < Cv) {
-          float v[VEC];
-          if (cv < C1v) load_vec<T>(x1 + row * C1 + (size_t)cv * VEC, v);
-          else load_vec<T>(x2 + row * C2 + (size_t)(cv - C1v) * VEC, v);
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) { s[j][e] += v[e]; ss[j][e] += v[e] * v[e]; }
-        }
-      }
-    }
-    // threads with the same lane (different token rows) share channels: <= rows_per_pass-way contention
-#pragma unroll
-    for (int j = 0; j < GN_MAXNV; ++j) {
-      int cv = lane + j * lanes;
-      if (cv < Cv) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          atomicAdd(&chan[cv * VEC + e], s[j][e]);
-          atomicAdd(&chan[C + cv * VEC + e], ss[j][e]);
-        }
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += GN_THREADS) {
-    const int g = i >> 1, which = i & 1;
-    const float* src = chan + which * C + g * cpg;
-    float a = 0.f;
-    for (int c = 0; c < cpg; ++c) a += src[c];
-    atomicAdd(&stats[(size_t)n * groups * 2 + i], (double)a);
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(GN_THREADS)
-gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restrict__ y, const float* __restrict__ gamma,
-                const float* __restrict__ beta, const double* __restrict__ stats, int T_tok, int C1, int C2, int groups,
-                float eps, int silu, int tok_per_block) {
+template <typename T, int NV>
+__global__ void __launch_bounds__(GN_THREADS, 3)
+gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restrict__ y, const float* __restrict__ gamma,
+                const float* __restrict__ beta, double* __restrict__ stats, unsigned* __restrict__ arrived, int N,
+                int T_tok, int C1, int C2, int groups, float eps, int silu, int tok_per_block, int chunks) {
   constexpr int VEC = VecOf<T>::N;
-  extern __shared__ float sm[];  // scale[C], shift[C]
+  typedef typename VecOf<T>::type Raw;
+  constexpr int UNR = 4 / NV < 1 ? 1 : 4 / NV;   // 16-byte loads in flight per thread = UNR * NV (kept packed)
+  extern __shared__ float sm[];  // phase 1: [2][C] channel partial sums; phase 3: scale[C], shift[C]
   const int C = C1 + C2, Cv = C / VEC, C1v = C1 / VEC, cpg = C / groups;
-  float* scale = sm;
-  float* shift = sm + C;
-  const int n = blockIdx.y;
-  const double cnt = (double)T_tok * cpg;
-  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
-    int g = c / cpg;
-    double mean = stats[((size_t)n * groups + g) * 2] / cnt;
-    double var = stats[((size_t)n * groups + g) * 2 + 1] / cnt - mean * mean;
-    if (var < 0) var = 0;
-    float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    float sc = rstd * gamma[c];
-    scale[c] = sc;
-    shift[c] = beta[c] - (float)mean * sc;
-  }
-  __syncthreads();
-  const int t0 = blockIdx.x * tok_per_block;
-  const int t1 = min(T_tok, t0 + tok_per_block);
   const int lanes = Cv < GN_THREADS ? Cv : GN_THREADS;
   const int rows_per_pass = GN_THREADS / lanes;
   const int lane = threadIdx.x % lanes, rip = threadIdx.x / lanes;
-  if (rip >= rows_per_pass) return;
-  for (int t = t0 + rip; t < t1; t += rows_per_pass) {
-    const size_t row = (size_t)n * T_tok + t;
-    for (int cv = lane; cv < Cv; cv += lanes) {
-      float v[VEC];
-      if (cv < C1v) load_vec<T>(x1 + row * C1 + (size_t)cv * VEC, v);
-      else load_vec<T>(x2 + row * C2 + (size_t)(cv - C1v) * VEC, v);
+  const bool active = rip < rows_per_pass;
+  const double cnt = (double)T_tok * cpg;
+  const Raw zero_raw = {};
+
+  auto src = [&](size_t row, int cv) -> const Raw* {
+    return reinterpret_cast<const Raw*>(cv < C1v ? x1 + row * C1 + (size_t)cv * VEC : x2 + row * C2 + (size_t)(cv - C1v) * VEC);
+  };
+
+  for (int item = blockIdx.x; item < N * chunks; item += gridDim.x) {
+    const int n = item / chunks;
+    const int t0 = (item - n * chunks) * tok_per_block;
+    const int t1 = min(T_tok, t0 + tok_per_block);
+    // ---------------- phase 1: statistics
+    for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
+    __syncthreads();
+    if (active) {
+      float s[NV][VEC], ss[NV][VEC];
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        int c = cv * VEC + e;
-        float o = v[e] * scale[c] + shift[c];
-        v[e] = silu ? silu_f(o) : o;
+      for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) s[j][e] = ss[j][e] = 0.f;
+      for (int t = t0 + rip; t < t1; t += UNR * rows_per_pass) {
+        Raw raw[UNR][NV];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int tt = t + u * rows_per_pass;
+          const size_t row = (size_t)n * T_tok + tt;
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            const int cv = lane + j * lanes;
+            raw[u][j] = (tt < t1 && cv < Cv) ? *src(row, cv) : zero_raw;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            float v[VEC];
+            unpack_vec<T>(raw[u][j], v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { s[j][e] += v[e]; ss[j][e] += v[e] * v[e]; }
+          }
       }
-      store_vec<T>(y + row * C + (size_t)cv * VEC, v);
+      // threads with the same lane (different token rows) share channels: <= rows_per_pass-way contention
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int cv = lane + j * lanes;
+        if (cv < Cv) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            atomicAdd(&sm[cv * VEC + e], s[j][e]);
+            atomicAdd(&sm[C + cv * VEC + e], ss[j][e]);
+          }
+        }
+      }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < groups * 2; i += GN_THREADS) {
+      const int g = i >> 1, which = i & 1;
+      const float* srcp = sm + which * C + g * cpg;
+      float a = 0.f;
+      for (int c = 0; c < cpg; ++c) a += srcp[c];
+      atomicAdd(&stats[(size_t)n * groups * 2 + i], (double)a);
+    }
+    // ---------------- phase 2: frame barrier
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicAdd(&arrived[n], 1u);
+      while (ld_acquire_u32(&arrived[n]) < (unsigned)chunks) __nanosleep(32);
+    }
+    __syncthreads();
+    // ---------------- phase 3: normalise
+    float* scale = sm;
+    float* shift = sm + C;
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+      const int g = c / cpg;
+      const double mean = __ldcg(&stats[((size_t)n * groups + g) * 2]) / cnt;
+      double var = __ldcg(&stats[((size_t)n * groups + g) * 2 + 1]) / cnt - mean * mean;
+      if (var < 0) var = 0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float sc = rstd * gamma[c];
+      scale[c] = sc;
+      shift[c] = beta[c] - (float)mean * sc;
+    }
+    __syncthreads();
+    if (active) {
+      for (int t = t0 + rip; t < t1; t += UNR * rows_per_pass) {
+        Raw raw[UNR][NV];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int tt = t + u * rows_per_pass;
+          const size_t row = (size_t)n * T_tok + tt;
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            const int cv = lane + j * lanes;
+            if (tt < t1 && cv < Cv) raw[u][j] = *src(row, cv);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int tt = t + u * rows_per_pass;
+          const size_t row = (size_t)n * T_tok + tt;
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            const int cv = lane + j * lanes;
+            if (tt < t1 && cv < Cv) {
+              float v[VEC];
+              unpack_vec<T>(raw[u][j], v);
+#pragma unroll
+              for (int q = 0; q < VEC / 4; ++q) {
+                const float4 sc = *reinterpret_cast<const float4*>(scale + cv * VEC + 4 * q);
+                const float4 sh = *reinterpret_cast<const float4*>(shift + cv * VEC + 4 * q);
+                float* o = &v[4 * q];
+                o[0] = o[0] * sc.x + sh.x; o[1] = o[1] * sc.y + sh.y; o[2] = o[2] * sc.z + sh.z; o[3] = o[3] * sc.w + sh.w;
+                if (silu) { o[0] = silu_f(o[0]); o[1] = silu_f(o[1]); o[2] = silu_f(o[2]); o[3] = silu_f(o[3]); }
+              }
+              store_vec<T>(y + row * C + (size_t)cv * VEC, v);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();   // sm is re-zeroed by the next item
   }
 }
 
@@ -200,6 +263,94 @@ layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __rest
   }
 }
 
+
+// Full-width fast path: a row is split over G = 8 / 16 / 32 lanes with VPL 16-byte vectors per lane, so one warp
+// normalises 32 / G rows at a time and every lane has VPL independent loads in flight (the one-warp-per-row
+// kernel below issues 1-2 loads per lane between two dependent shuffle reductions: latency-bound at C = 320).
+// gamma / beta sit in shared memory and are read as float4.
+template <typename T, int VPL, int G>
+__global__ void __launch_bounds__(256)
+layernorm_grp_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ pe, int64_t rows, int C, int T_tok, int F,
+                     float eps) {
+  constexpr int VEC = VecOf<T>::N;
+  extern __shared__ float gb[];   // gamma[C], beta[C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { gb[i] = gamma[i]; gb[C + i] = beta[i]; }
+  __syncthreads();
+  const int gl = threadIdx.x % G;
+  const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t ngrp = (int64_t)gridDim.x * blockDim.x / G;
+  const float inv_c = 1.f / (float)C;
+  for (int64_t row = grp; row < rows; row += ngrp) {
+    float v[VPL][VEC];
+    const T* xr = x + row * C;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) load_vec<T>(xr + (size_t)(gl + j * G) * VEC, v[j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) sum += v[j][e];
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { const float d = v[j][e] - mean; sq += d * d; }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_c + eps);
+    const float* pe_row = pe ? pe + (size_t)((row / T_tok) % F) * C : nullptr;
+    T* yr = y + row * C;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int c0 = (gl + j * G) * VEC;
+      float o[VEC];
+#pragma unroll
+      for (int q = 0; q < VEC / 4; ++q) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gb + c0 + 4 * q);
+        const float4 b4 = *reinterpret_cast<const float4*>(gb + C + c0 + 4 * q);
+        o[4 * q + 0] = (v[j][4 * q + 0] - mean) * rstd * g4.x + b4.x;
+        o[4 * q + 1] = (v[j][4 * q + 1] - mean) * rstd * g4.y + b4.y;
+        o[4 * q + 2] = (v[j][4 * q + 2] - mean) * rstd * g4.z + b4.z;
+        o[4 * q + 3] = (v[j][4 * q + 3] - mean) * rstd * g4.w + b4.w;
+        if (pe_row) {
+          const float4 p4 = __ldg(reinterpret_cast<const float4*>(pe_row + c0 + 4 * q));
+          o[4 * q + 0] += p4.x; o[4 * q + 1] += p4.y; o[4 * q + 2] += p4.z; o[4 * q + 3] += p4.w;
+        }
+      }
+      store_vec<T>(yr + c0, o);
+    }
+  }
+}
+
+template <typename T, int VPL, int G>
+void launch_ln_grp(mmgt_ctx* ctx, const void* x, void* y, const float* gamma, const float* beta, const float* pe,
+                   int64_t rows, int C, int T_tok, int F, float eps, cudaStream_t st) {
+  const int rows_per_block = 256 / G;
+  // two resident waves of row groups per SM slot keep the tail short
+  const int64_t blocks = std::min<int64_t>((rows + rows_per_block - 1) / rows_per_block, (int64_t)ctx->num_sms * 16);
+  layernorm_grp_kernel<T, VPL, G><<<(int)blocks, 256, sizeof(float) * 2 * C, st>>>((const T*)x, (T*)y, gamma, beta, pe, rows,
+                                                                                  C, T_tok, F, eps);
+}
+
+// Picks (VPL, G) with VPL * G == C / VEC for the widths of the full model (320 / 640 / 1280); false => generic kernel.
+template <typename T>
+bool try_ln_grp(mmgt_ctx* ctx, const void* x, void* y, const float* gamma, const float* beta, const float* pe, int64_t rows,
+                int C, int T_tok, int F, float eps, cudaStream_t st) {
+  const int Cv = C / VecOf<T>::N;
+#define LN_CASE(VPL_, G_)                                                                         \
+  if (Cv == VPL_ * G_) {                                                                          \
+    launch_ln_grp<T, VPL_, G_>(ctx, x, y, gamma, beta, pe, rows, C, T_tok, F, eps, st);           \
+    return true;                                                                                  \
+  }
+  LN_CASE(5, 8) LN_CASE(5, 16) LN_CASE(5, 32) LN_CASE(10, 32)
+#undef LN_CASE
+  return false;
+}
+
 }  // namespace
 
 extern "C" int mmgt_groupnorm(mmgt_ctx* ctx, const void* x1, const void* x2, void* y, const float* gamma,
@@ -216,24 +367,36 @@ extern "C" int mmgt_groupnorm(mmgt_ctx* ctx, const void* x1, const void* x2, voi
   MMGT_CHECK_ARG(C / vec <= GN_THREADS * GN_MAXNV, MMGT_E_UNSUPPORTED, "groupnorm: C=%d too large", C);
   MMGT_CHECK_ARG(aligned16(x1) && aligned16(y) && (!x2 || aligned16(x2)), MMGT_E_ALIGN, "groupnorm: 16B alignment");
   MMGT_CHECK_ARG(N <= 65535, MMGT_E_INVALID, "groupnorm: N too large");
-  // ~8 blocks per SM worth of token chunks
-  int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(T, ((int64_t)ctx->num_sms * 8 + N - 1) / N));
+  const int Cv = C / vec;
+  const int nv = (Cv + GN_THREADS - 1) / GN_THREADS;
+  const int lanes = std::min(Cv, GN_THREADS);
+  const int rpp = GN_THREADS / lanes;
+  const size_t smem = sizeof(float) * 2 * C;
+  // co-resident blocks (the frame barrier inside the kernel relies on it)
+  int per_sm = 0;
+#define GN_OCC(T_, NV_) MMGT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel<T_, NV_>, GN_THREADS, smem))
+  if (dtype == MMGT_F32) { if (nv == 1) GN_OCC(float, 1); else if (nv == 2) GN_OCC(float, 2); else GN_OCC(float, 3); }
+  else if (dtype == MMGT_BF16) { if (nv == 1) GN_OCC(bf16, 1); else if (nv == 2) GN_OCC(bf16, 2); else GN_OCC(bf16, 3); }
+  else { mmgt_set_error("groupnorm: bad dtype %d", dtype); return MMGT_E_INVALID; }
+#undef GN_OCC
+  MMGT_CHECK_ARG(per_sm > 0, MMGT_E_UNSUPPORTED, "groupnorm: kernel does not fit an SM (C=%d)", C);
+  const int capacity = per_sm * ctx->num_sms;
+  // token chunks per frame: one wave of items when the tensor is large enough
+  int chunks = (int)std::max<int64_t>(1, std::min<int64_t>((T + rpp - 1) / rpp, capacity / N));
   int tok_per_block = (T + chunks - 1) / chunks;
-  int lanes = std::min(C / vec, GN_THREADS);
-  int rpp = GN_THREADS / lanes;
   tok_per_block = std::max(tok_per_block, rpp);
   chunks = (T + tok_per_block - 1) / tok_per_block;
-  MMGT_CUDA_OK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * N * groups, st));
-  dim3 grid(chunks, N);
-  size_t smem_stats = sizeof(float) * 2 * C, smem_apply = sizeof(float) * 2 * C;
-  MMGT_DISPATCH_DTYPE(dtype, T_, {
-    gn_stats_kernel<T_><<<grid, GN_THREADS, smem_stats, st>>>((const T_*)x1, (const T_*)x2, stats_ws, T, C1, C2, groups,
-                                                              tok_per_block);
-    MMGT_LAUNCH_OK(ctx);
-    gn_apply_kernel<T_><<<grid, GN_THREADS, smem_apply, st>>>((const T_*)x1, (const T_*)x2, (T_*)y, gamma, beta, stats_ws,
-                                                              T, C1, C2, groups, eps, silu, tok_per_block);
-    MMGT_LAUNCH_OK(ctx);
-  });
+  const int grid = std::min(N * chunks, capacity);
+  // workspace: 2 * N * groups doubles of statistics, then N arrival counters
+  unsigned* arrived = reinterpret_cast<unsigned*>(stats_ws + (size_t)2 * N * groups);
+  MMGT_CUDA_OK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * N * groups + sizeof(unsigned) * N, st));
+#define GN_LAUNCH(T_, NV_)                                                                                               \
+  gn_fused_kernel<T_, NV_><<<grid, GN_THREADS, smem, st>>>((const T_*)x1, (const T_*)x2, (T_*)y, gamma, beta, stats_ws,   \
+                                                           arrived, N, T, C1, C2, groups, eps, silu, tok_per_block, chunks)
+  if (dtype == MMGT_F32) { if (nv == 1) GN_LAUNCH(float, 1); else if (nv == 2) GN_LAUNCH(float, 2); else GN_LAUNCH(float, 3); }
+  else { if (nv == 1) GN_LAUNCH(bf16, 1); else if (nv == 2) GN_LAUNCH(bf16, 2); else GN_LAUNCH(bf16, 3); }
+#undef GN_LAUNCH
+  MMGT_LAUNCH_OK(ctx);
   return 0;
 }
 
@@ -248,6 +411,14 @@ extern "C" int mmgt_layernorm(mmgt_ctx* ctx, const void* x, void* y, const float
   MMGT_CHECK_ARG(aligned16(x) && aligned16(y), MMGT_E_ALIGN, "layernorm: 16B alignment");
   if (T <= 0) T = 1;
   if (F <= 0) F = 1;
+  if (dtype == MMGT_F32 || dtype == MMGT_BF16) {
+    const bool done = dtype == MMGT_F32 ? try_ln_grp<float>(ctx, x, y, gamma, beta, pe, rows, C, T, F, eps, st)
+                                        : try_ln_grp<bf16>(ctx, x, y, gamma, beta, pe, rows, C, T, F, eps, st);
+    if (done) {
+      MMGT_LAUNCH_OK(ctx);
+      return 0;
+    }
+  }
   int64_t blocks64 = std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->num_sms * 16);
   int blocks = (int)blocks64;
   if (dtype == MMGT_F32) {

@@ -112,7 +112,7 @@ class Engine:
         C2 = x2.shape[-1] if x2 is not None else 0
         T = x1.numel() // (N * C1)
         out = self.empty(*x1.shape[:-1], C1 + C2)
-        ws = self._stats(2 * N * groups)
+        ws = self._stats(2 * N * groups + (N + 1) // 2)
         ev = self._t0()
         check(self.lib.mmgt_groupnorm(self.h, _p(x1), _p(x2), _p(out), _p(gamma), _p(beta), _p(ws), N, T, C1, C2, groups,
                                        float(eps), int(silu), self.dt, _stream()), "mmgt_groupnorm")

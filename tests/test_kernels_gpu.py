@@ -47,7 +47,8 @@ def test_layout_roundtrip_and_add(dev, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("shape", [(3, 16, 64, 0), (2, 64, 320, 0), (2, 16, 1280, 640), (4, 256, 128, 64), (2, 9, 1280, 1280)])
+@pytest.mark.parametrize("shape", [(3, 16, 64, 0), (2, 64, 320, 0), (2, 16, 1280, 640), (4, 256, 128, 64), (2, 9, 1280, 1280),
+                                   (24, 4096, 320, 0), (24, 1024, 640, 320), (5, 1000, 320, 0), (300, 7, 64, 0)])
 def test_groupnorm_with_virtual_concat_and_silu(dev, dtype, shape):
     N, T, C1, C2 = shape
     eng = eng_for(dev, dtype)
@@ -68,7 +69,7 @@ def test_groupnorm_with_virtual_concat_and_silu(dev, dtype, shape):
 @pytest.mark.parametrize("C", [64, 320, 640, 1280])
 def test_layernorm_and_positional_encoding(dev, dtype, C):
     eng = eng_for(dev, dtype)
-    Fr, T = 3, 5
+    Fr, T = 3, 333
     x = rnd(2 * Fr * T, C, dev=dev, dtype=dtype, seed=7) * 3 + 1
     g, b = rnd(C, dev=dev, seed=8) * 0.1 + 1, rnd(C, dev=dev, seed=9) * 0.1
     pe = rnd(32, C, dev=dev, seed=10)
@@ -142,6 +143,70 @@ def test_gemm_geglu(dev, dtype, tc, M, C):
         assert rel_l2(out.float(), _gemm_ref(A, W, bias, None, None, 1, None, 1.0, True)) < (1e-5 if dtype == torch.float32 else 8e-3)
     finally:
         eng.ctx.set_tensor_cores(True)
+
+
+# Shapes that take the weight-stationary kernel (B tile resident in shared memory; needs many m-tiles per CTA):
+# BN = 160 (N=320), 240 (N=960), 128 (N=640, K=640), and the GEGLU BN = 256; M is ragged on purpose.
+BRES_SHAPES = [(40003, 320, 320, False), (38021, 960, 320, False), (15001, 640, 640, False), (37999, 2560, 320, True),
+               (40000, 320, 328, False)]
+
+
+@pytest.mark.parametrize("M,N,K,geglu", BRES_SHAPES)
+def test_gemm_weight_stationary_matches_streaming_and_reference(dev, M, N, K, geglu):
+    from mmgt_b200.packing import geglu_interleave
+    eng = eng_for(dev, torch.bfloat16)
+    A = rnd(M, K, dev=dev, dtype=torch.bfloat16, seed=41)
+    W = rnd(N, K, dev=dev, dtype=torch.bfloat16, seed=42, scale=K ** -0.5)
+    bias = rnd(N, dev=dev, seed=43)
+    n_out = N // 2 if geglu else N
+    res = None if geglu else rnd(M, n_out, dev=dev, dtype=torch.bfloat16, seed=44)
+    rs = None if geglu else rnd(M, dev=dev, seed=45).abs() + 0.5
+    rpg = 4096
+    rb = None if geglu else rnd((M + rpg - 1) // rpg, N, dev=dev, seed=46)
+    gb = 0
+    Wk, bk = W, bias
+    if geglu:
+        gb = eng.geglu_block(N)
+        Wk, bk = geglu_interleave(W, bias, gb)
+        Wk, bk = Wk.contiguous(), bk.contiguous()
+    outs = []
+    try:
+        for on in (True, False):
+            eng.ctx.set_resident_weights(on)
+            outs.append(eng.gemm(A, Wk, bias=bk, rowscale=rs, rowbias=rb, rows_per_group=rpg if rb is not None else 0,
+                                 residual=res, alpha=0.9, geglu_block=gb))
+    finally:
+        eng.ctx.set_resident_weights(True)
+    ref = _gemm_ref(A, W, bias, rs, rb, rpg, res, 0.9, geglu)
+    assert rel_l2(outs[0].float(), ref) < 8e-3
+    # same tile shapes are not guaranteed between the two kernels, but both accumulate in fp32 over the same K order
+    assert rel_l2(outs[0].float(), outs[1].float()) < 2e-3
+
+
+def test_gemm_geglu_fast_erf_accuracy(dev):
+    """The tensor-core GEGLU epilogue evaluates erf by Abramowitz-Stegun 7.1.26: check it against exact GELU on a
+    gate sweep (value = 1, identity-like weights) at bf16 output resolution."""
+    from mmgt_b200.packing import geglu_interleave
+    eng = eng_for(dev, torch.bfloat16)
+    C = 64
+    M = 4096
+    gate = torch.linspace(-9, 9, M, device=dev)
+    A = torch.zeros(M, C, device=dev)
+    A[:, 0] = 1.0
+    A[:, 1] = gate
+    A = A.to(torch.bfloat16)
+    W = torch.zeros(8 * C, C, device=dev)
+    W[: 4 * C, 0] = 1.0            # value columns = 1
+    W[4 * C:, 1] = 1.0             # gate columns = gate
+    bias = torch.zeros(8 * C, device=dev)
+    gb = eng.geglu_block(8 * C)
+    Wi, bi = geglu_interleave(W.to(torch.bfloat16), bias, gb)
+    out = eng.gemm(A, Wi.contiguous(), bias=bi.contiguous(), geglu_block=gb).float()
+    g = A[:, 1].float()
+    ref = F.gelu(g)[:, None].expand(M, 4 * C)
+    err = (out - ref).abs()
+    assert float((err / (ref.abs() + 1e-3)).max()) < 6e-3      # bf16 output rounding (2^-8) dominates
+    assert float(err.max()) < 2e-2
 
 
 def test_gemm_strided_views_and_f32_vectors(dev):
