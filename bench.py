@@ -251,10 +251,17 @@ def run_ours(args):
         tot = sum(x[0] for x in rows)
         pk = peaks()
         log(f"--- per-operator time over one step (event-timed, {tot:.1f} ms in instrumented ops) ---")
-        for tms, key, r in rows[:40]:
+        table = []
+        for tms, key, r in rows:
             tf = r["flops"] / (tms * 1e-3) / 1e12 if tms > 0 else 0
             gb = r["bytes"] / (tms * 1e-3) / 1e9 if tms > 0 else 0
-            log(f"{tms:9.2f} ms {100 * tms / tot:5.1f}%  calls {r['calls']:5d}  {tf:8.1f} TFLOP/s {gb:8.1f} GB/s  {key}")
+            table.append(f"{tms:9.2f} ms {100 * tms / tot:5.1f}%  calls {r['calls']:5d}  {tf:8.1f} TFLOP/s {gb:8.1f} GB/s  {key}")
+        for line in table[:40]:
+            log(line)
+        if args.ops_out:
+            with open(args.ops_out, "w") as f:
+                f.write(f"# per-operator CUDA-event time over one eager DDIM step ({tot:.1f} ms in instrumented ops); "
+                        f"step under CUDA graph: {ms_per_step:.1f} ms\n" + "\n".join(table) + "\n")
         tms, key, r = rows[0]
         if r["flops"] > 0 and key[0] in ("gemm", "conv3x3", "attention"):
             ach = r["flops"] / (tms * 1e-3) / 1e12
@@ -362,6 +369,7 @@ def main():
     ap.add_argument("--no-tc", action="store_true", help="debug: CUDA-core kernels only")
     ap.add_argument("--no-graph", action="store_true", help="debug: eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ops-out", default=None, help="write the per-operator event-time table of one step to this file")
     ap.add_argument("--cpu-budget", type=float, default=150.0)
     args = ap.parse_args()
     if args.impl == "reference":

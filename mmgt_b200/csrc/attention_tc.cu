@@ -21,7 +21,11 @@ namespace {
 
 constexpr int BQ = 128;
 constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 2 x 4 softmax warps
-constexpr int KV_STAGES = 2;
+// K / V ring depths per head-dim class (DCH = ceil(d / 64)): as deep as shared memory allows.  K is requested when
+// QK(j) retires and V when PV(j) retires; with two stages the request precedes the use by ~1.5 tile periods, less
+// than a TMA round trip, and the softmax groups end up waiting for S.
+__host__ __device__ constexpr int k_stages(int dch) { return dch == 1 ? 4 : dch == 2 ? 2 : 3; }
+__host__ __device__ constexpr int v_stages(int dch) { return dch == 1 ? 3 : 2; }
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 
 struct AttnArgs {
@@ -94,6 +98,17 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (M = 128 lanes x K 16-bit values, two per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -122,6 +137,17 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// Orders the consumers of r[] after the tcgen05.wait::ld that precedes it (the loads are asynchronous and their
+// destination registers must not be read or moved before the wait).
+__device__ __forceinline__ void pin32(uint32_t (&r)[32]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+               "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+  asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+               "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
 __device__ __forceinline__ float ex2_approx(float x) {   // single MUFU.EX2, flush-to-zero (exp2f adds denormal fix-ups)
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -142,32 +168,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
                     const __grid_constant__ CUtensorMap tmV2, const AttnArgs args) {
   constexpr int DPAD = 64 * DCH;
+  constexpr int KS = k_stages(DCH), VS = v_stages(DCH);
   constexpr int Q_BYTES = BQ * DPAD * 2;
   constexpr int KV_BYTES = BN * DPAD * 2;        // one K (or V) stage
   constexpr int KV_CHUNK = BN * 128;             // bytes of one 64-wide d chunk of a K/V stage
-  constexpr int P_BYTES = BQ * BN * 2;           // one P buffer (per softmax group)
+  // P (the bf16 probabilities, A operand of P V) lives in TMEM when the 512 columns allow it (d <= 64): the softmax
+  // warps write it with tcgen05.st and the MMA reads it in place, instead of a round trip through 128B-swizzled
+  // shared memory.  Per 128 x 128 tile that removes 64 KB of shared-memory traffic (out of ~130 KB, at 128 B/clk a
+  // ~1000 clk resource just like MUFU and the TMEM read port) and the generic->async proxy fence per tile.
+  constexpr bool P_TMEM = (2 * BN + 2 * DPAD + BN) <= 512;
+  constexpr int P_BYTES = P_TMEM ? 0 : BQ * BN * 2;   // one P buffer in shared memory (per softmax group)
   constexpr int TM_S = 0, TM_O = 2 * BN;         // S buffers at 0 / BN, O accumulators at 2BN / 2BN + DPAD
+  constexpr int TM_P = TM_O + 2 * DPAD;          // P_TMEM: packed bf16 pairs, BN / 2 columns per group
   constexpr uint32_t IDESC_QK = idesc_bf16(BN, false);
   // Only ceil(d / 16) k-steps of Q K^T and round_up(d, 16) columns of P V are real: the rest of the 64-wide
   // TMA box is zero fill (d = 40 -> 3 of 4 k-steps, N = 48 of 64).
   const int qk_steps = (args.d + 15) >> 4;
   const uint32_t IDESC_PV = idesc_bf16(qk_steps << 4, true);
-  static_assert(TM_O + 2 * DPAD <= 512, "TMEM budget");
+  static_assert(TM_O + 2 * DPAD + (P_TMEM ? BN : 0) <= 512, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Q_BYTES;
-  uint8_t* sV = sK + KV_STAGES * KV_BYTES;
-  uint8_t* sP = sV + KV_STAGES * KV_BYTES;
+  uint8_t* sV = sK + KS * KV_BYTES;
+  uint8_t* sP = sV + VS * KV_BYTES;
   float* stats = reinterpret_cast<float*>(sP + 2 * P_BYTES);          // [128][2]: (m_ref, l) of group 1
   uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 2 * BQ);
   uint64_t* q_full = bars;                     // 1
-  uint64_t* k_full = bars + 1;                 // KV_STAGES
-  uint64_t* k_empty = k_full + KV_STAGES;
-  uint64_t* v_full = k_empty + KV_STAGES;
-  uint64_t* v_empty = v_full + KV_STAGES;
-  uint64_t* s_full = v_empty + KV_STAGES;      // 2 (buffer == group == tile parity)
+  uint64_t* k_full = bars + 1;                 // KS
+  uint64_t* k_empty = k_full + KS;
+  uint64_t* v_full = k_empty + KS;             // VS
+  uint64_t* v_empty = v_full + VS;
+  uint64_t* s_full = v_empty + VS;      // 2 (buffer == group == tile parity)
   uint64_t* s_empty = s_full + 2;              // 2
   uint64_t* p_full = s_empty + 2;              // 2
   uint64_t* p_empty = p_full + 2;              // 2  ("PV of this group's tile retired": P buffer free, O_g stable)
@@ -184,9 +217,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) {
-      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-    }
+    for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 4); mbar_init(&p_full[g], 4); mbar_init(&p_empty[g], 1);
     }
@@ -206,44 +238,46 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
     for (int c = 0; c < DCH; ++c) tma_load_3d(sQ + c * (BQ * 128), &tmQ, q_full, c * 64, h, n * args.Lq + q0);
-    // K runs one tile further ahead than V: the MMA warp issues QK(j+2) before PV(j), and K(j+2) only needs QK(j)
-    // retired while V(j+1) needs PV(j-1) retired (a strict K, V, K, V order would gate K(j+2) behind PV(j-1) and put
-    // a full TMA round trip on the MMA warp's critical path).
+    // Both rings are kept full: K(j + KS) is requested as soon as QK(j) retires, V(j + VS) as soon as PV(j) does.
     auto tile_row = [&](int j) {
       const bool second = j >= tiles1;
       return second ? seg2 * args.Lk2 + (j - tiles1) * BN : n * args.Lk + j * BN;
     };
     auto load_k = [&](int j) {
-      const int st = j % KV_STAGES;
+      const int st = j % KS;
       const bool second = j >= tiles1;
-      mbar_wait(&k_empty[st], ((j / KV_STAGES) & 1) ^ 1);
+      mbar_wait(&k_empty[st], ((j / KS) & 1) ^ 1);
       mbar_expect_tx(&k_full[st], KV_BYTES);
 #pragma unroll
       for (int c = 0; c < DCH; ++c)
         tma_load_3d(sK + st * KV_BYTES + c * KV_CHUNK, second ? &tmK2 : &tmK, &k_full[st], c * 64, h, tile_row(j));
     };
     auto load_v = [&](int j) {
-      const int st = j % KV_STAGES;
+      const int st = j % VS;
       const bool second = j >= tiles1;
-      mbar_wait(&v_empty[st], ((j / KV_STAGES) & 1) ^ 1);
+      mbar_wait(&v_empty[st], ((j / VS) & 1) ^ 1);
       mbar_expect_tx(&v_full[st], KV_BYTES);
 #pragma unroll
       for (int c = 0; c < DCH; ++c)
         tma_load_3d(sV + st * KV_BYTES + c * KV_CHUNK, second ? &tmV2 : &tmV, &v_full[st], c * 64, h, tile_row(j));
     };
-    load_k(0);
-    if (num_tiles > 1) load_k(1);
-    load_v(0);
-    for (int j = 0; j < num_tiles; ++j) {
-      if (j + 2 < num_tiles) load_k(j + 2);
-      if (j + 1 < num_tiles) load_v(j + 1);
+    // The MMA warp retires QK(2), PV(0), QK(3), PV(1), ...: K(i + 2 + KS) can be requested once QK(i + 2) is done and
+    // V(i + VS) once PV(i) is; requesting in that order keeps either ring from waiting behind the other.
+    for (int j = 0; j < KS && j < num_tiles; ++j) load_k(j);
+    for (int j = 0; j < VS && j < num_tiles; ++j) load_v(j);
+    for (int j = KS; j < KS + 2 && j < num_tiles; ++j) load_k(j);
+    for (int i = 0; i < num_tiles; ++i) {
+      if (i + VS < num_tiles) load_v(i + VS);
+      if (i + 2 + KS < num_tiles) load_k(i + 2 + KS);
     }
   } else if (threadIdx.x == 32) {
     // ===================== MMA issuer =====================
+    // Issue order: QK(0), QK(1), then per tile j: QK(j+2), PV(j).  QK(j+2) only needs group (j & 1) to have pulled
+    // S(j) out of TMEM (signalled three quarters into its softmax of tile j), so S(j+2) is ready when the group
+    // finishes tile j.  (An event-driven issue order, strict ping-pong of the two groups' exp phases, three / four
+    // softmax groups on 64-key tiles and shared-memory P were all measured: 2.0-3.0 ms vs 2.0 ms for this form.)
     auto issue_qk = [&](int j) {
-      const int st = j % KV_STAGES, g = j & 1;
-      mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
-      mbar_wait(&s_empty[g], ((j >> 1) & 1) ^ 1);
+      const int st = j % KS, g = j & 1;
       tc_fence_after();
       const uint32_t tS = tmem_base + TM_S + g * BN;
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + st * KV_BYTES);
@@ -257,28 +291,41 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       umma_commit(&k_empty[st]);
       umma_commit(&s_full[g]);
     };
-    // Issue order: QK(0), QK(1), then per tile j: QK(j+2), PV(j).  QK(j+2) only needs group (j & 1) to have pulled
-    // S(j) out of TMEM, which happens at the start of its softmax of tile j, so S(j+2) is ready by the time the group
-    // finishes tile j (issuing it after PV(j) left every group idle for a PV + QK round trip per tile).
-    mbar_wait(q_full, 0);
-    issue_qk(0);
-    if (num_tiles > 1) issue_qk(1);
-    for (int j = 0; j < num_tiles; ++j) {
-      if (j + 2 < num_tiles) issue_qk(j + 2);
-      const int st = j % KV_STAGES, g = j & 1;
-      mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
-      mbar_wait(&p_full[g], (j >> 1) & 1);
+    auto issue_pv = [&](int j) {
+      const int st = j % VS, g = j & 1;
       tc_fence_after();
-      const uint32_t aP = smem_u32(sP + g * P_BYTES), aV = smem_u32(sV + st * KV_BYTES);
+      const uint32_t aV = smem_u32(sV + st * KV_BYTES);
+      const uint32_t tOg = tmem_base + TM_O + g * DPAD;
+      if constexpr (P_TMEM) {
+        const uint32_t tPg = tmem_base + TM_P + g * (BN / 2);
 #pragma unroll
-      for (int k = 0; k < BN / 16; ++k) {
-        // A = P: K-major, 64-key chunks of (128 rows x 128 B); B = V: MN-major, 16 keys = 2 x 1024 B per step
-        const uint32_t offp = (k / 4) * (BQ * 128) + (k % 4) * 32;
-        umma(tmem_base + TM_O + g * DPAD, desc_kmajor(aP + offp), desc_mnmajor(aV + k * 2048, KV_CHUNK), IDESC_PV,
-             ((j >> 1) | k) != 0);
+        for (int k = 0; k < BN / 16; ++k)   // A = P from TMEM: 16 keys = 8 packed columns per step; B = V, MN-major
+          umma_ts(tOg, tPg + k * 8, desc_mnmajor(aV + k * 2048, KV_CHUNK), IDESC_PV, ((j >> 1) | k) != 0);
+      } else {
+        const uint32_t aP = smem_u32(sP + g * P_BYTES);
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) {
+          // A = P: K-major, 64-key chunks of (128 rows x 128 B); B = V: MN-major, 16 keys = 2 x 1024 B per step
+          const uint32_t offp = (k / 4) * (BQ * 128) + (k % 4) * 32;
+          umma(tOg, desc_kmajor(aP + offp), desc_mnmajor(aV + k * 2048, KV_CHUNK), IDESC_PV, ((j >> 1) | k) != 0);
+        }
       }
       umma_commit(&v_empty[st]);
       umma_commit(&p_empty[g]);
+    };
+    mbar_wait(q_full, 0);
+    auto wait_qk = [&](int j) {
+      mbar_wait(&k_full[j % KS], (j / KS) & 1);
+      mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+      issue_qk(j);
+    };
+    wait_qk(0);
+    if (num_tiles > 1) wait_qk(1);
+    for (int j = 0; j < num_tiles; ++j) {
+      if (j + 2 < num_tiles) wait_qk(j + 2);
+      mbar_wait(&v_full[j % VS], (j / VS) & 1);
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      issue_pv(j);
     }
   } else if (warp >= 2) {
     // ===================== softmax groups / merge / epilogue =====================
@@ -289,7 +336,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float c = args.scale_log2e;
     float m_ref = -INFINITY;   // reference maximum the stored O_g / l are relative to (raw score units)
     float l_run = 0.f;
-    uint8_t* prow = sP + g * P_BYTES + row * 128;
+    const uint32_t prow_s = smem_u32(sP + g * P_BYTES + row * 128);
     const int sw = row & 7;
     const uint32_t tO = tmem_base + TM_O + g * DPAD + lane_addr;
     int it = 0;
@@ -301,73 +348,114 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int valid = min(BN, seg_len - k0);       // keys of this tile that exist
       mbar_wait(&s_full[g], it & 1);
       tc_fence_after();
-      uint32_t s[BN];
+      // Online softmax in 32-column chunks, software-pipelined against the TMEM reads: tcgen05.ld moves only
+      // 16 B/clk per scheduler (a 128 x 128 fp32 tile costs ~1000 clk, as much as its MUFU.EX2 work), so the load
+      // of chunk i+1 is in flight while chunk i goes through max / exp2 / pack.  Each chunk is scored against the
+      // running reference m_ref; when a chunk maximum exceeds it by more than 2^THRESHOLD (first tile, then rare)
+      // the reference moves and what this tile already produced (packed P chunks, l) is rescaled in registers;
+      // alpha_tile carries the factor the O accumulator in TMEM still owes.
       const uint32_t tS = tmem_base + TM_S + g * BN + lane_addr;
-#pragma unroll
-      for (int i = 0; i < BN / 32; ++i) tmem_ld32(tS + i * 32, s + i * 32);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[g]);
-
-      if (valid < BN) {   // partial last tile of a segment: mask the keys that do not exist (warp-uniform branch)
-#pragma unroll
-        for (int i = 0; i < BN; ++i)
-          if (i >= valid) s[i] = 0xff800000u;   // -inf
-      }
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains: no serial latency
-#pragma unroll
-      for (int i = 0; i < BN; i += 4) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(s[i + e]));
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      // lazy rescale: keep the old reference unless the maximum moved by more than 2^THRESHOLD
-      float alpha = 1.f;
-      const bool need = (mx - m_ref) * c > RESCALE_THRESHOLD;     // true on the first tile (m_ref = -inf)
-      if (need) {
-        alpha = ex2_approx((m_ref - mx) * c);                     // 0 on the first tile
-        m_ref = mx;
-      }
-      const float mc = m_ref * c;
-      float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t sa[32], sb[32];
       uint32_t pk[BN / 2];
+      float alpha_tile = 1.f;
+      float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+      auto chunk = [&](uint32_t (&sc)[32], const int ci) {
+        if (valid < BN) {   // partial last tile of a segment: mask the keys that do not exist (warp-uniform branch)
 #pragma unroll
-      for (int i = 0; i < BN; i += 4) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), c, -mc));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), c, -mc));
-        const float p2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), c, -mc));
-        const float p3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), c, -mc));
-        pk[i / 2] = pack_bf16(p0, p1);
-        pk[i / 2 + 1] = pack_bf16(p2, p3);
-        lsum[0] += p0; lsum[1] += p1; lsum[2] += p2; lsum[3] += p3;
+          for (int i = 0; i < 32; ++i)
+            if (ci * 32 + i >= valid) sc[i] = 0xff800000u;   // -inf
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(sc[i + e]));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        if ((mx - m_ref) * c > RESCALE_THRESHOLD) {              // true for the first chunk ever (m_ref = -inf)
+          const float a = ex2_approx((m_ref - mx) * c);          // 0 the first time
+          m_ref = mx;
+          alpha_tile *= a;
+          l_run *= a;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) lsum[e] *= a;
+          const __nv_bfloat162 a2 = __float2bfloat162_rn(a);
+#pragma unroll
+          for (int i = 0; i < BN / 2; ++i) {
+            if (i < ci * 16) {                                    // chunks of this tile that are already packed
+              __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&pk[i]);
+              v = __hmul2(v, a2);
+              pk[i] = *reinterpret_cast<uint32_t*>(&v);
+            }
+          }
+        }
+        const float mc = m_ref * c;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sc[i]), c, -mc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sc[i + 1]), c, -mc));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(sc[i + 2]), c, -mc));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(sc[i + 3]), c, -mc));
+          pk[ci * 16 + i / 2] = pack_bf16(p0, p1);
+          pk[ci * 16 + i / 2 + 1] = pack_bf16(p2, p3);
+          lsum[0] += p0; lsum[1] += p1; lsum[2] += p2; lsum[3] += p3;
+        }
+      };
+      tmem_ld32(tS, sa);
+      tmem_ld_wait();
+      pin32(sa);
+#pragma unroll
+      for (int ci = 0; ci < BN / 32; ci += 2) {
+        tmem_ld32(tS + (ci + 1) * 32, sb);                        // in flight during chunk ci
+        chunk(sa, ci);
+        tmem_ld_wait();
+        pin32(sb);
+        if (ci + 2 < BN / 32) {
+          tmem_ld32(tS + (ci + 2) * 32, sa);                      // in flight during chunk ci + 1
+        } else {
+          tc_fence_before();                                      // S is in registers: hand the buffer back
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[g]);
+        }
+        chunk(sb, ci + 1);
+        if (ci + 2 < BN / 32) {
+          tmem_ld_wait();
+          pin32(sa);
+        }
       }
-      l_run = l_run * alpha + ((lsum[0] + lsum[1]) + (lsum[2] + lsum[3]));
+      l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
 
       if (it > 0) {
         mbar_wait(&p_empty[g], (it - 1) & 1);   // this group's previous PV retired: P buffer reusable, O_g stable
         tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {
+        if (__any_sync(0xffffffffu, alpha_tile != 1.f)) {
 #pragma unroll
           for (int cc = 0; cc < DPAD / 32; ++cc) {
             uint32_t o[32];
             tmem_ld32(tO + cc * 32, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha_tile);
             tmem_st32(tO + cc * 32, o);
           }
           tmem_st_wait();
         }
       }
-      // P -> smem, K-major 128B swizzle: 16-byte unit u of row r lands at unit (u ^ (r & 7)) of its 128-byte row
+      if constexpr (P_TMEM) {
+        // P -> TMEM: lane = query row, column = key pair
+        const uint32_t tP = tmem_base + TM_P + g * (BN / 2) + lane_addr;
 #pragma unroll
-      for (int u = 0; u < BN / 8; ++u) {
-        const int chunk = u >> 3, uu = u & 7;
-        uint4 val = make_uint4(pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
-        *reinterpret_cast<uint4*>(prow + chunk * (BQ * 128) + ((uu ^ sw) << 4)) = val;
+        for (int i = 0; i < BN / 64; ++i) tmem_st32(tP + i * 32, pk + i * 32);
+        tmem_st_wait();
+      } else {
+        // P -> smem, K-major 128B swizzle: 16-byte unit u of row r lands at unit (u ^ (r & 7)) of its 128-byte row
+#pragma unroll
+        for (int u = 0; u < BN / 8; ++u) {
+          const int chunk_id = u >> 3, uu = u & 7;
+          st_shared_v4(prow_s + chunk_id * (BQ * 128) + ((uu ^ sw) << 4), pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
+        }
+        fence_async_smem();
       }
-      fence_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
@@ -465,7 +553,9 @@ int encode_qkv_map(mmgt_ctx* ctx, CUtensorMap* map, const void* base, int d, int
 
 template <int DCH, int BN>
 int launch_attn(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaStream_t st) {
-  constexpr int smem = BQ * 64 * DCH * 2 + 2 * KV_STAGES * BN * 64 * DCH * 2 + 2 * BQ * BN * 2 + BQ * 8 + 1024 + 256;
+  constexpr bool p_tmem = (2 * BN + 2 * 64 * DCH + BN) <= 512;
+  constexpr int smem = BQ * 64 * DCH * 2 + (k_stages(DCH) + v_stages(DCH)) * BN * 64 * DCH * 2 + (p_tmem ? 0 : 2 * BQ * BN * 2) + BQ * 8 + 1024 + 256;
+  static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
     MMGT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<DCH, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

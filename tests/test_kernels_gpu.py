@@ -268,7 +268,9 @@ def _attn_ref(q, k, v, heads):
 
 ATTN_CASES = [(4, 64, 64, 64, 8, 40), (3, 100, 100, 100, 8, 8), (2, 256, 256, 0, 8, 80), (2, 70, 32, 0, 8, 40),
               (2, 64, 64, 64, 8, 160), (6, 16, 16, 16, 8, 32), (3, 1024, 1024, 1024, 8, 40), (2, 4096, 4096, 4096, 8, 40),
-              (2, 300, 300, 300, 8, 80), (2, 256, 256, 256, 8, 160), (2, 1024, 32, 0, 8, 80), (3, 200, 136, 72, 8, 16)]
+              (2, 300, 300, 300, 8, 80), (2, 256, 256, 256, 8, 160), (2, 1024, 32, 0, 8, 80), (3, 200, 136, 72, 8, 16),
+              # ragged shapes: partial q tile, partial key tiles in both segments, several key tiles per softmax group
+              (3, 300, 700, 520, 8, 40), (2, 640, 1000, 0, 8, 64), (2, 128, 512, 0, 8, 16), (4, 200, 130, 450, 8, 48)]
 
 
 @pytest.mark.parametrize("dtype,tc", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)],
@@ -279,8 +281,7 @@ def test_attention_two_segments(dev, dtype, tc, N, Lq, Lk, Lk2, heads, d):
     eng.ctx.set_tensor_cores(tc)
     try:
         C = heads * d
-        qkv = rnd(N, max(Lq, Lk), 3 * C, dev=dev, dtype=dtype, seed=51)
-        q = qkv[:, :Lq, :C]
+        q = rnd(N, Lq, 3 * C, dev=dev, dtype=dtype, seed=51)[:, :, :C]     # frames are Lq rows apart (row stride 3C)
         # keys / values of a frame must be Lk consecutive rows (row stride 3C), frames Lk rows apart
         kvbuf = rnd(N, Lk, 3 * C, dev=dev, dtype=dtype, seed=53)
         k, v = kvbuf[:, :, C:2 * C], kvbuf[:, :, 2 * C:]
