@@ -155,6 +155,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     L = args.frames
@@ -236,12 +237,13 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launch stream over one more step
     roof = None
+    # every rank runs this extra eager step (it contains the per-step all-reduce); only rank 0 instruments it
+    eng.prof = {} if rank == 0 else None
+    graph, loop._graph = loop._graph, None        # per-launch events need eager launches
+    loop.step(0)
+    loop._graph = graph
+    barrier()
     if rank == 0:
-        eng.prof = {}
-        graph, loop._graph = loop._graph, None        # per-launch events need eager launches
-        loop.step(0)
-        loop._graph = graph
-        torch.cuda.synchronize()
         prof, eng.prof = eng.prof, None
         rows = []
         for key, r in prof.items():
