@@ -167,15 +167,24 @@ def run_ours(args):
     ctl.set_banks([b.to(dev) for b in host["banks"]])
     sched = DDIMSchedule.from_config()
 
+    shards = args.frame_shards
+    if world % shards:
+        raise SystemExit(f"bench.py: --frame-shards {shards} must divide the number of ranks {world}")
+    shared = {}
+
     def make_loop(d):
-        loop = DenoiseLoop(unet, sched, N_STEPS, GUIDANCE, motion_scale=[1.0, 1.0, 2.0], rank=rank, world_size=world)
-        return loop.prepare(d["latents"], d["pose"], d["audio"], d["full"], d["face"], d["lip"], d["ehs"])
+        loop = DenoiseLoop(unet, sched, N_STEPS, GUIDANCE, motion_scale=[1.0, 1.0, 2.0], rank=rank, world_size=world,
+                           frame_shards=shards, shard_group=shared.get("group"))
+        loop.prepare(d["latents"], d["pose"], d["audio"], d["full"], d["face"], d["lip"], d["ehs"])
+        shared["group"] = loop.shard_group        # one set of peer buffers serves every loop of this process
+        return loop
 
     d = to_device(host, dev)
     loop = make_loop(d)
     eng = loop.eng
     if args.no_tc:
         eng.ctx.set_tensor_cores(False)
+    eng.unfused_exchange = args.unfused_exchange
     if not args.no_graph:
         t0 = time.time()
         loop.capture_graph()
@@ -279,6 +288,8 @@ def run_ours(args):
         roof["whole_step_tflops_per_gpu"] = whole
         roof["whole_step_frac_of_peak"] = whole / pk["tf_sustained"]
 
+    if shared.get("group") is not None:
+        shared["group"].check()                   # raises if any peer barrier timed out during the run
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(unet, steps=1, warmup=0, budget_s=args.cpu_budget)
@@ -289,7 +300,9 @@ def run_ours(args):
                     higher_is_better=True, scaling="strong", vs_baseline=None, dtype=args.dtype, data="synthetic",
                     config=dict(workload=f"pose2vid 512x512 (64x64 latent), {L} frames, 30 DDIM steps, CFG 3.5, full-width "
                                          "UNet3D random-init; step = 1 DDIM step = 10 windows x 2 CFG branches",
-                                parallelism=f"(window,cfg-branch) units over {world} rank(s)",
+                                parallelism=(f"(window,cfg-branch) units over {world // shards} rank group(s)"
+                                             + (f" x {shards} frame shards per window (motion modules: peer-store "
+                                                "row exchange over NVLink)" if shards > 1 else "")),
                                 l2_policy="per-step working set (weights 2.8 GB + activations) exceeds the 126 MB L2",
                                 tensor_cores=not args.no_tc),
                     clocks=clocks, gpu_launches=launches,
@@ -373,6 +386,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops-out", default=None, help="write the per-operator event-time table of one step to this file")
     ap.add_argument("--cpu-budget", type=float, default=150.0)
+    ap.add_argument("--frame-shards", type=int, default=int(os.environ.get("MMGT_FRAME_SHARDS", "1")),
+                    help="ranks that split the frames of one context window (SURVEY 8e level 3); must divide --gpus")
+    ap.add_argument("--unfused-exchange", action="store_true",
+                    help="A/B: GEMM + stand-alone row-exchange copy instead of peer stores from the GEMM epilogue")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

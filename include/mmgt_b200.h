@@ -82,6 +82,26 @@ MMGT_API int mmgt_layernorm(mmgt_ctx*, const void* x, void* y, const float* gamm
                    const float* pe_or_null, int64_t rows, int C, int T, int F, float eps, int dtype,
                    void* stream);
 
+/* Frame-shard <-> token-shard row exchange (multi-GPU, SURVEY.md section 8e level 3) ------------------
+ * k ranks share one context window: each holds F/k of the F frames ("frame-sharded", rows (b, f_loc, t)).
+ * Around every motion module the rows switch to "token-sharded" (rows (b, f, t_loc): all F frames of T/k pixels)
+ * -- the (b f) d c <-> (b d) f c rearranges of motion_module.py:361-363,386 turned into an all-to-all.  The exchange
+ * is written by the PRODUCING kernel: destination rows are stored straight into the peers' receive buffers over
+ * NVLink (peer_base[s] = receive buffer of shard s mapped into this process; peer_base[my] is the local one).
+ *   direction 1 (frame -> token): source row m = (b*F/k + f_loc)*T + t      -> shard t / (T/k),
+ *                                 destination row (b*F + my*F/k + f_loc)*(T/k) + t % (T/k)
+ *   direction 2 (token -> frame): source row m = (b*F + f)*(T/k) + t_loc    -> shard f / (F/k),
+ *                                 destination row (b*F/k + f % (F/k))*T + my*(T/k) + t_loc */
+#define MMGT_MAX_PEERS 8
+typedef struct {
+  void* peer_base[MMGT_MAX_PEERS];
+  int k;          /* shards (2..MMGT_MAX_PEERS) */
+  int my;         /* this rank's shard */
+  int direction;  /* 1 or 2 */
+  int B, F, T;    /* samples, frames per sample of the WHOLE window, tokens per frame; F % k == 0, T % k == 0 */
+  int64_t ld;     /* leading dimension (elements) of the destination rows */
+} mmgt_row_exchange;
+
 /* GEMM / convolution --------------------------------------------------------------------------- */
 typedef struct {
   const void* A;        /* (M,K) row-major, leading dim lda (elements) */
@@ -99,6 +119,9 @@ typedef struct {
                            D[m, j] = value * gelu_erf(gate), N_out = N/2 (diffusers GEGLU) */
   int dtype;            /* storage type of A, W, D, residual */
   int out_f32;          /* 1: D is float32 regardless of dtype (small-M vectors) */
+  const mmgt_row_exchange* exchange; /* HOST pointer or NULL.  Non-NULL: the epilogue stores row m of the result to the
+                           peer / row given by the exchange instead of D + m*ldd (D is ignored, may be NULL);
+                           tensor-core path only (bf16), otherwise MMGT_E_UNSUPPORTED */
 } mmgt_gemm_params;
 /* Replaces nn.Linear / 1x1 nn.Conv2d + bias + residual adds + GEGLU (diffusers Attention.to_q/k/v/out,
  * FeedForward; transformer_3d.py:176,253; resnet.py:226,243; attention.py:730-767;
@@ -188,6 +211,30 @@ MMGT_API int mmgt_cfg_ddim_step(mmgt_ctx*, float* latents, const float* noise_ac
  * scripts/audio2vid.py:475).  tmp: >= L*Hs*S bytes scratch.  out_u8 may be NULL. */
 MMGT_API int mmgt_mask_resize(mmgt_ctx*, const uint8_t* src, uint8_t* tmp, uint8_t* out_u8, float* out_f32, int L, int Hs,
                      int Ws, int S, float offset, void* stream);
+
+/* Peer memory over NVLink (one process per GPU) -------------------------------- */
+/* The ONLY entry points that allocate: a receive buffer other processes can map (cudaMalloc + CUDA IPC).
+ * export/import move the 64-byte IPC handle through host memory (the host exchanges it with torch.distributed). */
+MMGT_API int mmgt_peer_alloc(mmgt_ctx*, int64_t bytes, void** out_ptr);
+MMGT_API int mmgt_peer_free(mmgt_ctx*, void* ptr);
+MMGT_API int mmgt_peer_export(mmgt_ctx*, const void* ptr, unsigned char* handle64_host);
+MMGT_API int mmgt_peer_import(mmgt_ctx*, const unsigned char* handle64_host, void** out_ptr);
+MMGT_API int mmgt_peer_unmap(mmgt_ctx*, void* ptr);
+typedef struct {
+  uint32_t* flags[MMGT_MAX_PEERS]; /* flags[s]: the MMGT_MAX_PEERS-slot flag array living on shard s (peer-mapped) */
+  uint32_t* epoch;                 /* local device counter, starts at 0 */
+  uint32_t* status;                /* local device word: set to 1 if a wait timed out */
+  int k, my;
+  int timeout_ms;                  /* spin limit per barrier (0 = 2000) */
+} mmgt_peer_barrier_params;
+/* Stream-ordered barrier over the k shards: every store issued by earlier kernels of this stream (including the
+ * peer stores of a row exchange) is visible to all shards once their barrier has passed.  One 32-thread kernel:
+ * release-store epoch+1 into slot `my` of every peer's flag array, acquire-spin on the own array.  CUDA-graph safe. */
+MMGT_API int mmgt_peer_barrier(mmgt_ctx*, const mmgt_peer_barrier_params*, void* stream);
+/* The same row exchange as a stand-alone copy (float32 mode, tests, unfused baseline): src (rows, C) with leading
+ * dimension lds -> peers.  rows = B*(F/k)*T. */
+MMGT_API int mmgt_row_exchange_copy(mmgt_ctx*, const void* src, int64_t lds, int C, int dtype, const mmgt_row_exchange*,
+                                    void* stream);
 
 #ifdef __cplusplus
 }

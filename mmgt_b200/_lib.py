@@ -19,7 +19,7 @@ class GemmParams(C.Structure):
                 ("rowbias", c_void_p), ("residual", c_void_p),
                 ("lda", c_int64), ("ldw", c_int64), ("ldd", c_int64), ("ldr", c_int64),
                 ("M", c_int), ("N", c_int), ("K", c_int), ("rows_per_group", c_int), ("alpha", c_float),
-                ("geglu_block", c_int), ("dtype", c_int), ("out_f32", c_int)]
+                ("geglu_block", c_int), ("dtype", c_int), ("out_f32", c_int), ("exchange", c_void_p)]
 
 
 class Conv3x3Params(C.Structure):
@@ -36,6 +36,20 @@ class AttentionParams(C.Structure):
                 ("ldo", c_int64), ("kv_batch_stride", c_int64),
                 ("N", c_int), ("Lq", c_int), ("Lk", c_int), ("Lk2", c_int), ("heads", c_int), ("d", c_int), ("B2", c_int),
                 ("scale", c_float), ("dtype", c_int)]
+
+
+MAX_PEERS = 8
+
+
+class RowExchange(C.Structure):
+    """mmgt_row_exchange: frame-shard <-> token-shard row mapping + the peers' receive buffers."""
+    _fields_ = [("peer_base", c_void_p * MAX_PEERS), ("k", c_int), ("my", c_int), ("direction", c_int),
+                ("B", c_int), ("F", c_int), ("T", c_int), ("ld", c_int64)]
+
+
+class PeerBarrierParams(C.Structure):
+    _fields_ = [("flags", c_void_p * MAX_PEERS), ("epoch", c_void_p), ("status", c_void_p), ("k", c_int), ("my", c_int),
+                ("timeout_ms", c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/mmgt_b200.h declares (tests check this)
@@ -63,6 +77,13 @@ SIGNATURES = {
     "mmgt_window_accumulate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "mmgt_cfg_ddim_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_float] * 3 + [c_void_p]),
     "mmgt_mask_resize": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_float, c_void_p]),
+    "mmgt_peer_alloc": (c_int, [c_void_p, c_int64, C.POINTER(c_void_p)]),
+    "mmgt_peer_free": (c_int, [c_void_p, c_void_p]),
+    "mmgt_peer_export": (c_int, [c_void_p, c_void_p, C.c_char_p]),
+    "mmgt_peer_import": (c_int, [c_void_p, C.c_char_p, C.POINTER(c_void_p)]),
+    "mmgt_peer_unmap": (c_int, [c_void_p, c_void_p]),
+    "mmgt_peer_barrier": (c_int, [c_void_p, C.POINTER(PeerBarrierParams), c_void_p]),
+    "mmgt_row_exchange_copy": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, C.POINTER(RowExchange), c_void_p]),
 }
 
 _lib = None

@@ -65,8 +65,9 @@ class FeedForward(nn.Module):
         self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(dropout), nn.Linear(dim * mult, dim)])
         self._pack = Pack()
 
-    def run(self, eng: Engine, x_norm, residual):
-        """x_norm: (rows, dim) already layer-normed -> ff(x_norm) + residual."""
+    def run(self, eng: Engine, x_norm, residual, exchange=None):
+        """x_norm: (rows, dim) already layer-normed -> ff(x_norm) + residual.  ``exchange`` (frame_shard.Exchange):
+        the output rows are delivered to the shards that own them instead of being returned."""
         p1, p2 = self.net[0].proj, self.net[2]
 
         def build():
@@ -75,7 +76,7 @@ class FeedForward(nn.Module):
             return dict(gb=gb, w1=run(w1, eng), b1=f32(b1, eng), w2=run(p2.weight, eng), b2=f32(p2.bias, eng))
         pk = self._pack.get(eng, [p1.weight, p1.bias, p2.weight, p2.bias], build)
         h = eng.gemm(x_norm, pk["w1"], bias=pk["b1"], geglu_block=pk["gb"])
-        return eng.gemm(h, pk["w2"], bias=pk["b2"], residual=residual)
+        return eng.gemm(h, pk["w2"], bias=pk["b2"], residual=residual, exchange=exchange)
 
 
 class _LN(nn.LayerNorm):

@@ -70,6 +70,27 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Row exchange (include/mmgt_b200.h, mmgt_row_exchange): destination of source row m, as an element pointer.
+template <typename T>
+__device__ __forceinline__ T* exchange_row_ptr(const mmgt_row_exchange& ex, int m) {
+  const int Fl = ex.F / ex.k, Tc = ex.T / ex.k;
+  int s;
+  int64_t row;
+  if (ex.direction == 1) {
+    const int n_loc = m / ex.T, t = m - n_loc * ex.T;
+    const int b = n_loc / Fl, f_loc = n_loc - b * Fl;
+    s = t / Tc;
+    row = (int64_t)(b * ex.F + ex.my * Fl + f_loc) * Tc + (t - s * Tc);
+  } else {
+    const int n = m / Tc, t_loc = m - n * Tc;
+    const int b = n / ex.F, f = n - b * ex.F;
+    s = f / Fl;
+    row = (int64_t)(b * Fl + (f - s * Fl)) * ex.T + ex.my * Tc + t_loc;
+  }
+  return reinterpret_cast<T*>(ex.peer_base[s]) + row * ex.ld;
+}
+int mmgt_row_exchange_check(const mmgt_row_exchange* ex, int64_t rows, const char* who);
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }

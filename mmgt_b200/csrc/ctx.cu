@@ -14,7 +14,7 @@ void mmgt_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* mmgt_last_error(void) { return g_err; }
-extern "C" int mmgt_abi_version(void) { return 1; }
+extern "C" int mmgt_abi_version(void) { return 2; }
 
 extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
   MMGT_CHECK_ARG(out != nullptr, MMGT_E_INVALID, "mmgt_ctx_create: out is NULL");

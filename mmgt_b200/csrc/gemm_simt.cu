@@ -208,7 +208,7 @@ int launch(mmgt_ctx* ctx, const void* A, const void* W, void* D, int M, int N, i
 extern "C" int mmgt_gemm(mmgt_ctx* ctx, const mmgt_gemm_params* p, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   MMGT_CHECK_ARG(ctx && p, MMGT_E_INVALID, "gemm: null ctx/params");
-  MMGT_CHECK_ARG(p->A && p->W && p->D && p->M > 0 && p->N > 0 && p->K > 0, MMGT_E_INVALID, "gemm: bad args");
+  MMGT_CHECK_ARG(p->A && p->W && (p->D || p->exchange) && p->M > 0 && p->N > 0 && p->K > 0, MMGT_E_INVALID, "gemm: bad args");
   MMGT_CHECK_ARG(p->lda >= p->K && p->ldw >= p->K, MMGT_E_INVALID, "gemm: leading dims smaller than K");
   MMGT_CHECK_ARG(!p->rowbias || p->rows_per_group > 0, MMGT_E_INVALID, "gemm: rowbias needs rows_per_group");
   MMGT_CHECK_ARG(!p->residual || p->ldr > 0, MMGT_E_INVALID, "gemm: residual needs ldr");
@@ -216,8 +216,10 @@ extern "C" int mmgt_gemm(mmgt_ctx* ctx, const mmgt_gemm_params* p, void* stream)
     MMGT_CHECK_ARG(p->geglu_block > 0 && p->N % (2 * p->geglu_block) == 0, MMGT_E_INVALID,
                    "gemm: N=%d not a multiple of 2*geglu_block=%d", p->N, 2 * p->geglu_block);
   }
-  MMGT_CHECK_ARG(p->ldd >= (p->geglu_block ? p->N / 2 : p->N), MMGT_E_INVALID, "gemm: ldd too small");
+  MMGT_CHECK_ARG(p->exchange || p->ldd >= (p->geglu_block ? p->N / 2 : p->N), MMGT_E_INVALID, "gemm: ldd too small");
   if (p->dtype == MMGT_BF16 && !p->out_f32 && ctx->use_tc && mmgt_gemm_tc_supported(ctx, p)) return mmgt_gemm_tc(ctx, p, st);
+  MMGT_CHECK_ARG(!p->exchange, MMGT_E_UNSUPPORTED,
+                 "gemm: the fused row exchange needs the bf16 tensor-core path (use mmgt_row_exchange_copy otherwise)");
   if (p->dtype == MMGT_F32 && p->M <= GEMV_MAX_M && !p->geglu_block && !p->rowscale && !p->rowbias && !p->residual &&
       p->K % 4 == 0 && p->lda % 4 == 0 && p->ldw % 4 == 0 && aligned16(p->A) && aligned16(p->W)) {
     int blocks = std::min((p->N + 7) / 8, ctx->num_sms * 8);

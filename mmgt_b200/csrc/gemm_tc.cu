@@ -43,6 +43,10 @@ struct TcArgs {
   // BRES only: A ring depth (runtime: what is left of shared memory after the resident weight tile)
   int stages;
   int wide_io;   // D / residual rows are 32-byte aligned: 256-bit epilogue loads and stores
+  // Row exchange (multi-GPU frame-shard <-> token-shard switch around the motion modules): when ex.direction != 0
+  // the epilogue stores row m into the receive buffer of the shard that owns it -- local or a peer's, over NVLink --
+  // so the all-to-all is part of the GEMM that produces the rows and overlaps its main loop tile by tile.
+  mmgt_row_exchange ex;
 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -370,6 +374,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (args.residual != nullptr && tile_at(it + 1, mb2, nb2) && mb2 * BM + row_in_tile < args.M)
           res_next = args.residual + (int64_t)(mb2 * BM + row_in_tile) * args.ldr + nb2 * OUT_COLS + c_begin * 16;
       }
+      bf16* drow = args.D + (int64_t)m * args.ldd;
+      if (args.ex.direction != 0 && m_ok) drow = exchange_row_ptr<bf16>(args.ex, m);
       const float rs = (args.rowscale && m_ok ? args.rowscale[m] : 1.f) * args.alpha;
       const float* rb = (args.rowbias && m_ok) ? args.rowbias + (int64_t)(m / args.rows_per_group) * args.N_out : nullptr;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -424,7 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 v[2 * e] += f.x; v[2 * e + 1] += f.y;
               }
             }
-            st_row32(args.D + (int64_t)m * args.ldd + n_out0 + c, v, wide);
+            st_row32(drow + n_out0 + c, v, wide);
           }
           if (res_next) resv[i] = ld_row32(res_next + 16 * i, wide);
         }
@@ -607,9 +613,14 @@ bool mmgt_gemm_tc_supported(const mmgt_ctx* ctx, const mmgt_gemm_params* p) {
   if (!bn) return false;
   if (p->geglu_block && p->geglu_block != 16) return false;
   if (p->K % 8 || p->lda % 8 || p->ldw % 8) return false;
-  if (!aligned16(p->A) || !aligned16(p->W) || !aligned16(p->D)) return false;
+  if (!aligned16(p->A) || !aligned16(p->W)) return false;
   const int n_out = p->geglu_block ? p->N / 2 : p->N;
-  if (n_out % 16 || p->ldd % 8) return false;
+  if (p->exchange) {
+    if (p->exchange->ld % 8 || p->exchange->ld < n_out) return false;
+  } else if (!aligned16(p->D) || p->ldd % 8) {
+    return false;
+  }
+  if (n_out % 16) return false;
   if (p->residual && (!aligned16(p->residual) || p->ldr % 8)) return false;
   if ((p->bias && !aligned16(p->bias)) || (p->rowbias && !aligned16(p->rowbias))) return false;   // float4 epilogue loads
   if (p->M < 1) return false;
@@ -645,6 +656,14 @@ int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
   a.residual = (const bf16*)p->residual; a.D = (bf16*)p->D;
   a.ldd = p->ldd; a.ldr = p->ldr; a.rows_per_group = p->rows_per_group > 0 ? p->rows_per_group : 1; a.alpha = p->alpha;
   a.wide_io = aligned32(p->D) && p->ldd % 16 == 0 && (!p->residual || (aligned32(p->residual) && p->ldr % 16 == 0));
+  if (p->exchange) {
+    int rc = mmgt_row_exchange_check(p->exchange, p->M, "gemm");
+    if (rc) return rc;
+    a.ex = *p->exchange;
+    bool w = p->exchange->ld % 16 == 0 && (!p->residual || (aligned32(p->residual) && p->ldr % 16 == 0));
+    for (int s = 0; s < p->exchange->k; ++s) w = w && aligned32(p->exchange->peer_base[s]);
+    a.wide_io = w;
+  }
   if (bres) {
     a.stages = pl.stages;
     return dispatch_bres(ctx, pl, p->geglu_block != 0, tmA, tmB, a, st);

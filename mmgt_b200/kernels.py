@@ -45,6 +45,7 @@ class Engine:
         self.h = self.ctx.handle
         self._stats_ws = None
         self._conv_ws = None
+        self.unfused_exchange = False   # A/B switch: GEMM + mmgt_row_exchange_copy instead of the fused epilogue
         self.prof = None          # optional: dict key -> [events..., flops, bytes] filled by bench.py's roofline pass
 
     # ------------------------------------------------------------------ per-launch timing (bench.py only)
@@ -131,9 +132,11 @@ class Engine:
 
     # ------------------------------------------------------------------ gemm / conv
     def gemm(self, A, W, bias=None, rowscale=None, rowbias=None, rows_per_group: int = 0, residual=None,
-             alpha: float = 1.0, geglu_block: int = 0, out=None, out_f32: bool = False, dtype=None):
+             alpha: float = 1.0, geglu_block: int = 0, out=None, out_f32: bool = False, dtype=None, exchange=None):
         """D = alpha * rowscale * (A @ W^T + bias) + rowbias[row // rows_per_group] + residual (then GEGLU).
-        A: (..., K) rows with an arbitrary leading stride on the last-but-one dim; W: (N, K)."""
+        A: (..., K) rows with an arbitrary leading stride on the last-but-one dim; W: (N, K).
+        ``exchange``: a frame_shard.Exchange -- the result rows go to the shards that own them (peer stores from
+        the GEMM epilogue on the tensor-core path, GEMM + row-exchange copy otherwise); returns None."""
         K = A.shape[-1]
         M = A.numel() // K if A.is_contiguous() else A.shape[0]
         lda = K if A.is_contiguous() else A.stride(-2)
@@ -141,11 +144,21 @@ class Engine:
         ldw = W.stride(0)
         n_out = N // 2 if geglu_block else N
         dt = self.dt if dtype is None else dt_code(dtype)
+        fused_exchange = exchange is not None and self.dtype == torch.bfloat16 and self.ctx.tensor_cores() \
+            and not self.unfused_exchange
+        if exchange is not None and not fused_exchange:
+            tmp = self.gemm(A, W, bias=bias, rowscale=rowscale, rowbias=rowbias, rows_per_group=rows_per_group,
+                            residual=residual, alpha=alpha, geglu_block=geglu_block)
+            self.row_exchange_copy(tmp.view(-1, n_out), exchange)
+            return None
+        if fused_exchange:
+            out = exchange.recv_dummy
         if out is None:
             odt = torch.float32 if out_f32 else (self.dtype if dtype is None else dtype)
             out = torch.empty(tuple(A.shape[:-1]) + (n_out,), device=self.device, dtype=odt)
         p = GemmParams()
         p.A, p.W, p.D = A.data_ptr(), W.data_ptr(), out.data_ptr()
+        p.exchange = C.addressof(exchange.desc) if fused_exchange else None
         p.bias = bias.data_ptr() if bias is not None else None
         p.rowscale = rowscale.data_ptr() if rowscale is not None else None
         p.rowbias = rowbias.data_ptr() if rowbias is not None else None
@@ -160,9 +173,17 @@ class Engine:
         p.out_f32 = int(out_f32)
         ev = self._t0()
         check(self.lib.mmgt_gemm(self.h, C.byref(p), _stream()), "mmgt_gemm")
-        self._t1(ev, ("gemm", N, K, bool(geglu_block)), 2.0 * M * N * K,
+        self._t1(ev, ("gemm_exchange" if fused_exchange else "gemm", N, K, bool(geglu_block)), 2.0 * M * N * K,
                  (M * K + N * K + M * n_out * (2 if residual is not None else 1)) * A.element_size())
-        return out
+        return None if fused_exchange else out
+
+    def row_exchange_copy(self, src, exchange):
+        """Stand-alone form of the row exchange: src (rows, C) -> the owning shards' receive buffers."""
+        rows, Cc = src.shape
+        ev = self._t0()
+        check(self.lib.mmgt_row_exchange_copy(self.h, _p(src), src.stride(0), Cc, dt_code(src.dtype), C.byref(exchange.desc),
+                                               _stream()), "mmgt_row_exchange_copy")
+        self._t1(ev, ("row_exchange_copy", Cc), 0.0, 2.0 * src.numel() * src.element_size())
 
     def conv3x3(self, x, w_krsc, bias=None, rowbias=None, frames_per_group: int = 0, residual=None, stride: int = 1,
                 upsample2x: bool = False):

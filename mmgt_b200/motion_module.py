@@ -80,8 +80,9 @@ class TemporalTransformerBlock(nn.Module):
         self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
         self.ff_norm = _LN(dim)
 
-    def run(self, eng: Engine, x, B: int, F: int, T: int):
-        """x: (B*F*T, C) rows ordered (b, f, t) (motion_module.py:236-259, 351-388)."""
+    def run(self, eng: Engine, x, B: int, F: int, T: int, exchange=None):
+        """x: (B*F*T, C) rows ordered (b, f, t) (motion_module.py:236-259, 351-388).  T may be a pixel chunk
+        (token-sharded rows); ``exchange`` sends the block output back to the frame shards."""
         for attn, norm in zip(self.attention_blocks, self.norms):
             pk = attn.packed(eng)
             # LayerNorm, then + pe[frame]: the PE feeds q, k AND v (motion_module.py:365-366)
@@ -90,7 +91,7 @@ class TemporalTransformerBlock(nn.Module):
             a = eng.temporal_attention(qkv, B, F, T, attn.heads)
             x = eng.gemm(a, pk["o"], bias=pk["bo"], residual=x)
         n = self.ff_norm.run(eng, x)
-        return self.ff.run(eng, n, x)
+        return self.ff.run(eng, n, x, exchange=exchange)
 
 
 class TemporalTransformer3DModel(nn.Module):
@@ -115,11 +116,16 @@ class TemporalTransformer3DModel(nn.Module):
         self.proj_out = nn.Linear(inner, in_channels)
         self._pack = Pack()
 
-    def run(self, eng: Engine, x, frames: int):
-        """x: (N, H, W, C) -> same (motion_module.py:146-182)."""
+    def run(self, eng: Engine, x, frames: int, shard=None):
+        """x: (N, H, W, C) -> same (motion_module.py:146-182).  With ``shard`` (frame_shard.FrameShardGroup) x holds
+        this rank's ``frames`` = F/k frames per sample: proj_in delivers its rows token-sharded to the k shards, the
+        transformer blocks run on all F frames of T/k pixels, and the feed-forward's output projection delivers
+        the rows back frame-sharded (one exchange each way per module)."""
         N, H, W, C = x.shape
         T = H * W
         B = N // frames
+        if shard is not None and shard.k > 1:
+            return self._run_sharded(eng, x, B, frames, T, shard)
         wi, bi, wo, bo = self._pack.get(
             eng, [self.proj_in.weight, self.proj_in.bias, self.proj_out.weight, self.proj_out.bias],
             lambda: (run(self.proj_in.weight, eng), f32(self.proj_in.bias, eng), run(self.proj_out.weight, eng),
@@ -129,6 +135,28 @@ class TemporalTransformer3DModel(nn.Module):
         for blk in self.transformer_blocks:
             tok = blk.run(eng, tok, B, frames, T)
         out = eng.gemm(tok, wo, bias=bo, residual=x.view(N * T, C))
+        return out.view(N, H, W, C)
+
+
+    def _run_sharded(self, eng: Engine, x, B: int, frames_local: int, T: int, shard):
+        N, H, W, C = x.shape
+        k = shard.k
+        F, Tc = frames_local * k, T // k
+        wi, bi, wo, bo = self._pack.get(
+            eng, [self.proj_in.weight, self.proj_in.bias, self.proj_out.weight, self.proj_out.bias],
+            lambda: (run(self.proj_in.weight, eng), f32(self.proj_in.bias, eng), run(self.proj_out.weight, eng),
+                     f32(self.proj_out.bias, eng)))
+        h = self.norm.run(eng, x, None, silu=False)                      # per-frame GroupNorm: frame-local
+        to_tokens = shard.exchange(1, B, F, T, self.inner_dim)
+        eng.gemm(h.view(N * T, C), wi, bias=bi, exchange=to_tokens)      # rows land on the shard owning their pixel chunk
+        shard.barrier()
+        tok = to_tokens.recv                                             # (B*F*Tc, inner): rows (b, f, t_loc)
+        to_frames = shard.exchange(2, B, F, T, self.inner_dim)
+        last = len(self.transformer_blocks) - 1
+        for i, blk in enumerate(self.transformer_blocks):
+            tok = blk.run(eng, tok, B, F, Tc, exchange=to_frames if i == last else None)
+        shard.barrier()
+        out = eng.gemm(to_frames.recv, wo, bias=bo, residual=x.view(N * T, C))
         return out.view(N, H, W, C)
 
 
@@ -147,5 +175,5 @@ class VanillaTemporalModule(nn.Module):
         if zero_initialize:
             self.temporal_transformer.proj_out = zero_module(self.temporal_transformer.proj_out)
 
-    def run(self, eng: Engine, x, frames: int):
-        return self.temporal_transformer.run(eng, x, frames)
+    def run(self, eng: Engine, x, frames: int, shard=None):
+        return self.temporal_transformer.run(eng, x, frames, shard)

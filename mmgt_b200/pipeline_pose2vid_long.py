@@ -6,8 +6,10 @@ CFG, overlap-averaged, CFG-combined and DDIM-updated -- everything on the sm_100
 passes (CLIP, VAE, ReferenceNet write pass, pose guider) remain the caller's PyTorch modules.
 
 Multi-GPU (one process per GPU): the (window, CFG-branch) forwards of a step are independent
- and are dealt round-robin to the ranks; the only exchange is one all-reduce of the
-overlap-accumulated prediction (2*4*L*h*w float32) per step.
+ and are dealt round-robin to the rank groups; the only exchange between groups is one
+all-reduce of the overlap-accumulated prediction (2*4*L*h*w float32) per step.  With ``frame_shards = k > 1`` a
+group is k ranks that split the frames of each window (frame_shard.py): their motion modules switch between the
+frame-sharded and the token-sharded layout by storing rows into each other's memory over NVLink.
 """
 import math
 from dataclasses import dataclass
@@ -30,7 +32,7 @@ class DenoiseLoop:
     def __init__(self, unet, schedule: DDIMSchedule, num_inference_steps: int, guidance_scale: float,
                  context_frames: int = 12, context_stride: int = 1, context_overlap: int = 4,
                  context_schedule: str = "uniform", motion_scale: Optional[Sequence[float]] = None,
-                 rank: int = 0, world_size: int = 1, process_group=None):
+                 rank: int = 0, world_size: int = 1, process_group=None, frame_shards: int = 1, shard_group=None):
         self.unet = unet
         self.schedule = schedule
         self.n_steps = num_inference_steps
@@ -40,6 +42,10 @@ class DenoiseLoop:
         self.context_scheduler = get_context_scheduler(context_schedule)
         self.motion_scale = motion_scale
         self.rank, self.world, self.group = rank, world_size, process_group
+        if frame_shards < 1 or world_size % frame_shards:
+            raise ValueError(f"frame_shards={frame_shards} must divide the world size {world_size}")
+        self.frame_shards = frame_shards
+        self.shard_group = shard_group   # frame_shard.FrameShardGroup; created in prepare() unless one is passed in
         self.timesteps = schedule.timesteps(num_inference_steps)
         self._graph = None
         self.graph_launches = 0
@@ -61,11 +67,20 @@ class DenoiseLoop:
         # Work units of this rank.  Whole windows (both CFG branches batched as one B=2 forward: larger GEMM M) when the
         # windows divide evenly over the ranks, otherwise single (window, branch) forwards for a finer deal.
         nw = len(self.windows)
-        if nb == 2 and nw % self.world == 0:
-            units = [(wi, (0, 1)) for wi in range(nw)]
-        else:
-            units = [(wi, (b,)) for wi in range(nw) for b in range(nb)]
-        self.units = units[self.rank::self.world]
+        k = self.frame_shards
+        n_groups, group_idx, shard = self.world // k, self.rank // k, self.rank % k
+        self.units = plan_units(nw, nb, n_groups)[group_idx]
+        if k > 1:
+            bad = [len(c) for c in self.windows if len(c) % k]
+            if bad:
+                raise ValueError(f"frame_shards={k} needs every context window to hold a multiple of {k} frames, got {bad}")
+            if self.shard_group is None:
+                from .frame_shard import FrameShardGroup, max_exchange_bytes
+                esize = torch.empty((), dtype=eng.dtype).element_size()
+                nbr_max = max(len(b) for _, b in self.units) if self.units else 1
+                width0 = u.config.block_out_channels[0] if hasattr(u.config, "block_out_channels") else 320
+                need = max_exchange_bytes(nbr_max, max(len(c) for c in self.windows) // k, h * w, width0, esize)
+                self.shard_group = FrameShardGroup.create(eng, self.rank, self.world, k, need, self.group)
         counts = torch.zeros(L, dtype=torch.float32)
         for c in self.windows:
             for f in c:
@@ -82,6 +97,9 @@ class DenoiseLoop:
         self.prepared = []
         for wi, branches in self.units:
             c = self.windows[wi]
+            if k > 1:                     # this rank's frames of the window
+                fl = len(c) // k
+                c = c[shard * fl:(shard + 1) * fl]
             idx = torch.tensor(c, dtype=torch.int32, device=dev)
             nbr = len(branches)
             x_idx = idx.repeat(nbr)                                                      # latents / pose rows (frames)
@@ -102,7 +120,7 @@ class DenoiseLoop:
             x = eng.gather_rows(lat_tok, e["x_idx"])
             nbr, F_ = len(e["branches"]), e["frames"]
             out = u.forward_tokens(eng, x, self.t_dev, e["ehs"], e["audio"], e["pose"], e["masks"][0], e["masks"][1],
-                                   e["masks"][2], self.motion_scale, nbr, F_, ref_index=e["ref"])
+                                   e["masks"][2], self.motion_scale, nbr, F_, ref_index=e["ref"], shard=self.shard_group)
             pred = eng.tokens_to_ncfhw(out, nbr, F_, torch.float32)
             eng.window_accumulate(self.noise_acc, pred, e["idx"], e["branches"][0])
 
@@ -154,6 +172,17 @@ class DenoiseLoop:
         return self.latents
 
 
+def plan_units(n_windows: int, n_branches: int, n_groups: int):
+    """Deal the (window, CFG-branch) forwards of one step to ``n_groups`` rank groups.  Whole windows (both
+    branches batched as one B=2 forward: larger GEMM M) when the windows divide evenly, otherwise single
+    (window, branch) forwards for a finer deal.  Returns one list of (window index, branches) per group."""
+    if n_branches == 2 and n_windows % n_groups == 0:
+        units = [(wi, (0, 1)) for wi in range(n_windows)]
+    else:
+        units = [(wi, (b,)) for wi in range(n_windows) for b in range(n_branches)]
+    return [units[g::n_groups] for g in range(n_groups)]
+
+
 def _pad16(m: torch.Tensor) -> torch.Tensor:
     """Rows must be multiples of 16 bytes for mmgt_gather_rows (the 8x8 level has 64 floats: fine; 4x4 not)."""
     cols = m.shape[1]
@@ -174,7 +203,8 @@ class Pose2VideoPipeline:
         self.denoising_unet, self.pose_guider, self.scheduler = denoising_unet, pose_guider, scheduler
         self.image_proj_model, self.tokenizer, self.text_encoder = image_proj_model, tokenizer, text_encoder
         self.vae_scale_factor = 8
-        self.rank, self.world_size, self.process_group = 0, 1, None
+        self.rank, self.world_size, self.process_group = 0, 1, None     # set by the launcher for multi-GPU runs
+        self.frame_shards = 1                                           # k ranks split the frames of every window
 
     def to(self, *a, **k):
         for m in (self.vae, self.image_encoder, self.reference_unet, self.denoising_unet, self.pose_guider):
@@ -249,7 +279,8 @@ class Pose2VideoPipeline:
             audio = torch.cat([torch.zeros_like(audio), audio], dim=0)
         sched = self.scheduler if isinstance(self.scheduler, DDIMSchedule) else DDIMSchedule.from_scheduler(self.scheduler)
         loop = DenoiseLoop(self.denoising_unet, sched, num_inference_steps, guidance_scale, context_frames, context_stride,
-                           context_overlap, context_schedule, motion_scale, self.rank, self.world_size, self.process_group)
+                           context_overlap, context_schedule, motion_scale, self.rank, self.world_size, self.process_group,
+                           self.frame_shards)
         loop.prepare(latents, pose_fea, audio, dup(pixel_values_full_mask), dup(pixel_values_face_mask),
                      dup(pixel_values_lip_mask), ehs)
         latents = loop.run(callback, callback_steps)

@@ -322,8 +322,10 @@ class UNet3DConditionModel(nn.Module):
         return UNet3DConditionOutput(sample=res)
 
     def forward_tokens(self, eng: Engine, x, timestep, encoder_hidden_states, audio_embedding, pose, full_mask, face_mask,
-                       body_mask, motion_scale, B: int, F: int, ref_index=None):
-        """Channels-last core: x (N,H,W,4), pose (N,H,W,320) or None -> (N,H,W,4) in the run dtype."""
+                       body_mask, motion_scale, B: int, F: int, ref_index=None, shard=None):
+        """Channels-last core: x (N,H,W,4), pose (N,H,W,320) or None -> (N,H,W,4) in the run dtype.
+        ``shard`` (frame_shard.FrameShardGroup): x / pose / audio / masks hold only this rank's F frames of a window
+        whose k*F frames are spread over k ranks; the motion modules exchange rows with the peers."""
         N, H, W, _ = x.shape
         dev = eng.device
         # --- time embedding (unet_3d.py:481-502), float32 end to end
@@ -363,7 +365,7 @@ class UNet3DConditionModel(nn.Module):
                                    for m in (full_mask, face_mask, body_mask)))
         scale = tuple(float(s) for s in motion_scale) if motion_scale is not None else (1.0, 1.0, 1.0)
         si = StepInputs(frames=F, temb_silu=temb_silu, clip=clip, seg2_index=seg2, audio_rows=audio_rows, masks=masks,
-                        scale=scale)
+                        scale=scale, shard=shard)
         reaches = self._motion_scale_reaches_audio()
 
         # --- pre-process: conv_in (+ pose features fused as the residual) (unet_3d.py:517-519)

@@ -26,6 +26,7 @@ class StepInputs:
     audio_rows: Optional[torch.Tensor]      # (N*M, 768) run dtype
     masks: Optional[list]                   # [level] -> (full, face, lip) each (N*T_level,) float32
     scale: tuple = (1.0, 1.0, 1.0)          # motion_scale as seen by MM-HAA on this call
+    shard: Optional[object] = None          # frame_shard.FrameShardGroup: ``frames`` are then this rank's F/k frames
 
 
 def _resnet(in_c, out_c, temb_c, eps, groups):
@@ -81,7 +82,7 @@ class CrossAttnDownBlock3D(nn.Module):
                 scale = si.scale if motion_scale_reaches_audio else (1.0, 1.0, 1.0)
                 x = audio.run(eng, x, si.frames, audio_rows=si.audio_rows, masks=si.masks[self.depth], scale=scale)
             if motion is not None:
-                x = motion.run(eng, x, si.frames)
+                x = motion.run(eng, x, si.frames, si.shard)
             outs.append(x)
         if self.downsamplers is not None:
             x = self.downsamplers[0].run(eng, x)
@@ -110,7 +111,7 @@ class DownBlock3D(nn.Module):
         for resnet, motion in zip(self.resnets, self.motion_modules):
             x = resnet.run(eng, x, None, si.temb_silu, si.frames)
             if motion is not None:
-                x = motion.run(eng, x, si.frames)
+                x = motion.run(eng, x, si.frames, si.shard)
             outs.append(x)
         if self.downsamplers is not None:
             x = self.downsamplers[0].run(eng, x)
@@ -145,7 +146,7 @@ class UNetMidBlock3DCrossAttn(nn.Module):
         for attn, resnet, motion in zip(self.attentions, self.resnets[1:], self.motion_modules):
             x = attn.run(eng, x, si.frames, clip_b=si.clip, seg2_index=si.seg2_index)
             if motion is not None:
-                x = motion.run(eng, x, si.frames)
+                x = motion.run(eng, x, si.frames, si.shard)
             x = resnet.run(eng, x, None, si.temb_silu, si.frames)
         return x
 
@@ -179,7 +180,7 @@ class CrossAttnUpBlock3D(nn.Module):
             x = resnet.run(eng, x, skips.pop(), si.temb_silu, si.frames)
             x = attn.run(eng, x, si.frames, clip_b=si.clip, seg2_index=si.seg2_index)
             if motion is not None:
-                x = motion.run(eng, x, si.frames)
+                x = motion.run(eng, x, si.frames, si.shard)
         if self.upsamplers is not None:
             x = self.upsamplers[0].run(eng, x)
         return x
@@ -207,7 +208,7 @@ class UpBlock3D(nn.Module):
         for resnet, motion in zip(self.resnets, self.motion_modules):
             x = resnet.run(eng, x, skips.pop(), si.temb_silu, si.frames)
             if motion is not None:
-                x = motion.run(eng, x, si.frames)
+                x = motion.run(eng, x, si.frames, si.shard)
         if self.upsamplers is not None:
             x = self.upsamplers[0].run(eng, x)
         return x

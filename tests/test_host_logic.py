@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/mmgt_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == syms, "ctypes SIGNATURES and the header disagree"
-    assert _lib.load_library().mmgt_abi_version() == 1
+    assert _lib.load_library().mmgt_abi_version() == 2
 
 
 def test_library_is_sm100a_tensor_core_code(lib_built):
@@ -165,3 +165,110 @@ def test_unit_partition_and_allreduce_gloo_world2():
     assert sorted(r[1] for r in res) == [10, 10]
     for _, _, acc in res:
         assert torch.allclose(acc, ref)
+
+
+# ---------------------------------------------------------------------------------- frame shards (SURVEY 8e level 3)
+def test_plan_units_balances_groups():
+    from mmgt_b200.pipeline_pose2vid_long import plan_units
+    assert plan_units(10, 2, 1) == [[(wi, (0, 1)) for wi in range(10)]]
+    assert [len(u) for u in plan_units(10, 2, 2)] == [5, 5] and plan_units(10, 2, 2)[0][0] == (0, (0, 1))
+    four = plan_units(10, 2, 4)                       # 10 windows do not split over 4 groups: single-branch units
+    assert [len(u) for u in four] == [5, 5, 5, 5] and all(len(b) == 1 for g in four for _, b in g)
+    assert sorted(len(u) for u in plan_units(10, 2, 8)) == [2, 2, 2, 2, 3, 3, 3, 3]
+    every = sorted((wi, b) for g in plan_units(10, 2, 8) for wi, bs in g for b in bs)
+    assert every == [(wi, b) for wi in range(10) for b in range(2)]      # each (window, branch) exactly once
+
+
+@pytest.mark.parametrize("k,B,F,T", [(2, 1, 12, 16), (4, 2, 12, 64), (2, 2, 4, 6), (3, 1, 6, 9)])
+def test_exchange_mapping_is_the_temporal_rearrange(k, B, F, T):
+    """direction 1 == '(b f) t c -> all frames of a pixel chunk', direction 2 is its inverse: together they are the
+    (b f) d c <-> (b d) f c rearranges of motion_module.py:361-363,386 split over k shards."""
+    from mmgt_b200.frame_shard import exchange_destination
+    Fl, Tc, C = F // k, T // k, 3
+    x = torch.arange(B * F * T * C, dtype=torch.float32).view(B, F, T, C)
+    frame_shards = [x[:, s * Fl:(s + 1) * Fl].reshape(-1, C) for s in range(k)]          # rows (b, f_loc, t)
+    recv = [torch.full((B * F * Tc, C), -1.0) for _ in range(k)]
+    for my in range(k):
+        for m in range(B * Fl * T):
+            s, row = exchange_destination(1, m, k, my, B, F, T)
+            recv[s][row] = frame_shards[my][m]
+    for s in range(k):
+        assert torch.equal(recv[s], x[:, :, s * Tc:(s + 1) * Tc].reshape(-1, C))         # rows (b, f, t_loc)
+    back = [torch.full((B * Fl * T, C), -1.0) for _ in range(k)]
+    for my in range(k):
+        for m in range(B * F * Tc):
+            s, row = exchange_destination(2, m, k, my, B, F, T)
+            back[s][row] = recv[my][m]
+    for s in range(k):
+        assert torch.equal(back[s], frame_shards[s])
+
+
+def _frame_shard_worker(rank, world, port, q):
+    """Two processes run a stand-in 'motion module' (mean over frames per pixel) frame-sharded: rows are exchanged with
+    the production row mapping (all_to_all here instead of NVLink peer stores), mixed over frames token-sharded and
+    exchanged back; window predictions are overlap-accumulated and all-reduced as DenoiseLoop does."""
+    import torch.distributed as dist
+    from mmgt_b200.frame_shard import exchange_destination
+    from mmgt_b200.pipeline_pose2vid_long import plan_units
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    k, L, T, C = world, 20, 8, 2
+    windows = uniform_windows(0, L)
+    video = torch.arange(L * T * C, dtype=torch.float32).view(L, T, C) * 0.01
+    units = plan_units(len(windows), 2, world // k)[rank // k]
+    acc = torch.zeros(2, L, T, C)
+
+    def exchange(direction, src, B, F):
+        Fl, Tc = F // k, T // k
+        send = [[] for _ in range(k)]
+        for m in range(src.shape[0]):
+            s, row = exchange_destination(direction, m, k, rank % k, B, F, T)
+            send[s].append((row, src[m]))
+        out = torch.zeros_like(src)
+        parcels = [None] * k       # gloo has no all_to_all: gather every rank's per-destination parcels, keep ours
+        dist.all_gather_object(parcels, [[(r, v.tolist()) for r, v in send[s]] for s in range(k)])
+        for src_rank in range(k):
+            for r, v in parcels[src_rank][rank % k]:
+                out[r] = torch.tensor(v)
+        return out
+
+    for wi, branches in units:
+        c = windows[wi]
+        B, F = len(branches), len(c)
+        Fl = F // k
+        mine = c[(rank % k) * Fl:(rank % k + 1) * Fl]
+        x = torch.stack([video[mine] * (1 + b) for b in branches]).reshape(-1, C)          # rows (b, f_loc, t)
+        tok = exchange(1, x, B, F).view(B, F, T // k, C)                                   # rows (b, f, t_loc)
+        tok = tok + tok.mean(dim=1, keepdim=True)                                          # mixes ALL frames of a pixel
+        y = exchange(2, tok.reshape(-1, C), B, F).view(B, Fl, T, C)
+        for bi, b in enumerate(branches):
+            for j, f in enumerate(mine):
+                acc[b, f] += y[bi, j]
+    dist.all_reduce(acc)
+    q.put((rank, acc))
+    dist.destroy_process_group()
+
+
+def test_frame_sharded_window_matches_unsharded_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_frame_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    L, T, C = 20, 8, 2
+    windows = uniform_windows(0, L)
+    video = torch.arange(L * T * C, dtype=torch.float32).view(L, T, C) * 0.01
+    ref = torch.zeros(2, L, T, C)
+    for c in windows:
+        for b in range(2):
+            x = video[c] * (1 + b)
+            y = x + x.mean(dim=0, keepdim=True)
+            for j, f in enumerate(c):
+                ref[b, f] += y[j]
+    for _, acc in res:
+        assert torch.allclose(acc, ref, atol=1e-5)
