@@ -145,7 +145,7 @@ class Engine:
         n_out = N // 2 if geglu_block else N
         dt = self.dt if dtype is None else dt_code(dtype)
         fused_exchange = exchange is not None and self.dtype == torch.bfloat16 and self.ctx.tensor_cores() \
-            and not self.unfused_exchange
+            and not self.unfused_exchange and self.lib.mmgt_gemm_tc_block_n(int(N)) > 0 and K % 8 == 0 and n_out % 16 == 0
         if exchange is not None and not fused_exchange:
             tmp = self.gemm(A, W, bias=bias, rowscale=rowscale, rowbias=rowbias, rows_per_group=rows_per_group,
                             residual=residual, alpha=alpha, geglu_block=geglu_block)

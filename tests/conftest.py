@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# The single-GPU emulation of frame shards runs kernels that wait for each other on two streams: every kernel must be
+# loaded before the first such wait (lazy module loading synchronises the context).  Must be set before CUDA starts.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

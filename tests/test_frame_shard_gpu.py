@@ -142,7 +142,7 @@ def _shard_inputs(win, B, F, k, s):
 @pytest.mark.parametrize("compute_dtype,k,tol", [(torch.bfloat16, 2, 2e-3), (torch.bfloat16, 4, 2e-3), (torch.float32, 2, 2e-5)],
                          ids=["bf16-k2", "bf16-k4", "f32-k2"])
 def test_tiny_unet_frame_sharded_matches_unsharded(dev, compute_dtype, k, tol):
-    """A CFG window (B=2, F=4) run as k frame shards -- every motion module exchanging rows through the fused GEMM
+    """A CFG window (B=2, F=8) run as k frame shards -- every motion module exchanging rows through the fused GEMM
     epilogue (bf16) or GEMM + exchange copy (float32) and the flag barrier -- equals the unsharded forward."""
     from mmgt_b200.frame_shard import FrameShardGroup
     spec = UNetSpec(block_out_channels=TINY)
@@ -150,7 +150,7 @@ def test_tiny_unet_frame_sharded_matches_unsharded(dev, compute_dtype, k, tol):
     unet = build_cuda_unet(TINY, sd, compute_dtype=compute_dtype)
     unet.train()
     unet.enable_gradient_checkpointing()
-    B, F, latent = 2, 4, 16
+    B, F, latent = 2, 8, 16
     inp = make_inputs(spec, F, latent)
     attach_banks(unet, spec, make_banks(spec, latent), cfg=True)
     win = to_dev(window_inputs(inp, list(range(F))), "cuda")
@@ -167,6 +167,7 @@ def test_tiny_unet_frame_sharded_matches_unsharded(dev, compute_dtype, k, tol):
     torch.cuda.synchronize()
     groups = FrameShardGroup.emulate(base_eng, k, B * (F // k) * latent * latent * TINY[0] * 4)
     outs, errors = [None] * k, []
+    ready = threading.Barrier(k)
 
     def worker(s):
         try:
@@ -174,6 +175,10 @@ def test_tiny_unet_frame_sharded_matches_unsharded(dev, compute_dtype, k, tol):
             groups[s].eng = eng
             groups[s]._barrier.timeout_ms = 1500
             with torch.cuda.stream(torch.cuda.Stream()):
+                mine = _shard_inputs(win, B, F, k, s)
+                fwd(mine, F // k, eng, None)      # warm this stream's allocator pools / kernels: no cudaMalloc or module
+                torch.cuda.current_stream().synchronize()   # load may happen while the other shard waits in a barrier
+                ready.wait(timeout=60)
                 outs[s] = fwd(_shard_inputs(win, B, F, k, s), F // k, eng, groups[s]).float()
                 torch.cuda.current_stream().synchronize()
         except Exception as e:   # noqa: BLE001
