@@ -185,6 +185,8 @@ def run_ours(args):
     if args.no_tc:
         eng.ctx.set_tensor_cores(False)
     eng.unfused_exchange = args.unfused_exchange
+    if args.pdl is not None:
+        eng.ctx.set_pdl(bool(args.pdl))
     if not args.no_graph:
         t0 = time.time()
         loop.capture_graph()
@@ -304,7 +306,7 @@ def run_ours(args):
                                              + (f" x {shards} frame shards per window (motion modules: peer-store "
                                                 "row exchange over NVLink)" if shards > 1 else "")),
                                 l2_policy="per-step working set (weights 2.8 GB + activations) exceeds the 126 MB L2",
-                                tensor_cores=not args.no_tc),
+                                tensor_cores=not args.no_tc, programmatic_dependent_launch=eng.ctx.pdl()),
                     clocks=clocks, gpu_launches=launches,
                     e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=lat_bytes + h2d_bytes(host) // N_STEPS,
                              d2h_bytes_per_step=lat_bytes, prepare_s=prep_s, step_s=e2e_step),
@@ -388,6 +390,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=150.0)
     ap.add_argument("--frame-shards", type=int, default=int(os.environ.get("MMGT_FRAME_SHARDS", "1")),
                     help="ranks that split the frames of one context window (SURVEY 8e level 3); must divide --gpus")
+    ap.add_argument("--pdl", type=int, default=None, help="1 / 0: force programmatic dependent launch on / off (default: library default)")
     ap.add_argument("--unfused-exchange", action="store_true",
                     help="A/B: GEMM + stand-alone row-exchange copy instead of peer stores from the GEMM epilogue")
     args = ap.parse_args()

@@ -51,7 +51,10 @@ MMGT_API int mmgt_ctx_destroy(mmgt_ctx* ctx);
 MMGT_API const char* mmgt_last_error(void);
 /* flag 0: enable (1) / disable (0) the tcgen05 tensor-core kernels for bf16 (default 1).
  * flag 1: number of kernels launched through this context since creation (read with value<0).
- * flag 2: enable (1) / disable (0) the weight-stationary tensor-core GEMM variant for small K (default 1). */
+ * flag 2: enable (1) / disable (0) the weight-stationary tensor-core GEMM variant for small K (default 1).
+ * flag 3: enable (1) / disable (0) programmatic dependent launch: every kernel is launched with programmatic stream
+ *         serialization and waits (griddepcontrol.wait) before its first global access, so its scheduling and
+ *         prologue overlap the tail of the previous kernel; stream semantics are unchanged. */
 MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);
 
 /* Layout ------------------------------------------------------------------------------------- */

@@ -127,6 +127,8 @@ class Context:
         self.handle = h
         self.device_index = device_index
         self.lib = lib
+        if os.environ.get("MMGT_PDL") is not None:          # A/B switch for tests and profiling
+            lib.mmgt_ctx_flag(h, 3, 1 if os.environ["MMGT_PDL"] not in ("0", "") else 0)
 
     @classmethod
     def get(cls, device_index: int) -> "Context":
@@ -143,6 +145,13 @@ class Context:
     def set_resident_weights(self, on: bool) -> bool:
         """Weight-stationary GEMM variant (small K); on by default, switchable for A/B timing and tests."""
         return bool(self.lib.mmgt_ctx_flag(self.handle, 2, 1 if on else 0))
+
+    def set_pdl(self, on: bool) -> bool:
+        """Programmatic dependent launch (kernel i+1 is scheduled while kernel i drains); see common.cuh."""
+        return bool(self.lib.mmgt_ctx_flag(self.handle, 3, 1 if on else 0))
+
+    def pdl(self) -> bool:
+        return bool(self.lib.mmgt_ctx_flag(self.handle, 3, -1))
 
     def launches(self) -> int:
         return int(self.lib.mmgt_ctx_flag(self.handle, 1, -1))

@@ -29,6 +29,7 @@ __device__ __forceinline__ void load4g(const T* p, float (&o)[4]) {
 template <typename T, int DPL>
 __global__ void __launch_bounds__(AWARPS * 32)
 attention_kernel(mmgt_attention_params p) {
+  pdl_prologue();
   extern __shared__ float smem[];
   const int d = p.d, S = padded_stride(d);
   float* Qs = smem;                 // [AQ][S]
@@ -248,6 +249,7 @@ template <int DK>
 __global__ void __launch_bounds__(TMW * 32)
 temporal_attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B, int F, int T_tok, int heads, int d,
                               float scale_log2e) {
+  pdl_prologue();
   constexpr int DP = DK + 8;
   extern __shared__ __align__(16) uint8_t smem_u8[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -378,7 +380,7 @@ extern "C" int mmgt_attention(mmgt_ctx* ctx, const mmgt_attention_params* p, voi
                                         ctx->max_smem_optin));                                                     \
       configured = true;                                                                                           \
     }                                                                                                              \
-    attention_kernel<TT, DPL><<<grid, AWARPS * 32, smem, st>>>(*p);                                                \
+    MMGT_CUDA_OK(mmgt_launch(ctx, attention_kernel<TT, DPL>, grid, dim3(AWARPS * 32), smem, st, *p));            \
   } while (0)
   MMGT_DISPATCH_DTYPE(p->dtype, T_, {
     if (dpl <= 1) LAUNCH(T_, 1);
@@ -413,7 +415,8 @@ extern "C" int mmgt_temporal_attention(mmgt_ctx* ctx, const void* qkv, void* out
                                         ctx->max_smem_optin));                                                         \
       configured = true;                                                                                               \
     }                                                                                                                  \
-    temporal_attention_mma_kernel<DK_><<<blocks, TMW * 32, smem, st>>>((const bf16*)qkv, (bf16*)out, B, F, T, heads, d, sl2); \
+    MMGT_CUDA_OK(mmgt_launch(ctx, temporal_attention_mma_kernel<DK_>, dim3(blocks), dim3(TMW * 32), smem, st,         \
+                             (const bf16*)qkv, (bf16*)out, B, F, T, heads, d, sl2));                                   \
   } while (0)
     switch (DK) {
       case 16: TLAUNCH(16); break;

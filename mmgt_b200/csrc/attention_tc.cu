@@ -209,12 +209,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
 
-  int seg2 = -1;
-  if (args.has_seg2) seg2 = args.seg2_index ? args.seg2_index[n] : 0;
-  const int tiles1 = (args.Lk + BN - 1) / BN;
-  const int tiles2 = seg2 >= 0 ? (args.Lk2 + BN - 1) / BN : 0;
-  const int num_tiles = tiles1 + tiles2;
-
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
@@ -232,6 +226,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue();   // barriers and tensor memory are set up; the first global access (seg2_index, TMA) is below
+
+  int seg2 = -1;
+  if (args.has_seg2) seg2 = args.seg2_index ? args.seg2_index[n] : 0;
+  const int tiles1 = (args.Lk + BN - 1) / BN;
+  const int tiles2 = seg2 >= 0 ? (args.Lk2 + BN - 1) / BN : 0;
+  const int num_tiles = tiles1 + tiles2;
 
   if (threadIdx.x == 0) {
     // ===================== TMA producer =====================
@@ -562,7 +563,8 @@ int launch_attn(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaS
     configured = true;
   }
   dim3 grid((a.Lq + BQ - 1) / BQ, a.heads, a.N);
-  attention_tc_kernel<DCH, BN><<<grid, NUM_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], a);
+  MMGT_CUDA_OK(mmgt_launch(ctx, attention_tc_kernel<DCH, BN>, grid, dim3(NUM_THREADS), smem, st, maps[0], maps[1], maps[2], maps[3],
+                           maps[4], a));
   MMGT_LAUNCH_OK(ctx);
   return 0;
 }

@@ -13,6 +13,7 @@ struct mmgt_ctx {
   int max_smem_optin;
   int use_tc;                 // tcgen05 kernels enabled for bf16
   int use_bres;               // weight-stationary GEMM variant enabled (small K)
+  int use_pdl;                // launch with programmatic stream serialization (kernel prologues overlap the previous tail)
   long long launches;         // kernels launched through this context
   void* encode_tiled;         // PFN of cuTensorMapEncodeTiled (resolved lazily through the runtime)
 };
@@ -48,6 +49,34 @@ void mmgt_set_error(const char* fmt, ...);
   } while (0)
 
 typedef __nv_bfloat16 bf16;
+
+// ---- Programmatic dependent launch (PDL).  A step is ~23 000 short dependent kernels replayed from one CUDA graph;
+// with the attribute below kernel i+1 is scheduled while kernel i drains: its CTAs become resident as soon as
+// resources free up, run their prologue (barrier init, TMEM allocation, tensor-map fetch) and block in
+// griddepcontrol.wait until every CTA of kernel i has finished and its stores are visible.  Every kernel launched
+// through mmgt_launch() calls pdl_prologue() before its first global-memory access, which keeps plain stream
+// semantics (the attribute without the wait would be a race).  Launched without the attribute (flag 3 off, or by
+// a plain <<<>>>) both instructions are no-ops.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t mmgt_launch(const mmgt_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                               cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }

@@ -29,6 +29,7 @@ extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   c->use_tc = 1;
   c->use_bres = 1;
+  c->use_pdl = 0;
   c->launches = 0;
   c->encode_tiled = nullptr;
   *out = c;
@@ -50,6 +51,10 @@ extern "C" int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value) {
   if (flag == 2) {
     if (value >= 0) ctx->use_bres = value ? 1 : 0;
     return ctx->use_bres;
+  }
+  if (flag == 3) {
+    if (value >= 0) ctx->use_pdl = value ? 1 : 0;
+    return ctx->use_pdl;
   }
   return MMGT_E_INVALID;
 }

@@ -256,6 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue();   // everything above touched only shared / tensor memory; global reads and writes start below
 
   const int num_tiles = args.num_m_tiles * args.num_n_tiles;
   // Tile schedule.  Streaming: tile = blockIdx.x + i * gridDim.x, n fastest (the n-tiles of one m-block run on
@@ -518,7 +519,7 @@ int launch_tc(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, con
   }
   const int tiles = a.num_m_tiles * a.num_n_tiles;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  gemm_tc_kernel<BN, CONV, GEGLU, false><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a);
+  MMGT_CUDA_OK(mmgt_launch(ctx, gemm_tc_kernel<BN, CONV, GEGLU, false>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, a));
   MMGT_LAUNCH_OK(ctx);
   return 0;
 }
@@ -580,7 +581,7 @@ int launch_bres(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, c
     configured = true;
   }
   const int smem = BRES_OVERHEAD + a.num_k_blocks * BN * BK * 2 + a.stages * A_STAGE_BYTES;
-  gemm_tc_kernel<BN, false, GEGLU, true><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a);
+  MMGT_CUDA_OK(mmgt_launch(ctx, gemm_tc_kernel<BN, false, GEGLU, true>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, a));
   MMGT_LAUNCH_OK(ctx);
   return 0;
 }

@@ -79,6 +79,7 @@ gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restric
   constexpr int VEC = VecOf<T>::N;
   typedef typename VecOf<T>::type Raw;
   constexpr int UNR = 4 / NV < 1 ? 1 : 4 / NV;   // 16-byte loads in flight per thread = UNR * NV (kept packed)
+  pdl_prologue();   // launched plainly (a memset node precedes it), but lets the NEXT kernel be scheduled early
   extern __shared__ float sm[];  // phase 1: [2][C] channel partial sums; phase 3: scale[C], shift[C]
   const int C = C1 + C2, Cv = C / VEC, C1v = C1 / VEC, cpg = C / groups;
   const int lanes = Cv < GN_THREADS ? Cv : GN_THREADS;
@@ -275,6 +276,7 @@ layernorm_grp_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __
                      float eps) {
   constexpr int VEC = VecOf<T>::N;
   extern __shared__ float gb[];   // gamma[C], beta[C]
+  pdl_prologue();
   for (int i = threadIdx.x; i < C; i += blockDim.x) { gb[i] = gamma[i]; gb[C + i] = beta[i]; }
   __syncthreads();
   const int gl = threadIdx.x % G;
@@ -332,8 +334,8 @@ void launch_ln_grp(mmgt_ctx* ctx, const void* x, void* y, const float* gamma, co
   const int rows_per_block = 256 / G;
   // two resident waves of row groups per SM slot keep the tail short
   const int64_t blocks = std::min<int64_t>((rows + rows_per_block - 1) / rows_per_block, (int64_t)ctx->num_sms * 16);
-  layernorm_grp_kernel<T, VPL, G><<<(int)blocks, 256, sizeof(float) * 2 * C, st>>>((const T*)x, (T*)y, gamma, beta, pe, rows,
-                                                                                  C, T_tok, F, eps);
+  mmgt_launch(ctx, layernorm_grp_kernel<T, VPL, G>, dim3((int)blocks), dim3(256), sizeof(float) * 2 * C, st, (const T*)x, (T*)y,
+              gamma, beta, pe, rows, C, T_tok, F, eps);
 }
 
 // Picks (VPL, G) with VPL * G == C / VEC for the widths of the full model (320 / 640 / 1280); false => generic kernel.
