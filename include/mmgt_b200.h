@@ -175,6 +175,27 @@ typedef struct {
  * (mutual_self_attention.py:157-188; attention.py:694,720-750). */
 MMGT_API int mmgt_attention(mmgt_ctx*, const mmgt_attention_params*, void* stream);
 
+/* MM-HAA audio cross-attention, three regions in one launch with the mask gate fused (attention.py:719-767).
+ * For region r in {full, face, lip}, frame n, row t, head h:
+ *   out[n*T+t, r*C + h*d + :] = gate_r * softmax_k(q3[n*T+t, r*C + h*d + :] . K_r[n, k, h] * softmax_scale) V_r[n, :, h]
+ *   out[n*T+t, 3C + r] = gate_r,  out[n*T+t, 3C+3 .. 3C+7] = 0,   gate_r = mask[r][n*T+t] * scale[r]
+ * with K_r = kv6[:, 2r*C : (2r+1)*C], V_r = kv6[:, (2r+1)*C : (2r+2)*C] (the fused to_k / to_v projections of the M
+ * audio tokens of frame n).  One GEMM of `out` (K = 3C + 8) against [Wz_0 Wo_0 | Wz_1 Wo_1 | Wz_2 Wo_2 | Wz_r bo_r | 0]
+ * then yields sum_r scale_r * zero_conv_r(mask_r * to_out_r(attn_r)) (+ bias, + residual) -- replacing, per layer,
+ * three SDPA calls, three mask multiplies, six projections and the 3-way add (attention.py:719-767).  bf16 only. */
+typedef struct {
+  const void* q3;        /* (N*T, 3C), row stride ldq */
+  const void* kv6;       /* (N*M, 6C), row stride ldkv */
+  const float* mask[3];  /* (N*T) float32 each: full, face, lip motion masks at this level */
+  float scale[3];        /* motion_scale per region (1 when it does not reach MM-HAA) */
+  void* out;             /* (N*T, ldo >= 3C + 8) */
+  int64_t ldq, ldkv, ldo;
+  int N, T, M, heads, d; /* M <= 32 audio tokens per frame; d % 8 == 0 */
+  float softmax_scale;   /* d^-0.5 */
+  int dtype;
+} mmgt_audio_attention_params;
+MMGT_API int mmgt_audio_attention(mmgt_ctx*, const mmgt_audio_attention_params*, void* stream);
+
 /* Temporal self-attention of the motion module: sequences run over the F frames of each (batch, token).
  * qkv: (B*F*T, 3*C) fused projections [q|k|v] of rows ordered (b, f, t); out: (B*F*T, C).
  * Replaces VersatileAttention.forward incl. both rearranges (motion_module.py:351-388). */

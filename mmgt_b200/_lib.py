@@ -38,6 +38,13 @@ class AttentionParams(C.Structure):
                 ("scale", c_float), ("dtype", c_int)]
 
 
+class AudioAttentionParams(C.Structure):
+    _fields_ = [("q3", c_void_p), ("kv6", c_void_p), ("mask", c_void_p * 3), ("scale", c_float * 3), ("out", c_void_p),
+                ("ldq", c_int64), ("ldkv", c_int64), ("ldo", c_int64),
+                ("N", c_int), ("T", c_int), ("M", c_int), ("heads", c_int), ("d", c_int),
+                ("softmax_scale", c_float), ("dtype", c_int)]
+
+
 MAX_PEERS = 8
 
 
@@ -68,6 +75,7 @@ SIGNATURES = {
     "mmgt_conv3x3_workspace_bytes": (c_int64, [c_void_p, C.POINTER(Conv3x3Params)]),
     "mmgt_conv3x3": (c_int, [c_void_p, C.POINTER(Conv3x3Params), c_void_p, c_int64, c_void_p]),
     "mmgt_attention": (c_int, [c_void_p, C.POINTER(AttentionParams), c_void_p]),
+    "mmgt_audio_attention": (c_int, [c_void_p, C.POINTER(AudioAttentionParams), c_void_p]),
     "mmgt_temporal_attention": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_float, c_int, c_void_p]),
     "mmgt_timestep_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "mmgt_silu_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

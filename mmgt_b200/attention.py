@@ -215,6 +215,8 @@ class AudioTemporalBasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
         self.norm3 = _LN(dim)
         self._pack = Pack()
+        self.fuse_regions = True       # bf16 tier: fused three-region kernel + one GEMM (False = per-region operators)
+        self._fused_key, self._fused_val = None, None
 
     def _packed(self, eng: Engine):
         branches = (self.attn2_0, self.attn2_1, self.attn2_2)
@@ -233,6 +235,28 @@ class AudioTemporalBasicTransformerBlock(nn.Module):
             return d
         return self._pack.get(eng, params, build)
 
+    def _fused_regions(self, eng: Engine, pk, scale):
+        """W' = [Wz_0 Wo_0 | Wz_1 Wo_1 | Wz_2 Wo_2 | Wz_0 bo_0, Wz_1 bo_1, Wz_2 bo_2, 0 x 5]  (C, 3C + 8) and
+        bias' = sum_r scale_r bz_r: with A' = [gate_r * attn_r | gate_r | 0] (mmgt_audio_attention),
+        A' W'^T + bias' = sum_r scale_r * zero_conv_r(mask_r * to_out_r(attn_r)), attention.py:719-767."""
+        key = (id(pk), scale)
+        if self._fused_key != key:
+            branches = (self.attn2_0, self.attn2_1, self.attn2_2)
+            zcs = (self.zero_conv_full, self.zero_conv_face, self.zero_conv_lip)
+            with torch.no_grad():
+                cols, tails, bias = [], [], 0.0
+                for a, z, s in zip(branches, zcs, scale):
+                    wz = z.weight.detach().double().reshape(z.weight.shape[0], -1)
+                    cols.append(wz @ a.to_out[0].weight.detach().double())
+                    tails.append(wz @ a.to_out[0].bias.detach().double())
+                    bias = bias + s * z.bias.detach().double()
+                Cc = cols[0].shape[0]
+                w = torch.cat(cols + [torch.stack(tails, dim=1), torch.zeros(Cc, 5, dtype=torch.float64, device=cols[0].device)],
+                              dim=1)
+                self._fused_val = dict(w=run(w.float(), eng), bias=f32(bias.float(), eng))
+            self._fused_key = key
+        return self._fused_val
+
     def run(self, eng: Engine, tok, audio_rows, masks, scale):
         """tok (N,T,C); audio_rows (N*M, 768) run dtype; masks: 3 x (N*T,) float32; scale: 3 floats."""
         N, T, C = tok.shape
@@ -248,6 +272,15 @@ class AudioTemporalBasicTransformerBlock(nn.Module):
         n2 = self.norm2.run(eng, x)
         q3 = eng.gemm(n2, pk["q3"]).view(N, T, 3 * C)
         M = audio_rows.shape[0] // N
+        if self.fuse_regions and eng.audio_attention_supported(M, C // heads):
+            # One kernel for the three audio cross-attentions with the mask gate and motion_scale in its epilogue, then
+            # ONE GEMM (K = 3C + 8) for to_out_r -> zero_conv_r -> weighted sum -> + x (weights pre-multiplied).
+            fz = self._fused_regions(eng, pk, tuple(float(s) for s in scale))
+            kv6 = eng.gemm(audio_rows, pk["kv6"])
+            gated = eng.audio_attention(q3.view(rows, 3 * C), kv6, masks, scale, N, T, heads)
+            x = eng.gemm(gated, fz["w"], bias=fz["bias"], residual=x)
+            n3 = self.norm3.run(eng, x)
+            return self.ff.run(eng, n3, x).view(N, T, C)
         kv6 = eng.gemm(audio_rows, pk["kv6"]).view(N, M, 6 * C)
         acc = x
         for r in range(3):

@@ -9,7 +9,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import AttentionParams, Context, Conv3x3Params, GemmParams, check
+from ._lib import AttentionParams, AudioAttentionParams, Context, Conv3x3Params, GemmParams, check
 
 _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
 
@@ -233,6 +233,32 @@ class Engine:
         lk_tot = k.shape[1] + (k2.shape[1] if k2 is not None else 0)   # upper bound: frames without segment 2 do less
         self._t1(ev, ("attention", d, k.shape[1], k2 is not None), 4.0 * N * heads * Lq * lk_tot * d,
                  (2 * q.numel() + 2 * N * lk_tot * Cc) * q.element_size())
+        return out
+
+    def audio_attention_supported(self, M: int, d: int) -> bool:
+        """The fused three-region MM-HAA kernel: bf16 tensor-core tier, <= 32 audio tokens per frame."""
+        return self.dtype == torch.bfloat16 and self.ctx.tensor_cores() and M <= 32 and d % 8 == 0 and d <= 160
+
+    def audio_attention(self, q3, kv6, masks, scale, N: int, T: int, heads: int):
+        """q3 (N*T, 3C), kv6 (N*M, 6C), masks 3 x (N*T,) float32, scale 3 floats -> (N*T, 3C + 8) gated outputs of the
+        three regions + the gate columns (layout: mmgt_audio_attention in include/mmgt_b200.h)."""
+        rows, C3 = q3.shape
+        Cc = C3 // 3
+        d = Cc // heads
+        M = kv6.shape[0] // N
+        out = self.empty(rows, C3 + 8)
+        p = AudioAttentionParams()
+        p.q3, p.kv6, p.out = q3.data_ptr(), kv6.data_ptr(), out.data_ptr()
+        for r in range(3):
+            p.mask[r] = masks[r].data_ptr()
+            p.scale[r] = float(scale[r])
+        p.ldq, p.ldkv, p.ldo = q3.stride(0), kv6.stride(0), out.stride(0)
+        p.N, p.T, p.M, p.heads, p.d = N, T, M, heads, d
+        p.softmax_scale = float(d) ** -0.5
+        p.dtype = self.dt
+        ev = self._t0()
+        check(self.lib.mmgt_audio_attention(self.h, C.byref(p), _stream()), "mmgt_audio_attention")
+        self._t1(ev, ("audio_attention", d, M), 4.0 * 3 * rows * heads * M * d, (q3.numel() + out.numel()) * q3.element_size())
         return out
 
     def temporal_attention(self, qkv, B: int, F: int, T: int, heads: int):

@@ -373,3 +373,56 @@ def test_small_pieces(dev):
     want = 0.9 * lat + (-0.3) * (u + 3.5 * (c - u))
     eng.cfg_ddim_step(lat, noise, inv, True, 3.5, 0.9, -0.3)
     assert torch.allclose(lat, want, atol=1e-5)
+
+
+@pytest.mark.parametrize("N,T,M,heads,d", [(3, 100, 32, 8, 40), (2, 256, 32, 8, 8), (2, 64, 20, 8, 80), (1, 16, 32, 4, 160),
+                                           (2, 300, 32, 8, 16), (2, 1024, 32, 8, 40)])
+def test_audio_attention_three_regions_gated(dev, N, T, M, heads, d):
+    """mmgt_audio_attention: the three MM-HAA cross-attentions (attention.py:719-750) with mask gate x motion_scale in
+    the epilogue, plus the gate columns, against softmax(q k^T) v * gate in float32 from the same bf16 inputs."""
+    eng = eng_for(dev, torch.bfloat16)
+    C = heads * d
+    q3 = rnd(N * T, 3 * C, dev=dev, dtype=torch.bfloat16, seed=31)
+    kv6 = rnd(N * M, 6 * C, dev=dev, dtype=torch.bfloat16, seed=32)
+    masks = [torch.rand(N * T, generator=torch.Generator().manual_seed(40 + r)).to(dev) + (1.0 if r == 0 else 0.0) for r in range(3)]
+    scale = (1.0, 1.5, 2.0)
+    out = eng.audio_attention(q3, kv6, masks, scale, N, T, heads).float()
+    assert out.shape == (N * T, 3 * C + 8)
+    for r in range(3):
+        q = q3[:, r * C:(r + 1) * C].float().view(N, T, heads, d).transpose(1, 2)
+        k = kv6[:, 2 * r * C:(2 * r + 1) * C].float().view(N, M, heads, d).transpose(1, 2)
+        v = kv6[:, (2 * r + 1) * C:(2 * r + 2) * C].float().view(N, M, heads, d).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(N * T, C)
+        gate = masks[r] * scale[r]
+        assert rel_l2(out[:, r * C:(r + 1) * C], o * gate[:, None]) < TOL[torch.bfloat16]
+        assert torch.equal(out[:, 3 * C + r], gate.to(torch.bfloat16).float())
+    assert torch.count_nonzero(out[:, 3 * C + 3:]) == 0
+
+
+def test_mmhaa_fused_regions_match_per_region_operators(dev):
+    """AudioTemporalBasicTransformerBlock: fused three-region kernel + one K = 3C+8 GEMM vs the per-region chain
+    (attention -> to_out * mask -> zero_conv * scale -> sum), both bf16, against each other and a float32 run."""
+    from mmgt_b200.attention import AudioTemporalBasicTransformerBlock
+    torch.manual_seed(5)
+    C, heads, N, T, M = 320, 8, 4, 256, 32
+    blk = AudioTemporalBasicTransformerBlock(C, heads, C // heads, cross_attention_dim=768, depth=0, unet_block_name="down",
+                                             stack_enable_blocks_name=["down"], stack_enable_blocks_depth=[0]).to(dev)
+    with torch.no_grad():
+        for z in (blk.zero_conv_full, blk.zero_conv_face, blk.zero_conv_lip):
+            z.weight.normal_(0, 0.05)
+            z.bias.normal_(0, 0.05)
+    x = rnd(N, T, C, dev=dev, seed=51)
+    audio = rnd(N * M, 768, dev=dev, seed=52)
+    masks = [torch.rand(N * T, generator=torch.Generator().manual_seed(60 + r)).to(dev) for r in range(3)]
+    scale = (1.0, 1.0, 2.0)
+    e32, e16 = eng_for(dev, torch.float32), eng_for(dev, torch.bfloat16)
+    ref = blk.run(e32, x, audio, masks, scale).float()
+    xb, ab = x.to(torch.bfloat16), audio.to(torch.bfloat16)
+    blk.fuse_regions = True
+    fused = blk.run(e16, xb, ab, masks, scale).float()
+    blk.fuse_regions = False
+    chain = blk.run(e16, xb, ab, masks, scale).float()
+    e_f, e_c = rel_l2(fused, ref), rel_l2(chain, ref)
+    print(f"MM-HAA block bf16 vs float32: fused {e_f:.3e}, per-region {e_c:.3e}")
+    assert e_f < 1.2e-2 and e_c < 1.2e-2
+    assert e_f < 1.5 * e_c + 1e-3
