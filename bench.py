@@ -142,6 +142,18 @@ def h2d_bytes(v):
     return tot
 
 
+def _describe(world, shards, remainder, loop):
+    whole = sum(1 for _, _, sh in loop.units if not sh)
+    shared = sum(1 for _, _, sh in loop.units if sh)
+    if shards == 1 or shared == 0:
+        return f"(window,cfg-branch) forwards dealt whole over {world} rank(s)"
+    if remainder:
+        return (f"(window,cfg-branch) forwards over {world} ranks: {whole} whole per rank + {shared} shared by each group of "
+                f"{shards} ranks as frame shards (motion modules: peer-store row exchange over NVLink)")
+    return (f"(window,cfg-branch) forwards over {world // shards} rank group(s) x {shards} frame shards per window "
+            "(motion modules: peer-store row exchange over NVLink)")
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch.distributed as dist
@@ -167,17 +179,33 @@ def run_ours(args):
     ctl.set_banks([b.to(dev) for b in host["banks"]])
     sched = DDIMSchedule.from_config()
 
-    shards = args.frame_shards
+    # Schedule.  Default ("auto"): whole (window, branch) forwards dealt to the ranks; when they do not divide (20 over 8
+    # GPUs) each pair of ranks also shares one forward, frame-sharded (2 + 1/2 forwards per rank instead of 3 / 2).
+    shards, remainder = args.frame_shards, args.shard_remainder
+    n_units = UNITS_PER_STEP * L // VIDEO_LENGTH if L % VIDEO_LENGTH == 0 else None
+    if shards == 0:
+        shards, remainder = 1, False
+        if n_units and world % 2 == 0 and n_units % world and (n_units % world) % (world // 2) == 0:
+            shards, remainder = 2, True
     if world % shards:
         raise SystemExit(f"bench.py: --frame-shards {shards} must divide the number of ranks {world}")
-    shared = {}
+    shared = {"shards": shards, "remainder": remainder}
 
     def make_loop(d):
-        loop = DenoiseLoop(unet, sched, N_STEPS, GUIDANCE, motion_scale=[1.0, 1.0, 2.0], rank=rank, world_size=world,
-                           frame_shards=shards, shard_group=shared.get("group"))
-        loop.prepare(d["latents"], d["pose"], d["audio"], d["full"], d["face"], d["lip"], d["ehs"])
-        shared["group"] = loop.shard_group        # one set of peer buffers serves every loop of this process
-        return loop
+        for attempt in range(2):
+            loop = DenoiseLoop(unet, sched, N_STEPS, GUIDANCE, motion_scale=[1.0, 1.0, 2.0], rank=rank, world_size=world,
+                               frame_shards=shared["shards"], shard_group=shared.get("group"),
+                               shard_remainder=shared["remainder"])
+            try:
+                loop.prepare(d["latents"], d["pose"], d["audio"], d["full"], d["face"], d["lip"], d["ehs"])
+            except RuntimeError as e:
+                if attempt == 0 and args.frame_shards == 0 and "peer memory" in str(e):   # raised on every rank together
+                    log(f"[rank {rank}] {e}; falling back to whole forwards only")
+                    shared.update(shards=1, remainder=False)
+                    continue
+                raise
+            shared["group"] = loop.shard_group        # one set of peer buffers serves every loop of this process
+            return loop
 
     d = to_device(host, dev)
     loop = make_loop(d)
@@ -302,9 +330,7 @@ def run_ours(args):
                     higher_is_better=True, scaling="strong", vs_baseline=None, dtype=args.dtype, data="synthetic",
                     config=dict(workload=f"pose2vid 512x512 (64x64 latent), {L} frames, 30 DDIM steps, CFG 3.5, full-width "
                                          "UNet3D random-init; step = 1 DDIM step = 10 windows x 2 CFG branches",
-                                parallelism=(f"(window,cfg-branch) units over {world // shards} rank group(s)"
-                                             + (f" x {shards} frame shards per window (motion modules: peer-store "
-                                                "row exchange over NVLink)" if shards > 1 else "")),
+                                parallelism=_describe(world, shared["shards"], shared["remainder"], loop),
                                 l2_policy="per-step working set (weights 2.8 GB + activations) exceeds the 126 MB L2",
                                 tensor_cores=not args.no_tc, programmatic_dependent_launch=eng.ctx.pdl()),
                     clocks=clocks, gpu_launches=launches,
@@ -388,8 +414,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops-out", default=None, help="write the per-operator event-time table of one step to this file")
     ap.add_argument("--cpu-budget", type=float, default=150.0)
-    ap.add_argument("--frame-shards", type=int, default=int(os.environ.get("MMGT_FRAME_SHARDS", "1")),
-                    help="ranks that split the frames of one context window (SURVEY 8e level 3); must divide --gpus")
+    ap.add_argument("--frame-shards", type=int, default=int(os.environ.get("MMGT_FRAME_SHARDS", "0")),
+                    help="ranks that split the frames of one context window (SURVEY 8e level 3); must divide --gpus; "
+                         "0 = auto: whole forwards, plus frame-sharded leftovers when they do not divide over the ranks")
+    ap.add_argument("--shard-remainder", action="store_true",
+                    help="with --frame-shards k: frame-shard only the forwards left over by the whole deal")
     ap.add_argument("--pdl", type=int, default=None, help="1 / 0: force programmatic dependent launch on / off (default: library default)")
     ap.add_argument("--unfused-exchange", action="store_true",
                     help="A/B: GEMM + stand-alone row-exchange copy instead of peer stores from the GEMM epilogue")

@@ -106,19 +106,31 @@ class FrameShardGroup:
         g0 = (rank // k) * k
         shard = rank - g0
         recv_ptrs, flag_ptrs, mapped = [[0] * k, [0] * k], [0] * k, []
-        for s in range(k):
-            if s == shard:
-                ptrs = mine
-            else:
-                ptrs = []
-                for i in range(3):
-                    p = C.c_void_p()
-                    check(lib.mmgt_peer_import(h, gathered[g0 + s][64 * i:64 * (i + 1)], C.byref(p)),
-                          f"mmgt_peer_import (shard {s}: CUDA IPC / NVLink peer access is required for frame sharding)")
-                    mapped.append(p.value)
-                    ptrs.append(p.value)
-            recv_ptrs[0][s], recv_ptrs[1][s], flag_ptrs[s] = ptrs
-        dist.barrier(group=process_group)
+        error = None
+        try:
+            for s in range(k):
+                if s == shard:
+                    ptrs = mine
+                else:
+                    ptrs = []
+                    for i in range(3):
+                        p = C.c_void_p()
+                        check(lib.mmgt_peer_import(h, gathered[g0 + s][64 * i:64 * (i + 1)], C.byref(p)),
+                              f"mmgt_peer_import (shard {s}: CUDA IPC / NVLink peer access is required for frame sharding)")
+                        mapped.append(p.value)
+                        ptrs.append(p.value)
+                recv_ptrs[0][s], recv_ptrs[1][s], flag_ptrs[s] = ptrs
+        except Exception as e:   # noqa: BLE001 -- every rank must learn about it: the others are about to wait for us
+            error = e
+        ok = torch.tensor([0.0 if error is not None else 1.0], device=eng.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+        if float(ok) != 1.0:
+            for p in mapped:
+                lib.mmgt_peer_unmap(h, C.c_void_p(p))
+            dist.barrier(group=process_group)
+            for p in owned:
+                lib.mmgt_peer_free(h, C.c_void_p(p))
+            raise RuntimeError(f"frame-shard peer memory could not be mapped on every rank ({error or 'a peer failed'})")
         return cls(eng, k, shard, recv_ptrs, flag_ptrs, buf_bytes, owned, mapped)
 
     @classmethod

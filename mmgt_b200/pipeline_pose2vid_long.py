@@ -32,7 +32,8 @@ class DenoiseLoop:
     def __init__(self, unet, schedule: DDIMSchedule, num_inference_steps: int, guidance_scale: float,
                  context_frames: int = 12, context_stride: int = 1, context_overlap: int = 4,
                  context_schedule: str = "uniform", motion_scale: Optional[Sequence[float]] = None,
-                 rank: int = 0, world_size: int = 1, process_group=None, frame_shards: int = 1, shard_group=None):
+                 rank: int = 0, world_size: int = 1, process_group=None, frame_shards: int = 1, shard_group=None,
+                 shard_remainder: bool = False):
         self.unet = unet
         self.schedule = schedule
         self.n_steps = num_inference_steps
@@ -45,6 +46,9 @@ class DenoiseLoop:
         if frame_shards < 1 or world_size % frame_shards:
             raise ValueError(f"frame_shards={frame_shards} must divide the world size {world_size}")
         self.frame_shards = frame_shards
+        # shard_remainder: deal whole (window, branch) forwards to ALL ranks and frame-shard only the ones left over when
+        # the count does not divide (20 forwards on 8 GPUs: 2 whole ones per rank + 1 shared by each pair of ranks)
+        self.shard_remainder = bool(shard_remainder) and frame_shards > 1
         self.shard_group = shard_group   # frame_shard.FrameShardGroup; created in prepare() unless one is passed in
         self.timesteps = schedule.timesteps(num_inference_steps)
         self._graph = None
@@ -69,15 +73,25 @@ class DenoiseLoop:
         nw = len(self.windows)
         k = self.frame_shards
         n_groups, group_idx, shard = self.world // k, self.rank // k, self.rank % k
-        self.units = plan_units(nw, nb, n_groups)[group_idx]
-        if k > 1:
+        need_group = k > 1                  # rank-independent: creating the peer buffers is a collective
+        if self.shard_remainder and (nw * nb) % self.world == 0:
+            self.units = [(wi, b, False) for wi, b in plan_units(nw, nb, self.world)[self.rank]]      # nothing left over
+            need_group = False
+        elif self.shard_remainder:
+            whole, shared = plan_units_mixed(nw, nb, self.world, k)
+            # the shared forwards go first: all ranks leave the per-step all-reduce together, so the peers meet at once
+            self.units = [(wi, b, True) for wi, b in shared[group_idx]] + [(wi, b, False) for wi, b in whole[self.rank]]
+            need_group = any(len(s) for s in shared)
+        else:
+            self.units = [(wi, b, k > 1) for wi, b in plan_units(nw, nb, n_groups)[group_idx]]
+        if need_group:
             bad = [len(c) for c in self.windows if len(c) % k]
             if bad:
                 raise ValueError(f"frame_shards={k} needs every context window to hold a multiple of {k} frames, got {bad}")
             if self.shard_group is None:
                 from .frame_shard import FrameShardGroup, max_exchange_bytes
                 esize = torch.empty((), dtype=eng.dtype).element_size()
-                nbr_max = max(len(b) for _, b in self.units) if self.units else 1
+                nbr_max = max([len(b) for _, b, sh in self.units if sh] or [1])
                 width0 = u.config.block_out_channels[0] if hasattr(u.config, "block_out_channels") else 320
                 need = max_exchange_bytes(nbr_max, max(len(c) for c in self.windows) // k, h * w, width0, esize)
                 self.shard_group = FrameShardGroup.create(eng, self.rank, self.world, k, need, self.group)
@@ -95,9 +109,9 @@ class DenoiseLoop:
         masks = [[m.to(device=dev, dtype=torch.float32).contiguous() for m in ms] for ms in (full_mask, face_mask, lip_mask)]
         mask_pads = [[_pad16(m) for m in ms] for ms in masks]
         self.prepared = []
-        for wi, branches in self.units:
+        for wi, branches, sharded in self.units:
             c = self.windows[wi]
-            if k > 1:                     # this rank's frames of the window
+            if sharded:                   # this rank's frames of the window
                 fl = len(c) // k
                 c = c[shard * fl:(shard + 1) * fl]
             idx = torch.tensor(c, dtype=torch.int32, device=dev)
@@ -110,7 +124,8 @@ class DenoiseLoop:
             ref = [None if (self.cfg and b == 0) else b for b in branches]
             self.prepared.append(dict(idx=idx, x_idx=x_idx, frames=len(c), branches=branches,
                                       pose=eng.gather_rows(pose_tok, x_idx) if pose_tok is not None else None,
-                                      audio=aud, masks=mk, ehs=ehs[list(branches)].contiguous(), ref=ref))
+                                      audio=aud, masks=mk, ehs=ehs[list(branches)].contiguous(), ref=ref,
+                                      shard=self.shard_group if sharded else None))
         return self
 
     # ------------------------------------------------------------------ the hot loop
@@ -120,7 +135,7 @@ class DenoiseLoop:
             x = eng.gather_rows(lat_tok, e["x_idx"])
             nbr, F_ = len(e["branches"]), e["frames"]
             out = u.forward_tokens(eng, x, self.t_dev, e["ehs"], e["audio"], e["pose"], e["masks"][0], e["masks"][1],
-                                   e["masks"][2], self.motion_scale, nbr, F_, ref_index=e["ref"], shard=self.shard_group)
+                                   e["masks"][2], self.motion_scale, nbr, F_, ref_index=e["ref"], shard=e["shard"])
             pred = eng.tokens_to_ncfhw(out, nbr, F_, torch.float32)
             eng.window_accumulate(self.noise_acc, pred, e["idx"], e["branches"][0])
 
@@ -183,6 +198,26 @@ def plan_units(n_windows: int, n_branches: int, n_groups: int):
     return [units[g::n_groups] for g in range(n_groups)]
 
 
+def plan_units_mixed(n_windows: int, n_branches: int, world: int, k: int):
+    """Whole forwards for every rank plus frame-sharded leftovers: the n = n_windows * n_branches single-branch forwards
+    are dealt whole, n // world to each of the ``world`` ranks; the n % world left over are shared out to the world // k
+    groups of k ranks, which run them frame-sharded (when they do not divide over the groups either, they are dealt
+    whole to the first ranks).  Returns (whole: one list per rank, shared: one list per group)."""
+    units = [(wi, (b,)) for wi in range(n_windows) for b in range(n_branches)]
+    groups = world // k
+    per_rank, rem = divmod(len(units), world)
+    whole = [units[r * per_rank:(r + 1) * per_rank] for r in range(world)]
+    left = units[per_rank * world:]
+    shared = [[] for _ in range(groups)]
+    if rem and rem % groups == 0:
+        for i, u in enumerate(left):
+            shared[i % groups].append(u)
+    else:
+        for i, u in enumerate(left):
+            whole[i].append(u)
+    return whole, shared
+
+
 def _pad16(m: torch.Tensor) -> torch.Tensor:
     """Rows must be multiples of 16 bytes for mmgt_gather_rows (the 8x8 level has 64 floats: fine; 4x4 not)."""
     cols = m.shape[1]
@@ -204,7 +239,8 @@ class Pose2VideoPipeline:
         self.image_proj_model, self.tokenizer, self.text_encoder = image_proj_model, tokenizer, text_encoder
         self.vae_scale_factor = 8
         self.rank, self.world_size, self.process_group = 0, 1, None     # set by the launcher for multi-GPU runs
-        self.frame_shards = 1                                           # k ranks split the frames of every window
+        self.frame_shards = 1                                           # k ranks split the frames of a window
+        self.shard_remainder = False                                    # only the forwards left over by the whole deal
 
     def to(self, *a, **k):
         for m in (self.vae, self.image_encoder, self.reference_unet, self.denoising_unet, self.pose_guider):
@@ -280,7 +316,7 @@ class Pose2VideoPipeline:
         sched = self.scheduler if isinstance(self.scheduler, DDIMSchedule) else DDIMSchedule.from_scheduler(self.scheduler)
         loop = DenoiseLoop(self.denoising_unet, sched, num_inference_steps, guidance_scale, context_frames, context_stride,
                            context_overlap, context_schedule, motion_scale, self.rank, self.world_size, self.process_group,
-                           self.frame_shards)
+                           self.frame_shards, shard_remainder=self.shard_remainder)
         loop.prepare(latents, pose_fea, audio, dup(pixel_values_full_mask), dup(pixel_values_face_mask),
                      dup(pixel_values_lip_mask), ehs)
         latents = loop.run(callback, callback_steps)

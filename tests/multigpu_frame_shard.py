@@ -72,6 +72,29 @@ def main():
         diff = rel_l2(res[world], res[1])
         print(f"[rank {rank}] {dtype}: frame-sharded vs window-parallel rel-L2 {diff:.3e}", flush=True)
         ok = ok and diff < (1e-5 if dtype == torch.float32 else 5e-3)
+        # Mixed schedule (what bench.py uses when the forwards do not divide over the ranks): without CFG the 3 windows
+        # are 3 forwards for 2 ranks -> one whole forward each + one shared as two frame shards; vs all-whole dealing.
+        attach_banks(unet, spec, banks, cfg=False)
+        nocfg = dict(audio=d["audio"][1:2], ehs=d["encoder_hidden_states"][1:2],
+                     masks=[[m[L:] for m in d[name]] for name in ("full_mask", "face_mask", "lip_mask")])
+        mixed = {}
+        for remainder in (True, False):
+            loop = DenoiseLoop(unet, DDIMSchedule.from_config(), n_steps, 1.0, motion_scale=inp["motion_scale"], rank=rank,
+                               world_size=world, frame_shards=world if remainder else 1, shard_remainder=remainder)
+            loop.prepare(d["latents"], d["pose_fea"], nocfg["audio"], nocfg["masks"][0], nocfg["masks"][1], nocfg["masks"][2],
+                         nocfg["ehs"])
+            if remainder:
+                assert sorted(sh for _, _, sh in loop.units) == [False, True], loop.units
+            if dtype == torch.bfloat16:
+                loop.capture_graph()
+            loop.step(0)
+            mixed[remainder] = loop.step(1).clone()
+            if loop.shard_group is not None:
+                loop.shard_group.check()
+                loop.shard_group.close()
+        diff = rel_l2(mixed[True], mixed[False])
+        print(f"[rank {rank}] {dtype}: whole + shared-remainder schedule vs whole-only rel-L2 {diff:.3e}", flush=True)
+        ok = ok and diff < (1e-5 if dtype == torch.float32 else 5e-3)
         del unet
         torch.cuda.empty_cache()
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)

@@ -272,3 +272,15 @@ def test_frame_sharded_window_matches_unsharded_gloo_world2():
                 ref[b, f] += y[j]
     for _, acc in res:
         assert torch.allclose(acc, ref, atol=1e-5)
+
+
+def test_plan_units_mixed_shares_the_remainder():
+    from mmgt_b200.pipeline_pose2vid_long import plan_units_mixed
+    whole, shared = plan_units_mixed(10, 2, 8, 2)          # 20 forwards on 8 GPUs: 2 whole each + 1 per pair
+    assert [len(w) for w in whole] == [2] * 8 and [len(s) for s in shared] == [1] * 4
+    every = sorted(u for part in whole + shared for u in part)
+    assert every == sorted((wi, (b,)) for wi in range(10) for b in range(2))
+    whole, shared = plan_units_mixed(3, 1, 2, 2)           # 3 forwards on 2 GPUs: 1 whole each + 1 shared
+    assert [len(w) for w in whole] == [1, 1] and shared == [[(2, (0,))]]
+    whole, shared = plan_units_mixed(10, 2, 6, 2)          # 2 left over for 3 pairs: dealt whole instead
+    assert sorted(len(w) for w in whole) == [3, 3, 3, 3, 4, 4] and not any(shared)
