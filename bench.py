@@ -207,6 +207,8 @@ def run_ours(args):
             shared["group"] = loop.shard_group        # one set of peer buffers serves every loop of this process
             return loop
 
+    torch.cuda.synchronize()
+    t_first0 = time.perf_counter()
     d = to_device(host, dev)
     loop = make_loop(d)
     eng = loop.eng
@@ -219,6 +221,8 @@ def run_ours(args):
         t0 = time.time()
         loop.capture_graph()
         log(f"[rank {rank}] CUDA graph of one step captured in {time.time() - t0:.1f}s ({loop.graph_launches} kernel launches)")
+    torch.cuda.synchronize()
+    first_video_prepare_s = time.perf_counter() - t_first0      # one-off per process and video shape (includes graph capture)
 
     def barrier():
         if world > 1:
@@ -246,14 +250,14 @@ def run_ours(args):
     ms_per_step = float(ms) / args.steps
     value = L / (N_STEPS * ms_per_step / 1e3)
 
-    # ---- end-to-end through the public loop API with HOST buffers: per step H2D of the latents from pinned memory and
-    #      D2H of the updated latents; the one-off conditioning upload + prepare() is timed and amortised over 30 steps.
+    # ---- end-to-end through the public loop API with HOST buffers: a NEW video of the same shape.  Its conditioning is
+    #      uploaded from pinned host memory and written into the loop's static buffers (DenoiseLoop.reload: the CUDA graph
+    #      captured for the first video keeps serving) -- timed and amortised over the 30 steps; every step then does the
+    #      H2D copy of the latents and the D2H read of the updated latents.
     barrier()
     t_prep0 = time.perf_counter()
     d2 = to_device(host, dev)
-    loop2 = make_loop(d2)
-    if not args.no_graph:
-        loop2.capture_graph()
+    loop2 = loop.reload(d2["latents"], d2["pose"], d2["audio"], d2["full"], d2["face"], d2["lip"], d2["ehs"])
     torch.cuda.synchronize()
     prep_s = time.perf_counter() - t_prep0
     lat_host = host["latents"]
@@ -272,7 +276,7 @@ def run_ours(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = L / (N_STEPS * float(e2e_t))
     lat_bytes = lat_host.numel() * 4
-    del loop2, d2
+    del d2
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launch stream over one more step
     roof = None
@@ -335,7 +339,8 @@ def run_ours(args):
                                 tensor_cores=not args.no_tc, programmatic_dependent_launch=eng.ctx.pdl()),
                     clocks=clocks, gpu_launches=launches,
                     e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=lat_bytes + h2d_bytes(host) // N_STEPS,
-                             d2h_bytes_per_step=lat_bytes, prepare_s=prep_s, step_s=e2e_step),
+                             d2h_bytes_per_step=lat_bytes, prepare_s=prep_s, step_s=e2e_step,
+                             first_video_prepare_s=first_video_prepare_s),
                     roofline=roof, cpu_baseline=cpu, frame_evals_per_s=UNITS_PER_STEP * 12 * (L / 80.0) / (ms_per_step / 1e3))
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -102,12 +102,6 @@ class DenoiseLoop:
         self.inv_count = (1.0 / counts).to(dev)
         self.noise_acc = torch.zeros((nb, C, L, h, w), device=dev, dtype=torch.float32)
         self.t_dev = torch.zeros(1, device=dev, dtype=torch.float32)
-        # whole-video constants in kernel layout
-        pose_tok = eng.ncfhw_to_tokens(pose_fea) if pose_fea is not None else None      # (L,h,w,320)
-        audio_all = audio.to(device=dev, dtype=eng.dtype).contiguous()                   # (nb,L,M,768)
-        ehs = encoder_hidden_states.to(dev)
-        masks = [[m.to(device=dev, dtype=torch.float32).contiguous() for m in ms] for ms in (full_mask, face_mask, lip_mask)]
-        mask_pads = [[_pad16(m) for m in ms] for ms in masks]
         self.prepared = []
         for wi, branches, sharded in self.units:
             c = self.windows[wi]
@@ -118,14 +112,52 @@ class DenoiseLoop:
             nbr = len(branches)
             x_idx = idx.repeat(nbr)                                                      # latents / pose rows (frames)
             rows = torch.cat([idx + b * L for b in branches])                            # rows of the (nb*L, ...) tensors
-            aud = eng.gather_rows(audio_all.view(nb * L, -1), rows).view(nbr, len(c), audio_all.shape[2], audio_all.shape[3])
+            ref = [None if (self.cfg and b == 0) else b for b in branches]
+            self.prepared.append(dict(idx=idx, x_idx=x_idx, rows=rows, frames=len(c), branches=branches, ref=ref,
+                                      shard=self.shard_group if sharded else None))
+        self._fill_conditioning(pose_fea, audio, full_mask, face_mask, lip_mask, encoder_hidden_states, first=True)
+        self._signature = self._conditioning_signature(latents, pose_fea, audio, full_mask, encoder_hidden_states)
+        return self
+
+    @staticmethod
+    def _conditioning_signature(latents, pose_fea, audio, full_mask, ehs):
+        return (tuple(latents.shape), None if pose_fea is None else tuple(pose_fea.shape), tuple(audio.shape),
+                tuple(tuple(m.shape) for m in full_mask), tuple(ehs.shape))
+
+    def _fill_conditioning(self, pose_fea, audio, full_mask, face_mask, lip_mask, encoder_hidden_states, first: bool):
+        """Whole-video constants -> per-unit tensors in kernel layout.  ``first`` allocates them; later calls write into
+        the SAME storage, which is what a captured CUDA graph reads."""
+        eng, dev, L, nb = self.eng, self.eng.device, self.L, self.nb
+        pose_tok = eng.ncfhw_to_tokens(pose_fea) if pose_fea is not None else None      # (L,h,w,320)
+        audio_all = audio.to(device=dev, dtype=eng.dtype).contiguous()                   # (nb,L,M,768)
+        ehs = encoder_hidden_states.to(dev)
+        masks = [[m.to(device=dev, dtype=torch.float32).contiguous() for m in ms] for ms in (full_mask, face_mask, lip_mask)]
+        mask_pads = [[_pad16(m) for m in ms] for ms in masks]
+        for e in self.prepared:
+            nbr, fr, rows = len(e["branches"]), e["frames"], e["rows"]
+            aud = eng.gather_rows(audio_all.view(nb * L, -1), rows, out=None if first else e["audio"].view(nbr * fr, -1))
             mk = [[eng.gather_rows(mp, rows)[:, : m.shape[1]].contiguous() for mp, m in zip(mps, ms)]
                   for mps, ms in zip(mask_pads, masks)]
-            ref = [None if (self.cfg and b == 0) else b for b in branches]
-            self.prepared.append(dict(idx=idx, x_idx=x_idx, frames=len(c), branches=branches,
-                                      pose=eng.gather_rows(pose_tok, x_idx) if pose_tok is not None else None,
-                                      audio=aud, masks=mk, ehs=ehs[list(branches)].contiguous(), ref=ref,
-                                      shard=self.shard_group if sharded else None))
+            pose = None
+            if pose_tok is not None:
+                pose = eng.gather_rows(pose_tok, e["x_idx"], out=None if first else e["pose"])
+            sel = ehs[list(e["branches"])].contiguous()
+            if first:
+                e.update(pose=pose, audio=aud.view(nbr, fr, audio_all.shape[2], audio_all.shape[3]), masks=mk, ehs=sel)
+            else:
+                for dst_r, src_r in zip(e["masks"], mk):
+                    for dst, src in zip(dst_r, src_r):
+                        dst.copy_(src)
+                e["ehs"].copy_(sel)
+
+    def reload(self, latents, pose_fea, audio, full_mask, face_mask, lip_mask, encoder_hidden_states):
+        """The next video of the same shape: refill the latents and the per-unit conditioning in place, so the CUDA
+        graph captured for the first video (and the peer buffers of a frame-shard group) keep serving."""
+        sig = self._conditioning_signature(latents, pose_fea, audio, full_mask, encoder_hidden_states)
+        if sig != self._signature:
+            raise ValueError(f"reload() needs the shapes prepare() saw: {self._signature}, got {sig}")
+        self.latents.copy_(latents.to(torch.float32))
+        self._fill_conditioning(pose_fea, audio, full_mask, face_mask, lip_mask, encoder_hidden_states, first=False)
         return self
 
     # ------------------------------------------------------------------ the hot loop

@@ -154,3 +154,39 @@ def test_denoise_step_matches_oracle(compute_dtype, tol):
     err = rel_l2(lat, lat_ref)
     print(f"denoise 2 steps {compute_dtype}: latents rel-L2 {err:.3e}")
     assert err < tol
+
+
+def test_denoise_loop_reload_serves_a_new_video_from_the_captured_graph():
+    """DenoiseLoop.reload(): a second video of the same shape is written into the static buffers the CUDA graph of the
+    first video reads; its latents must equal those of a freshly prepared (eager) loop on the second video."""
+    from mmgt_b200.pipeline_pose2vid_long import DenoiseLoop
+    from mmgt_b200.scheduling_ddim import DDIMSchedule
+    spec = UNetSpec(block_out_channels=TINY)
+    sd = synthetic_state_dict("tiny")
+    unet = build_cuda_unet(TINY, sd, compute_dtype=torch.bfloat16)
+    unet.train()
+    unet.enable_gradient_checkpointing()
+    L, latent, n_steps = 20, 16, 30
+    attach_banks(unet, spec, make_banks(spec, latent), cfg=True)
+    vids = [to_dev(make_inputs(spec, L, latent, seed=s), "cuda") for s in (11, 12)]
+
+    def args(d):
+        return (d["latents"], d["pose_fea"], d["audio"], d["full_mask"], d["face_mask"], d["lip_mask"], d["encoder_hidden_states"])
+    loop = DenoiseLoop(unet, DDIMSchedule.from_config(), n_steps, 3.5, motion_scale=vids[0]["motion_scale"])
+    loop.prepare(*args(vids[0]))
+    loop.capture_graph()
+    loop.step(0)
+    first = loop.step(1).clone()
+    loop.reload(*args(vids[1]))
+    loop.step(0)
+    second = loop.step(1).clone()
+    fresh = DenoiseLoop(unet, DDIMSchedule.from_config(), n_steps, 3.5, motion_scale=vids[1]["motion_scale"])
+    fresh.prepare(*args(vids[1]))
+    fresh.step(0)
+    want = fresh.step(1)
+    assert rel_l2(second, first) > 1e-2                 # it really is another video
+    err = rel_l2(second, want)
+    print(f"reload: latents of video 2 from the reused graph vs fresh loop rel-L2 {err:.3e}")
+    assert err < 1e-3
+    with pytest.raises(ValueError):
+        loop.reload(vids[1]["latents"][:, :, :12], *args(vids[1])[1:])
