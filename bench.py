@@ -233,6 +233,17 @@ def run_ours(args):
     for i in range(args.warmup):
         loop.step(i % N_STEPS)
     barrier()
+    if args.ncu_step:
+        # `ncu --profile-from-start off --metrics gpu__time_duration.sum ... python bench.py --ncu-step`: exactly one DDIM
+        # step (eager launches) between cudaProfilerStart / Stop -> the launch list under profiles/; prints no bench line.
+        graph, loop._graph = loop._graph, None
+        torch.cuda.cudart().cudaProfilerStart()
+        loop.step(args.warmup % N_STEPS)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        loop._graph = graph
+        log("[ncu-step] one step profiled; no bench line is printed under a profiler")
+        return
     sampler = ClockSampler(local)
     sampler.start()
     n0 = eng.ctx.launches()
@@ -308,15 +319,21 @@ def run_ours(args):
                 f.write(f"# per-operator CUDA-event time over one eager DDIM step ({tot:.1f} ms in instrumented ops); "
                         f"step under CUDA graph: {ms_per_step:.1f} ms\n" + "\n".join(table) + "\n")
         tms, key, r = rows[0]
+        traffic = None
+        try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f)["per_launch_bytes"].get(str(key))
+        except Exception:
+            traffic = None
         if r["flops"] > 0 and key[0] in ("gemm", "conv3x3", "attention"):
             ach = r["flops"] / (tms * 1e-3) / 1e12
             roof = dict(bound="tensor", kernel=str(key), achieved=ach, peak=pk["tf_sustained"], unit="TFLOP/s",
-                        frac=ach / pk["tf_sustained"], traffic=None, peak_source=pk["src"] + " sustained bf16",
+                        frac=ach / pk["tf_sustained"], traffic=traffic, peak_source=pk["src"] + " sustained bf16",
                         launches=r["calls"], avg_launch_ms=tms / r["calls"], share_of_step=tms / tot)
         else:
             ach = r["bytes"] / (tms * 1e-3) / 1e9
             roof = dict(bound="hbm", kernel=str(key), achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
-                        traffic=None, peak_source=pk["src"], launches=r["calls"], avg_launch_ms=tms / r["calls"],
+                        traffic=traffic, peak_source=pk["src"], launches=r["calls"], avg_launch_ms=tms / r["calls"],
                         share_of_step=tms / tot)
         whole = UNITS_PER_STEP * (L / 80.0) * FLOP_PER_UNIT / (ms_per_step * 1e-3) / 1e12 / world
         roof["whole_step_tflops_per_gpu"] = whole
@@ -419,6 +436,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops-out", default=None, help="write the per-operator event-time table of one step to this file")
     ap.add_argument("--cpu-budget", type=float, default=150.0)
+    ap.add_argument("--ncu-step", action="store_true", help="profiling aid: one eager step between cudaProfilerStart/Stop, then exit")
     ap.add_argument("--frame-shards", type=int, default=int(os.environ.get("MMGT_FRAME_SHARDS", "0")),
                     help="ranks that split the frames of one context window (SURVEY 8e level 3); must divide --gpus; "
                          "0 = auto: whole forwards, plus frame-sharded leftovers when they do not divide over the ranks")

@@ -46,6 +46,17 @@ def make_ops(eng, dev):
     kv6 = rnd(N, 32, 1920)
     ops["attn_audio_d40"] = (lambda: eng.attention(q3[:, :, :320], kv6[:, :, :320], kv6[:, :, 320:640], 8),
                              4.0 * 8 * N * T0 * 32 * 40, 2.0 * N * T0 * 320 * 2)
+    # ---- fused three-region MM-HAA cross attention (mask gate in the epilogue) + its K = 3C+8 GEMM
+    masks = [torch.rand(N * T0, generator=g).to(dev) for _ in range(3)]
+    q3f, kv6f = q3.view(N * T0, 960), kv6.view(N * 32, 1920)
+    ops["audio_attention_fused_d40"] = (lambda: eng.audio_attention(q3f, kv6f, masks, (1.0, 1.0, 2.0), N, T0, 8),
+                                        4.0 * 3 * 8 * N * T0 * 32 * 40, (N * T0 * 960 + N * T0 * 968) * 2.0)
+    a968 = rnd(N * T0, 968)
+    w968 = rnd(320, 968, scale=0.03)
+    res968 = rnd(N * T0, 320)
+    b968 = rnd(320, dtype=torch.float32)
+    ops["gemm_320x968_res"] = (lambda: eng.gemm(a968, w968, bias=b968, residual=res968), 2.0 * N * T0 * 320 * 968,
+                               (N * T0 * 968 + 2 * N * T0 * 320) * 2.0)
     # ---- GEMMs (rows = 24 * 4096)
     M = N * T0
     a320 = rnd(M, 320)
