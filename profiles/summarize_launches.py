@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list of bench.py into a per-kernel table.
 
-  python profiles/summarize_launches.py gpurun_out/r1_launches.csv profiles/r1_launches_step [--step 1]
+  python profiles/summarize_launches.py gpurun_out/r1_launches.csv profiles/r1_launches_step [--step 1 | --all]
 
 Picks one full DDIM step (the launches between two consecutive cfg_ddim_step kernels), writes
 <out>.csv.gz (the raw rows of that step) and <out>.md (time share per kernel, per template instance)."""
@@ -29,9 +29,12 @@ def main():
     rows = [r for r in rd]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
     marks = [i for i, r in enumerate(rows) if "ddim" in r[ki]]
-    if len(marks) <= step:
-        raise SystemExit(f"only {len(marks)} step marker(s) in the list")
-    lo, hi = marks[step - 1] + 1, marks[step] + 1
+    if "--all" in sys.argv:          # list captured with `bench.py --ncu-step`: exactly one step between profiler start/stop
+        lo, hi = 0, len(rows)
+    else:
+        if len(marks) <= step:
+            raise SystemExit(f"only {len(marks)} step marker(s) in the list")
+        lo, hi = marks[step - 1] + 1, marks[step] + 1
     sel = rows[lo:hi]
     with gzip.open(out + ".csv.gz", "wt", newline="") as g:
         w = csv.writer(g)

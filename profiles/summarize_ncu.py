@@ -38,6 +38,7 @@ def main():
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
     lines = ["| # | kernel | " + " | ".join(m[0] for m in METRICS) + " |", "|---|---|" + "---:|" * len(METRICS)]
+    data = [r for r in data if "at::" not in r[col["Kernel Name"]]]     # drop torch's L2-flush fills between the operators
     for k, r in enumerate(data):
         name = re.sub(r"\(.*", "", r[col["Kernel Name"]]).replace("void ", "").replace("<unnamed>::", "")
         if k < len(labels):
