@@ -40,6 +40,10 @@ struct TcArgs {
   float alpha;
   // conv geometry (CONV only)
   int H, W, cin_blocks;
+  // CONV, patch tiles: when no run of 128 consecutive (n, h, w) rows is a TMA box (W = 96, 48, 24, 12: the 768^2 / 384^2
+  // latents of config 5) an M tile is a (pf frames) x (ph rows) x (pw columns) patch, pw * ph * pf = 128.  pw == 0:
+  // tiles are 128 consecutive rows.
+  int pw, ph, pf, n_frames;
   // BRES only: A ring depth (runtime: what is left of shared memory after the resident weight tile)
   int stages;
   int wide_io;   // D / residual rows are 32-byte aligned: 256-bit epilogue loads and stores
@@ -287,11 +291,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
       int cn = 0, ch = 0, cw = 0;
       if (CONV) {
-        const int m0 = m_blk * BM, hw = args.H * args.W;
-        cn = m0 / hw;
-        const int rem = m0 - cn * hw;
-        ch = rem / args.W;
-        cw = rem - ch * args.W;
+        if (args.pw) {
+          const int tiles_w = args.W / args.pw, per_group = tiles_w * (args.H / args.ph);
+          const int ng = m_blk / per_group, r = m_blk - ng * per_group;
+          cn = ng * args.pf;
+          ch = (r / tiles_w) * args.ph;
+          cw = (r - (r / tiles_w) * tiles_w) * args.pw;
+        } else {
+          const int m0 = m_blk * BM, hw = args.H * args.W;
+          cn = m0 / hw;
+          const int rem = m0 - cn * hw;
+          ch = rem / args.W;
+          cw = rem - ch * args.W;
+        }
       }
       for (int kb = 0; kb < args.num_k_blocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -356,8 +368,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // main loop, is the critical path and nothing else would cover the HBM latency of these loads).
     Row32 resv[CH0];
     int m_blk, n_blk;
-    if (args.residual != nullptr && tile_at(0, m_blk, n_blk) && m_blk * BM + row_in_tile < args.M) {
-      const bf16* rp = args.residual + (int64_t)(m_blk * BM + row_in_tile) * args.ldr + n_blk * OUT_COLS + c_begin * 16;
+    // output row of this thread in M tile mb (>= M: none).  Patch tiles (CONV, args.pw != 0) are not consecutive rows.
+    auto row_of = [&](int mb) -> int {
+      if (CONV && args.pw) {
+        const int tiles_w = args.W / args.pw, per_group = tiles_w * (args.H / args.ph);
+        const int ng = mb / per_group, r = mb - ng * per_group;
+        const int per_frame = args.pw * args.ph;
+        const int dn = row_in_tile / per_frame, rr = row_in_tile - dn * per_frame;
+        const int dh = rr / args.pw, dw = rr - dh * args.pw;
+        const int fr = ng * args.pf + dn;
+        if (fr >= args.n_frames) return args.M;
+        return (fr * args.H + (r / tiles_w) * args.ph + dh) * args.W + (r - (r / tiles_w) * tiles_w) * args.pw + dw;
+      }
+      return mb * BM + row_in_tile;
+    };
+    if (args.residual != nullptr && tile_at(0, m_blk, n_blk) && row_of(m_blk) < args.M) {
+      const bf16* rp = args.residual + (int64_t)row_of(m_blk) * args.ldr + n_blk * OUT_COLS + c_begin * 16;
 #pragma unroll
       for (int i = 0; i < CH0; ++i)
         if (i < c_count) resv[i] = ld_row32(rp + 16 * i, wide);
@@ -365,15 +391,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m = m_blk * BM + row_in_tile;
+      const int m = row_of(m_blk);
       const bool m_ok = m < args.M;
       const int n_out0 = n_blk * OUT_COLS;
       const bool has_res = args.residual != nullptr && m_ok;
       const bf16* res_next = nullptr;
       {
         int mb2, nb2;
-        if (args.residual != nullptr && tile_at(it + 1, mb2, nb2) && mb2 * BM + row_in_tile < args.M)
-          res_next = args.residual + (int64_t)(mb2 * BM + row_in_tile) * args.ldr + nb2 * OUT_COLS + c_begin * 16;
+        if (args.residual != nullptr && tile_at(it + 1, mb2, nb2) && row_of(mb2) < args.M)
+          res_next = args.residual + (int64_t)row_of(mb2) * args.ldr + nb2 * OUT_COLS + c_begin * 16;
       }
       bf16* drow = args.D + (int64_t)m * args.ldd;
       if (args.ex.direction != 0 && m_ok) drow = exchange_row_ptr<bf16>(args.ex, m);
@@ -691,12 +717,28 @@ static bool conv_box(const mmgt_conv3x3_params* p, uint32_t* bw, uint32_t* bh, u
   return true;
 }
 
+// Patch tile for widths that conv_box cannot cover with consecutive rows: the widest pw | W with 128 % pw == 0, then
+// the tallest ph | H with ph | 128 / pw; the rest of the 128 rows are consecutive frames.
+static bool conv_patch(const mmgt_conv3x3_params* p, uint32_t* pw, uint32_t* ph, uint32_t* pf) {
+  for (int w = 64; w >= 1; w >>= 1) {
+    if (p->W % w) continue;
+    const int rest = BM / w;
+    for (int h = rest; h >= 1; h >>= 1) {
+      if (p->H % h) continue;
+      if (rest / h > 256) return false;
+      *pw = w; *ph = h; *pf = rest / h;
+      return true;
+    }
+  }
+  return false;
+}
+
 bool mmgt_conv3x3_tc_supported(const mmgt_ctx* ctx, const mmgt_conv3x3_params* p) {
   (void)ctx;
   if (p->dtype != MMGT_BF16 || p->stride != 1 || p->upsample2x) return false;
   if (p->Cin % BK || !pick_bn(p->Cout) || p->Cout % 16) return false;
   uint32_t bw, bh, bf;
-  if (!conv_box(p, &bw, &bh, &bf)) return false;
+  if (!conv_box(p, &bw, &bh, &bf) && !conv_patch(p, &bw, &bh, &bf)) return false;
   if (!aligned16(p->x) || !aligned16(p->w) || !aligned16(p->y) || (p->residual && !aligned16(p->residual))) return false;
   if ((p->bias && !aligned16(p->bias)) || (p->rowbias && !aligned16(p->rowbias))) return false;
   return true;
@@ -705,7 +747,8 @@ bool mmgt_conv3x3_tc_supported(const mmgt_ctx* ctx, const mmgt_conv3x3_params* p
 int mmgt_conv3x3_tc(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, cudaStream_t st) {
   const int bn = pick_bn_for(p->Cout, p->N * p->H * p->W, ctx->num_sms);
   uint32_t bw, bh, bf;
-  conv_box(p, &bw, &bh, &bf);
+  const bool patch = !conv_box(p, &bw, &bh, &bf);
+  if (patch) conv_patch(p, &bw, &bh, &bf);
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
@@ -725,6 +768,11 @@ int mmgt_conv3x3_tc(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, cudaStream_t st
   a.M = p->N * p->H * p->W;
   a.N_out = p->Cout;
   a.num_m_tiles = (a.M + BM - 1) / BM;
+  a.n_frames = p->N;
+  if (patch) {
+    a.pw = (int)bw; a.ph = (int)bh; a.pf = (int)bf;
+    a.num_m_tiles = ((p->N + (int)bf - 1) / (int)bf) * (p->H / (int)bh) * (p->W / (int)bw);
+  }
   a.num_n_tiles = p->Cout / bn;
   a.cin_blocks = p->Cin / BK;
   a.num_k_blocks = 9 * a.cin_blocks;

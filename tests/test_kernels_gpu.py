@@ -227,7 +227,10 @@ def test_gemm_strided_views_and_f32_vectors(dev):
 CONV_CASES = [  # N, H, W, Cin, Cout, stride, upsample
     (3, 16, 16, 64, 64, 1, 0), (2, 8, 8, 128, 256, 1, 0), (5, 4, 4, 256, 256, 1, 0), (2, 32, 32, 64, 128, 1, 0),
     (2, 64, 64, 64, 64, 1, 0), (3, 2, 2, 256, 256, 1, 0), (2, 16, 16, 64, 64, 2, 0), (2, 8, 8, 128, 128, 1, 1),
-    (2, 16, 16, 4, 64, 1, 0), (2, 16, 16, 64, 4, 1, 0), (3, 16, 16, 320, 320, 1, 0), (2, 8, 8, 1920, 640, 1, 0)]
+    (2, 16, 16, 4, 64, 1, 0), (2, 16, 16, 64, 4, 1, 0), (3, 16, 16, 320, 320, 1, 0), (2, 8, 8, 1920, 640, 1, 0),
+    # widths no run of 128 consecutive rows covers (config 5: 96 / 48 / 24 / 12 latents): patch tiles pw x ph x frames
+    (2, 96, 96, 64, 64, 1, 0), (1, 48, 48, 128, 64, 1, 0), (3, 24, 24, 64, 128, 1, 0), (5, 12, 12, 128, 128, 1, 0),
+    (3, 6, 6, 256, 256, 1, 0), (2, 24, 48, 64, 64, 1, 0)]
 
 
 @pytest.mark.parametrize("dtype,tc", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)],

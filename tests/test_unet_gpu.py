@@ -190,3 +190,71 @@ def test_denoise_loop_reload_serves_a_new_video_from_the_captured_graph():
     assert err < 1e-3
     with pytest.raises(ValueError):
         loop.reload(vids[1]["latents"][:, :, :12], *args(vids[1])[1:])
+
+
+@pytest.mark.parametrize("compute_dtype,tol", [(torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16_FWD)], ids=["f32", "bf16tc"])
+def test_tiny_unet_config5_geometry_vs_oracle(compute_dtype, tol):
+    """BASELINE config 5 geometry at reduced size: a 24 x 24 latent gives the non-power-of-two pyramid 24 / 12 / 6 / 3
+    (768^2 -> 96 / 48 / 24 / 12): patch-tiled tensor-core convs, token counts 576 / 144 / 36 / 9, CFG, 6 frames."""
+    spec = UNetSpec(block_out_channels=TINY)
+    sd = synthetic_state_dict("tiny")
+    unet = build_cuda_unet(TINY, sd, compute_dtype=compute_dtype)
+    unet.train()
+    unet.enable_gradient_checkpointing()
+    frames, latent = 6, 24
+    inp = make_inputs(spec, frames, latent, seed=23)
+    banks = make_banks(spec, latent)
+    attach_banks(unet, spec, banks, cfg=True)
+    win = window_inputs(inp, list(range(frames)))
+    with torch.no_grad():
+        ref = unet3d_forward(sd, spec, win["sample"], 321, win["encoder_hidden_states"], win["audio_embedding"],
+                             win["pose_cond_fea"], win["full_mask"], win["face_mask"], win["body_mask"], win["motion_scale"],
+                             banks, ref_index=[None, 1], apply_motion_scale=True)
+    out = run_cuda_unet(unet, win, 321)
+    err = rel_l2(out, ref)
+    print(f"config-5 geometry {compute_dtype}: rel-L2 vs oracle {err:.3e}")
+    assert err < tol
+
+
+def test_thirty_step_denoise_latent_psnr():
+    """north_star: final frames >= 40 dB PSNR.  The VAE is out of scope, so the criterion is applied
+    where the hot path ends: the latents after all 30 DDIM steps (CFG 3.5, one 12-frame window) against the float32
+    oracle run of the same loop; peak = the oracle latents' range.  bf16 tier >= 40 dB, float32 tier >= 80 dB."""
+    import math
+    from mmgt_b200.pipeline_pose2vid_long import DenoiseLoop
+    from mmgt_b200.scheduling_ddim import DDIMSchedule
+    spec = UNetSpec(block_out_channels=TINY)
+    sd = synthetic_state_dict("tiny")
+    L, latent, n_steps = 12, 16, 30
+    inp = make_inputs(spec, L, latent, seed=31)
+    banks = make_banks(spec, latent)
+    windows = uniform_windows(0, L)
+
+    def unet_fn(sample, t, ehs, aud, pose, full, face, lip, ms):
+        with torch.no_grad():
+            return unet3d_forward(sd, spec, sample, t, ehs, aud, pose, full, face, lip, ms, banks, ref_index=[None, 1],
+                                  apply_motion_scale=True)
+    ddim = DDIM()
+    lat_ref = inp["latents"].clone()
+    for t in ddim.timesteps(n_steps):
+        lat_ref, _ = denoise_step(unet_fn, lat_ref, t, n_steps, ddim, 3.5, windows, inp["pose_fea"], inp["audio"],
+                                  inp["full_mask"], inp["face_mask"], inp["lip_mask"], inp["encoder_hidden_states"],
+                                  inp["motion_scale"])
+    peak = float(lat_ref.max() - lat_ref.min())
+    d = to_dev(inp, "cuda")
+    for dtype, floor in ((torch.float32, 80.0), (torch.bfloat16, 40.0)):
+        unet = build_cuda_unet(TINY, sd, compute_dtype=dtype)
+        unet.train()
+        unet.enable_gradient_checkpointing()
+        attach_banks(unet, spec, banks, cfg=True)
+        loop = DenoiseLoop(unet, DDIMSchedule.from_config(), n_steps, 3.5, motion_scale=inp["motion_scale"])
+        loop.prepare(d["latents"], d["pose_fea"], d["audio"], d["full_mask"], d["face_mask"], d["lip_mask"],
+                     d["encoder_hidden_states"])
+        loop.capture_graph()
+        lat = loop.run().float().cpu()
+        mse = float(((lat - lat_ref) ** 2).mean())
+        psnr = 10.0 * math.log10(peak * peak / max(mse, 1e-30))
+        print(f"30-step denoise {dtype}: latent PSNR {psnr:.1f} dB (rel-L2 {rel_l2(lat, lat_ref):.3e})")
+        assert psnr >= floor
+        del unet, loop
+        torch.cuda.empty_cache()
