@@ -12,6 +12,8 @@ __global__ void k(float* out, int iters, float seed) {
       if (MODE == 0) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i])); }
       else if (MODE == 1) { x[i] = fmaf(x[i], 0.999f, 0.001f); }
       else if (MODE == 2) { asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[i])); }
+      else if (MODE == 4) { unsigned u = __float_as_uint(x[i]); asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u)); x[i] = __uint_as_float(u); }
+      else if (MODE == 5) { unsigned u = __float_as_uint(x[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u)); x[i] = __uint_as_float(u); }
       else { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i])); x[(i + 4) & 7] = fmaf(x[(i + 4) & 7], 0.999f, 0.001f); x[(i + 5) & 7] = fmaf(x[(i + 5) & 7], 0.999f, 0.001f); x[(i+6)&7] = fmaf(x[(i + 6) & 7], 0.999f, 0.001f);}
     }
   }
@@ -37,6 +39,8 @@ template <int MODE> void run(const char* name, int threads, int blocks_per_sm) {
 int main() {
   run<0>("MUFU.EX2", 256, 4); run<0>("MUFU.EX2", 128, 2); run<0>("MUFU.EX2 (1 warp/SMSP)", 128, 1);
   run<2>("MUFU.RCP", 256, 4);
+  run<4>("EX2 bf16x2 (instr count; x2 elements)", 256, 4); run<4>("EX2 bf16x2, 1 warp/SMSP", 128, 1);
+  run<5>("EX2 f16x2 (instr count; x2 elements)", 256, 4);
   run<1>("FFMA", 256, 4);
   run<3>("EX2 + 3 FFMA interleaved (EX2 count)", 256, 4); run<3>("EX2 + 3 FFMA, 1 warp/SMSP", 128, 1);
   return 0;
