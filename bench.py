@@ -148,8 +148,8 @@ def _describe(world, shards, remainder, loop):
     if shards == 1 or shared == 0:
         return f"(window,cfg-branch) forwards dealt whole over {world} rank(s)"
     if remainder:
-        return (f"(window,cfg-branch) forwards over {world} ranks: {whole} whole per rank + {shared} shared by each group of "
-                f"{shards} ranks as frame shards (motion modules: peer-store row exchange over NVLink)")
+        return (f"(window,cfg-branch) forwards over {world} ranks: {whole} whole unit(s) per rank + {shared} shared by each "
+                f"group of {shards} ranks as frame shards (motion modules: peer-store row exchange over NVLink)")
     return (f"(window,cfg-branch) forwards over {world // shards} rank group(s) x {shards} frame shards per window "
             "(motion modules: peer-store row exchange over NVLink)")
 
@@ -179,13 +179,16 @@ def run_ours(args):
     ctl.set_banks([b.to(dev) for b in host["banks"]])
     sched = DDIMSchedule.from_config()
 
-    # Schedule.  Default ("auto"): whole (window, branch) forwards dealt to the ranks; when they do not divide (20 over 8
-    # GPUs) each pair of ranks also shares one forward, frame-sharded (2 + 1/2 forwards per rank instead of 3 / 2).
+    # Schedule.  Default ("auto"): whole windows (B=2), then single-branch forwards, dealt evenly to the ranks; forwards that
+    # still do not divide (10 windows on 8 GPUs: one window each, 4 forwards left) are shared by pairs of ranks as frame
+    # shards (2.5 forwards of work per rank instead of 3 / 2).
     shards, remainder = args.frame_shards, args.shard_remainder
-    n_units = UNITS_PER_STEP * L // VIDEO_LENGTH if L % VIDEO_LENGTH == 0 else None
     if shards == 0:
+        from mmgt_b200.context import get_context_scheduler
+        from mmgt_b200.pipeline_pose2vid_long import plan_units_mixed
+        n_windows = len(list(get_context_scheduler("uniform")(0, N_STEPS, L, 12, 1, 4)))
         shards, remainder = 1, False
-        if n_units and world % 2 == 0 and n_units % world and (n_units % world) % (world // 2) == 0:
+        if world % 2 == 0 and any(plan_units_mixed(n_windows, 2, world, 2)[1]):
             shards, remainder = 2, True
     if world % shards:
         raise SystemExit(f"bench.py: --frame-shards {shards} must divide the number of ranks {world}")

@@ -74,10 +74,7 @@ class DenoiseLoop:
         k = self.frame_shards
         n_groups, group_idx, shard = self.world // k, self.rank // k, self.rank % k
         need_group = k > 1                  # rank-independent: creating the peer buffers is a collective
-        if self.shard_remainder and (nw * nb) % self.world == 0:
-            self.units = [(wi, b, False) for wi, b in plan_units(nw, nb, self.world)[self.rank]]      # nothing left over
-            need_group = False
-        elif self.shard_remainder:
+        if self.shard_remainder:
             whole, shared = plan_units_mixed(nw, nb, self.world, k)
             # the shared forwards go first: all ranks leave the per-step all-reduce together, so the peers meet at once
             self.units = [(wi, b, True) for wi, b in shared[group_idx]] + [(wi, b, False) for wi, b in whole[self.rank]]
@@ -220,34 +217,47 @@ class DenoiseLoop:
 
 
 def plan_units(n_windows: int, n_branches: int, n_groups: int):
-    """Deal the (window, CFG-branch) forwards of one step to ``n_groups`` rank groups.  Whole windows (both
-    branches batched as one B=2 forward: larger GEMM M) when the windows divide evenly, otherwise single
-    (window, branch) forwards for a finer deal.  Returns one list of (window index, branches) per group."""
-    if n_branches == 2 and n_windows % n_groups == 0:
-        units = [(wi, (0, 1)) for wi in range(n_windows)]
-    else:
-        units = [(wi, (b,)) for wi in range(n_windows) for b in range(n_branches)]
-    return [units[g::n_groups] for g in range(n_groups)]
+    """Deal the (window, CFG-branch) forwards of one step to ``n_groups`` rank groups, as large as they come: first whole
+    windows (both CFG branches batched as one B=2 forward: twice the GEMM M), n_windows // n_groups to every group; the
+    windows left over are split into single-branch forwards and dealt round; what still does not divide goes to the first
+    groups.  Returns one list of (window index, branches) per group."""
+    whole, left = _deal_large(n_windows, n_branches, n_groups)
+    for i, u in enumerate(left):
+        whole[i % n_groups].append(u)
+    return whole
 
 
 def plan_units_mixed(n_windows: int, n_branches: int, world: int, k: int):
-    """Whole forwards for every rank plus frame-sharded leftovers: the n = n_windows * n_branches single-branch forwards
-    are dealt whole, n // world to each of the ``world`` ranks; the n % world left over are shared out to the world // k
-    groups of k ranks, which run them frame-sharded (when they do not divide over the groups either, they are dealt
-    whole to the first ranks).  Returns (whole: one list per rank, shared: one list per group)."""
-    units = [(wi, (b,)) for wi in range(n_windows) for b in range(n_branches)]
+    """Like plan_units over all ``world`` ranks, but the single-branch forwards that do not divide over the ranks are shared
+    out to the world // k groups of k ranks, which run them frame-sharded (20 forwards on 8 GPUs: one B=2 window per rank,
+    and each pair of ranks shares one more single-branch forward; when the leftovers do not divide over the groups either
+    they are dealt whole to the first ranks).  Returns (whole: one list per rank, shared: one list per group)."""
+    whole, left = _deal_large(n_windows, n_branches, world)
     groups = world // k
-    per_rank, rem = divmod(len(units), world)
-    whole = [units[r * per_rank:(r + 1) * per_rank] for r in range(world)]
-    left = units[per_rank * world:]
     shared = [[] for _ in range(groups)]
-    if rem and rem % groups == 0:
+    if left and len(left) % groups == 0:
         for i, u in enumerate(left):
             shared[i % groups].append(u)
     else:
         for i, u in enumerate(left):
-            whole[i].append(u)
+            whole[i % world].append(u)
     return whole, shared
+
+
+def _deal_large(n_windows: int, n_branches: int, n: int):
+    """-> (per-receiver lists after the even deals, the forwards left over: fewer than n single-branch ones)."""
+    out = [[] for _ in range(n)]
+    first_single = 0
+    if n_branches == 2:
+        per = n_windows // n
+        for r in range(n):
+            out[r] += [(wi, (0, 1)) for wi in range(r * per, (r + 1) * per)]
+        first_single = per * n
+    singles = [(wi, (b,)) for wi in range(first_single, n_windows) for b in range(n_branches)]
+    per = len(singles) // n
+    for r in range(n):
+        out[r] += singles[r * per:(r + 1) * per]
+    return out, singles[per * n:]
 
 
 def _pad16(m: torch.Tensor) -> torch.Tensor:

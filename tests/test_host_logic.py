@@ -168,15 +168,22 @@ def test_unit_partition_and_allreduce_gloo_world2():
 
 
 # ---------------------------------------------------------------------------------- frame shards (SURVEY 8e level 3)
+def _forwards(groups):
+    return sorted((wi, b) for g in groups for wi, bs in g for b in bs)
+
+
 def test_plan_units_balances_groups():
+    """Whole B=2 windows as far as they go, then single-branch forwards, every (window, branch) exactly once."""
     from mmgt_b200.pipeline_pose2vid_long import plan_units
+    every = [(wi, b) for wi in range(10) for b in range(2)]
     assert plan_units(10, 2, 1) == [[(wi, (0, 1)) for wi in range(10)]]
-    assert [len(u) for u in plan_units(10, 2, 2)] == [5, 5] and plan_units(10, 2, 2)[0][0] == (0, (0, 1))
-    four = plan_units(10, 2, 4)                       # 10 windows do not split over 4 groups: single-branch units
-    assert [len(u) for u in four] == [5, 5, 5, 5] and all(len(b) == 1 for g in four for _, b in g)
-    assert sorted(len(u) for u in plan_units(10, 2, 8)) == [2, 2, 2, 2, 3, 3, 3, 3]
-    every = sorted((wi, b) for g in plan_units(10, 2, 8) for wi, bs in g for b in bs)
-    assert every == [(wi, b) for wi in range(10) for b in range(2)]      # each (window, branch) exactly once
+    assert [[len(b) for _, b in g] for g in plan_units(10, 2, 2)] == [[2] * 5] * 2
+    assert [[len(b) for _, b in g] for g in plan_units(10, 2, 4)] == [[2, 2, 1]] * 4        # 2 windows + 1 forward per rank
+    eight = plan_units(10, 2, 8)                                                              # 1 window each + 4 left over
+    assert sorted(sum(len(b) for _, b in g) for g in eight) == [2, 2, 2, 2, 3, 3, 3, 3]
+    for n in (1, 2, 3, 4, 5, 6, 8):
+        assert _forwards(plan_units(10, 2, n)) == every
+    assert _forwards(plan_units(3, 1, 2)) == [(0, 0), (1, 0), (2, 0)]                         # no CFG: windows are the forwards
 
 
 @pytest.mark.parametrize("k,B,F,T", [(2, 1, 12, 16), (4, 2, 12, 64), (2, 2, 4, 6), (3, 1, 6, 9)])
@@ -276,11 +283,14 @@ def test_frame_sharded_window_matches_unsharded_gloo_world2():
 
 def test_plan_units_mixed_shares_the_remainder():
     from mmgt_b200.pipeline_pose2vid_long import plan_units_mixed
-    whole, shared = plan_units_mixed(10, 2, 8, 2)          # 20 forwards on 8 GPUs: 2 whole each + 1 per pair
-    assert [len(w) for w in whole] == [2] * 8 and [len(s) for s in shared] == [1] * 4
-    every = sorted(u for part in whole + shared for u in part)
-    assert every == sorted((wi, (b,)) for wi in range(10) for b in range(2))
+    every = [(wi, b) for wi in range(10) for b in range(2)]
+    whole, shared = plan_units_mixed(10, 2, 8, 2)          # 20 forwards on 8 GPUs: one B=2 window each + 1 forward per pair
+    assert [[len(b) for _, b in w] for w in whole] == [[2]] * 8 and [len(s) for s in shared] == [1] * 4
+    assert _forwards(whole + shared) == every
+    whole, shared = plan_units_mixed(10, 2, 4, 2)          # divides: 2 windows + 1 forward per rank, nothing shared
+    assert [[len(b) for _, b in w] for w in whole] == [[2, 2, 1]] * 4 and not any(shared)
     whole, shared = plan_units_mixed(3, 1, 2, 2)           # 3 forwards on 2 GPUs: 1 whole each + 1 shared
     assert [len(w) for w in whole] == [1, 1] and shared == [[(2, (0,))]]
-    whole, shared = plan_units_mixed(10, 2, 6, 2)          # 2 left over for 3 pairs: dealt whole instead
-    assert sorted(len(w) for w in whole) == [3, 3, 3, 3, 4, 4] and not any(shared)
+    whole, shared = plan_units_mixed(10, 2, 6, 2)          # 8 single forwards for 6 ranks: 2 left for 3 pairs -> dealt whole
+    assert not any(shared) and _forwards(whole) == every
+    assert sorted(sum(len(b) for _, b in w) for w in whole) == [3, 3, 3, 3, 4, 4]
