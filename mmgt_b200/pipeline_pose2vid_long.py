@@ -68,19 +68,11 @@ class DenoiseLoop:
         self.latents = latents.to(torch.float32).contiguous().clone()
         cf, cs, co = self.ctx_args
         self.windows = [list(map(int, c)) for c in self.context_scheduler(0, self.n_steps, L, cf, cs, co)]
-        # Work units of this rank.  Whole windows (both CFG branches batched as one B=2 forward: larger GEMM M) when the
-        # windows divide evenly over the ranks, otherwise single (window, branch) forwards for a finer deal.
+        # Work units of this rank (plan_rank): whole B=2 windows first, then single-branch forwards, optionally frame shards.
         nw = len(self.windows)
         k = self.frame_shards
-        n_groups, group_idx, shard = self.world // k, self.rank // k, self.rank % k
-        need_group = k > 1                  # rank-independent: creating the peer buffers is a collective
-        if self.shard_remainder:
-            whole, shared = plan_units_mixed(nw, nb, self.world, k)
-            # the shared forwards go first: all ranks leave the per-step all-reduce together, so the peers meet at once
-            self.units = [(wi, b, True) for wi, b in shared[group_idx]] + [(wi, b, False) for wi, b in whole[self.rank]]
-            need_group = any(len(s) for s in shared)
-        else:
-            self.units = [(wi, b, k > 1) for wi, b in plan_units(nw, nb, n_groups)[group_idx]]
+        shard = self.rank % k
+        self.units, need_group = plan_rank(nw, nb, self.rank, self.world, k, self.shard_remainder)
         if need_group:
             bad = [len(c) for c in self.windows if len(c) % k]
             if bad:
@@ -214,6 +206,18 @@ class DenoiseLoop:
             if callback is not None and i % callback_steps == 0:
                 callback(i, self.timesteps[i], self.latents)
         return self.latents
+
+
+def plan_rank(n_windows: int, n_branches: int, rank: int, world: int, k: int, shard_remainder: bool):
+    """This rank's work for one step: [(window index, branches, frame-sharded?)], and whether the run needs peer buffers at
+    all (the same answer on every rank: creating them is a collective).  Frame-sharded forwards come first: all ranks leave
+    the per-step all-reduce together, so the k peers of a group meet at once."""
+    group_idx = rank // k
+    if shard_remainder and k > 1:
+        whole, shared = plan_units_mixed(n_windows, n_branches, world, k)
+        units = [(wi, b, True) for wi, b in shared[group_idx]] + [(wi, b, False) for wi, b in whole[rank]]
+        return units, any(len(s) for s in shared)
+    return [(wi, b, k > 1) for wi, b in plan_units(n_windows, n_branches, world // k)[group_idx]], k > 1
 
 
 def plan_units(n_windows: int, n_branches: int, n_groups: int):

@@ -294,3 +294,59 @@ def test_plan_units_mixed_shares_the_remainder():
     whole, shared = plan_units_mixed(10, 2, 6, 2)          # 8 single forwards for 6 ranks: 2 left for 3 pairs -> dealt whole
     assert not any(shared) and _forwards(whole) == every
     assert sorted(sum(len(b) for _, b in w) for w in whole) == [3, 3, 3, 3, 4, 4]
+
+
+@pytest.mark.parametrize("world,k,remainder", [(1, 1, False), (2, 1, False), (4, 1, False), (8, 1, False), (8, 2, True),
+                                               (4, 2, True), (2, 2, True), (2, 2, False), (8, 4, False), (6, 2, True)])
+def test_every_frame_of_every_forward_is_computed_exactly_once(world, k, remainder):
+    """The schedules DenoiseLoop runs (bench.py at 1 / 2 / 4 / 8 GPUs and the explicit frame-shard modes): over all ranks,
+    each (window, CFG branch, frame) appears exactly once, and all ranks agree on whether peer buffers are needed."""
+    from mmgt_b200.pipeline_pose2vid_long import plan_rank
+    windows = uniform_windows(0, 80)
+    seen, need, load = [], set(), []
+    for rank in range(world):
+        units, need_group = plan_rank(len(windows), 2, rank, world, k, remainder)
+        need.add(need_group)
+        work = 0.0
+        for wi, branches, sharded in units:
+            c = windows[wi]
+            if sharded:
+                fl = len(c) // k
+                c = c[(rank % k) * fl:(rank % k + 1) * fl]
+            seen += [(wi, b, f) for b in branches for f in c]
+            work += len(branches) * len(c) / 12.0
+        load.append(work)
+    assert sorted(seen) == sorted((wi, b, f) for wi, c in enumerate(windows) for b in range(2) for f in c)
+    assert len(need) == 1
+    if (world, k, remainder) in ((8, 2, True), (4, 2, True), (4, 1, False), (2, 1, False)):
+        assert max(load) == min(load) == 20.0 / world          # perfectly balanced: 2.5 forwards per rank on 8 GPUs
+
+
+def test_ctypes_structs_match_the_c_header_layout(tmp_path):
+    """The ctypes mirrors in mmgt_b200/_lib.py must have the size and field offsets gcc gives the structs of
+    include/mmgt_b200.h (a silent mismatch would hand kernels garbage pointers)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from mmgt_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"mmgt_gemm_params": _lib.GemmParams, "mmgt_conv3x3_params": _lib.Conv3x3Params,
+             "mmgt_attention_params": _lib.AttentionParams, "mmgt_audio_attention_params": _lib.AudioAttentionParams,
+             "mmgt_row_exchange": _lib.RowExchange, "mmgt_peer_barrier_params": _lib.PeerBarrierParams}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mmgt_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l.strip()}
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, f"{cname}.{fname}"
