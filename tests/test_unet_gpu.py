@@ -258,3 +258,45 @@ def test_thirty_step_denoise_latent_psnr():
         assert psnr >= floor
         del unet, loop
         torch.cuda.empty_cache()
+
+
+def test_pose2video_pipeline_call_matches_oracle_loop():
+    """The top of the drop-in boundary: Pose2VideoPipeline.__call__ with the reference's argument list (conditioning passes
+    supplied precomputed, output_type="latent") runs CFG duplication, ReferenceAttentionControl, the windowed DDIM loop --
+    and must reproduce the oracle's loop on the same inputs (float32 tier)."""
+    from helpers import bank_pairing_order
+    from mmgt_b200.pipeline_pose2vid_long import Pose2VideoPipeline, Pose2VideoPipelineOutput
+    from mmgt_b200.scheduling_ddim import DDIMSchedule
+    spec = UNetSpec(block_out_channels=TINY)
+    sd = synthetic_state_dict("tiny")
+    unet = build_cuda_unet(TINY, sd, compute_dtype=torch.float32)
+    unet.train()
+    unet.enable_gradient_checkpointing()      # what scripts/pose2vid.py:184 does
+    L, latent, n_steps = 20, 16, 4
+    inp = make_inputs(spec, L, latent, seed=17)
+    banks = make_banks(spec, latent)
+    windows = uniform_windows(0, L)
+
+    def unet_fn(sample, t, ehs, aud, pose, full, face, lip, ms):
+        with torch.no_grad():
+            return unet3d_forward(sd, spec, sample, t, ehs, aud, pose, full, face, lip, ms, banks, ref_index=[None, 1],
+                                  apply_motion_scale=True)
+    ddim = DDIM()
+    lat_ref = inp["latents"].clone()
+    for t in ddim.timesteps(n_steps):
+        lat_ref, _ = denoise_step(unet_fn, lat_ref, t, n_steps, ddim, 3.5, windows, inp["pose_fea"], inp["audio"],
+                                  inp["full_mask"], inp["face_mask"], inp["lip_mask"], inp["encoder_hidden_states"],
+                                  inp["motion_scale"])
+    cond = lambda ms: [m[:L].cuda() for m in ms]   # noqa: E731  the pipeline duplicates for CFG itself
+    pipe = Pose2VideoPipeline(vae=None, image_encoder=None, reference_unet=None, denoising_unet=unet, pose_guider=None,
+                              scheduler=DDIMSchedule.from_config())
+    out = pipe(None, None, inp["audio"][1:2].cuda(), cond(inp["full_mask"]), cond(inp["face_mask"]), cond(inp["lip_mask"]),
+               width=latent * 8, height=latent * 8, video_length=L, num_inference_steps=n_steps, guidance_scale=3.5,
+               motion_scale=inp["motion_scale"], output_type="latent",
+               clip_image_embeds=inp["encoder_hidden_states"][1].cuda(), pose_fea=inp["pose_fea"].cuda(),
+               reference_banks=[banks[p].cuda() for p in bank_pairing_order(spec)], latents=inp["latents"].cuda())
+    assert isinstance(out, Pose2VideoPipelineOutput) and out.videos.shape == inp["latents"].shape
+    err = rel_l2(out.videos, lat_ref)
+    print(f"Pose2VideoPipeline.__call__ ({n_steps} steps, float32): latents rel-L2 vs oracle loop {err:.3e}")
+    assert err < TOL_F32
+    assert all(len(b.bank) == 0 for b in unet.spatial_blocks())        # reader.clear() ran (pipeline_pose2vid_long.py:648-649)
