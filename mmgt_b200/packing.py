@@ -52,3 +52,26 @@ def geglu_interleave(weight: torch.Tensor, bias: torch.Tensor, gb: int):
     bv, bg = bias[:n].reshape(n // gb, gb), bias[n:].reshape(n // gb, gb)
     b = torch.stack([bv, bg], dim=1).reshape(2 * n)
     return w, b
+
+
+def subpixel_upsample_weights(weight: torch.Tensor):
+    """Upsample3D = nearest x2 followed by a 3x3 / pad 1 convolution (resnet.py:70-88).  Each output parity (a, b) of
+    out[2y+a, 2x+b] only ever sees a 2x2 neighbourhood of the LOW-resolution input, so the operator is four 2x2-tap
+    convolutions on the input with pre-summed weights: rows {y-1, y} for a = 0 and {y, y+1} for a = 1 (same for columns),
+    zero outside the image -- 16 tap-GEMMs at input resolution instead of 9 at output resolution (2.25x fewer FLOPs) and
+    no upsampled / im2col tensor.  Not wired into the kernels yet; the identity is checked in
+    tests/test_host_logic.py.
+
+    weight (Cout, Cin, 3, 3) -> dict[(a, b)] = (taps (Cout, Cin, 2, 2), row offsets (2,), column offsets (2,))."""
+    w = weight.detach()
+    out = {}
+    for a in (0, 1):
+        # a = 0: upsampled rows 2y-1, 2y, 2y+1 -> input rows y-1, y, y     a = 1: rows 2y, 2y+1, 2y+2 -> y, y, y+1
+        rows = ([w[:, :, 0], w[:, :, 1] + w[:, :, 2]], (-1, 0)) if a == 0 else ([w[:, :, 0] + w[:, :, 1], w[:, :, 2]], (0, 1))
+        for b in (0, 1):
+            taps = []
+            for r in rows[0]:                                    # r: (Cout, Cin, 3) over kernel columns
+                cols = [r[:, :, 0], r[:, :, 1] + r[:, :, 2]] if b == 0 else [r[:, :, 0] + r[:, :, 1], r[:, :, 2]]
+                taps.append(torch.stack(cols, dim=-1))
+            out[(a, b)] = (torch.stack(taps, dim=-2), rows[1], (-1, 0) if b == 0 else (0, 1))
+    return out

@@ -350,3 +350,24 @@ def test_ctypes_structs_match_the_c_header_layout(tmp_path):
         assert got[(cname, "size")] == ctypes.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert got[(cname, fname)] == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
+def test_subpixel_upsample_weights_equal_upsample_then_conv():
+    """packing.subpixel_upsample_weights: four 2x2-tap convolutions on the low-resolution input == conv3x3(nearest x2)."""
+    import torch.nn.functional as F
+    from mmgt_b200.packing import subpixel_upsample_weights
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 5, 6, 7, generator=g, dtype=torch.float64)
+    w = torch.randn(4, 5, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, padding=1)
+    out = torch.zeros_like(ref)
+    H, W = x.shape[2:]
+    for (a, b), (taps, dys, dxs) in subpixel_upsample_weights(w).items():
+        acc = torch.zeros(2, 4, H, W, dtype=torch.float64)
+        xp = F.pad(x, (1, 1, 1, 1))
+        for i, dy in enumerate(dys):
+            for j, dx in enumerate(dxs):
+                patch = xp[:, :, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W]
+                acc += torch.einsum("nchw,oc->nohw", patch, taps[:, :, i, j])
+        out[:, :, a::2, b::2] = acc
+    assert torch.allclose(out, ref, atol=1e-10)
