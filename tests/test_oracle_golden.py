@@ -93,3 +93,24 @@ def test_bank_pairing_order_is_down_up_mid():
     assert len(order) == 16
     assert order[:6] == ["down_blocks.2.attentions.0", "down_blocks.2.attentions.1", "up_blocks.1.attentions.0",
                          "up_blocks.1.attentions.1", "up_blocks.1.attentions.2", "mid_block.attentions.0"]
+
+
+def test_conditioning_oracle_matches_reference_golden():
+    """SURVEY section 8f row f1 groundwork: the restated PoseGuider / AudioProjModel (oracle/conditioning.py) against outputs
+    of the reference's own classes on the same seeded weights and inputs (oracle/make_golden_f1.py)."""
+    import json
+    from oracle.conditioning import audio_proj_forward, pose_guider_forward
+    from oracle.make_golden_f1 import AUDIO_CFG, POSE_CFG, audio_input, pose_input, zero_init_visible
+    from oracle.weights import make_state_dict
+    g = np.load(os.path.join(GOLD, "conditioning.npz"))
+    with open(os.path.join(GOLD, "conditioning_spec.json")) as f:
+        specs = json.load(f)
+    with torch.no_grad():
+        sd = zero_init_visible(make_state_dict([(k, tuple(s)) for k, s in specs["pose_guider"]], seed=3), "conv_out", seed=31)
+        out = pose_guider_forward(sd, pose_input(), POSE_CFG["block_out_channels"])
+        assert out.shape == (1, 320, 3, 8, 8)                     # 64 x 64 pose image -> 8 x 8 x 320 features
+        assert rel_l2(out, torch.from_numpy(g["pose_out"])) < 1e-5
+        sd = make_state_dict([(k, tuple(s)) for k, s in specs["audio_proj"]], seed=4)
+        out = audio_proj_forward(sd, audio_input(), AUDIO_CFG["context_tokens"], AUDIO_CFG["output_dim"])
+        assert out.shape == (1, 2, 32, 768)
+        assert rel_l2(out, torch.from_numpy(g["audio_out"])) < 1e-5
