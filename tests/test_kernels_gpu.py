@@ -326,17 +326,20 @@ def test_mask_pyramid_bit_exact(dev):
     from mmgt_b200.image_processor import MaskPyramid
     from oracle.mask_pyramid import full_mask_from_lips, mask_pyramid_u8, preprocess_mov_mask
     from oracle.synthetic import synthetic_masks_u8
-    face, lips = synthetic_masks_u8(7)
+    import os
+    from helpers import GOLD
+    real = np.load(os.path.join(GOLD, "real_masks.npz"))      # the reference's bundled case, oracle/make_golden_masks.py
+    for face, lips in (synthetic_masks_u8(7), (real["face"], real["lips"])):
+        for image_size in (512, 256, 768):
+            mp = MaskPyramid(image_size, dev)
+            f_gpu, l_gpu = mp.preprocess_mov_mask(list(face), list(lips))
+            f_ref, l_ref = preprocess_mov_mask(face, lips, image_size)
+            full_gpu, full_ref = mp.full_mask_from_lips(list(lips)), full_mask_from_lips(l_ref)
+            for k in range(4):
+                assert torch.equal(f_gpu[k].cpu(), torch.from_numpy(f_ref[k])), (image_size, k)
+                assert torch.equal(l_gpu[k].cpu(), torch.from_numpy(l_ref[k])), (image_size, k)
+                assert torch.equal(full_gpu[k].cpu(), torch.from_numpy(full_ref[k])), (image_size, k)
     noise = np.random.default_rng(5).integers(0, 256, (3, 64, 64), dtype=np.uint8)
-    for image_size in (512, 256, 768):
-        mp = MaskPyramid(image_size, dev)
-        f_gpu, l_gpu = mp.preprocess_mov_mask(list(face), list(lips))
-        f_ref, l_ref = preprocess_mov_mask(face, lips, image_size)
-        full_gpu, full_ref = mp.full_mask_from_lips(list(lips)), full_mask_from_lips(l_ref)
-        for k in range(4):
-            assert torch.equal(f_gpu[k].cpu(), torch.from_numpy(f_ref[k])), (image_size, k)
-            assert torch.equal(l_gpu[k].cpu(), torch.from_numpy(l_ref[k])), (image_size, k)
-            assert torch.equal(full_gpu[k].cpu(), torch.from_numpy(full_ref[k])), (image_size, k)
     eng = eng_for(dev, torch.float32)
     for s, ref in zip((64, 32, 16, 8), mask_pyramid_u8(noise, 512)):
         _, u8 = eng.mask_resize(torch.from_numpy(noise).to(dev), s, want_u8=True)

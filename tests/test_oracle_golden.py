@@ -114,3 +114,27 @@ def test_conditioning_oracle_matches_reference_golden():
         out = audio_proj_forward(sd, audio_input(), AUDIO_CFG["context_tokens"], AUDIO_CFG["output_dim"])
         assert out.shape == (1, 2, 32, 768)
         assert rel_l2(out, torch.from_numpy(g["audio_out"])) < 1e-5
+
+
+def test_mask_pyramid_on_the_reference_case_masks_bit_exact_vs_pillow():
+    """The bundled real case (config/cases/oliver#103842_slice18_{face,lips}_mask.mp4 through the scripts' blur_mask
+    front-end, oracle/make_golden_masks.py): the restated Pillow resize must reproduce live torchvision + Pillow bit for bit
+    at every pyramid size of the 512^2 and 768^2 configurations, and ToTensor's u8 / 255."""
+    from PIL import Image
+    import torchvision.transforms as T
+    g = np.load(os.path.join(GOLD, "real_masks.npz"))
+    face, lips = g["face"], g["lips"]
+    assert face.shape == lips.shape == (6, 64, 64) and face.dtype == np.uint8
+    for stack in (face, lips):
+        for img in stack:
+            for s in (64, 32, 16, 8, 96, 48, 24, 12):
+                ref = np.array(T.Resize((s, s))(Image.fromarray(img, "L")))
+                assert np.array_equal(ref, resize_bilinear_u8(img, s, s)), s
+    for image_size in (512, 768):
+        f_lvls, l_lvls = preprocess_mov_mask(face, lips, image_size)
+        for k in range(4):
+            s = image_size // 8 >> k
+            tt = T.Compose([T.Resize((s, s)), T.ToTensor()])
+            for lv, stack in ((f_lvls, face), (l_lvls, lips)):
+                ref = torch.stack([tt(Image.fromarray(m, "L")) for m in stack]).view(len(stack), -1)
+                assert torch.equal(ref, torch.from_numpy(lv[k])), (image_size, k)
