@@ -230,9 +230,11 @@ class Engine:
         p.dtype = self.dt
         ev = self._t0()
         check(self.lib.mmgt_attention(self.h, C.byref(p), _stream()), "mmgt_attention")
-        lk_tot = k.shape[1] + (k2.shape[1] if k2 is not None else 0)   # upper bound: frames without segment 2 do less
-        self._t1(ev, ("attention", d, k.shape[1], k2 is not None), 4.0 * N * heads * Lq * lk_tot * d,
-                 (2 * q.numel() + 2 * N * lk_tot * Cc) * q.element_size())
+        # algorithmic work: frames whose seg2 index is -1 (the CFG uncond half) attend to the first segment only
+        n2 = 0 if k2 is None else (N if seg2_index is None else getattr(seg2_index, "_n_seg2", N))
+        keys = N * k.shape[1] + (n2 * k2.shape[1] if k2 is not None else 0)        # sum over frames of their key count
+        self._t1(ev, ("attention", d, k.shape[1], k2 is not None), 4.0 * heads * Lq * keys * d,
+                 (2 * q.numel() + 2 * keys * Cc) * q.element_size())
         return out
 
     def audio_attention_supported(self, M: int, d: int) -> bool:

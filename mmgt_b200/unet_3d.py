@@ -283,6 +283,7 @@ class UNet3DConditionModel(nn.Module):
         key = (str(eng.device), B, F, tuple(-1 if r is None else int(r) for r in ref_index))
         if key not in self._idx_cache:
             idx = torch.tensor([v for v in key[3] for _ in range(F)], dtype=torch.int32, device=eng.device)
+            idx._n_seg2 = sum(F for v in key[3] if v >= 0)     # host-side count for the FLOP accounting of bench.py
             self._idx_cache[key] = idx
         return self._idx_cache[key]
 
