@@ -371,3 +371,14 @@ def test_subpixel_upsample_weights_equal_upsample_then_conv():
                 acc += torch.einsum("nchw,oc->nohw", patch, taps[:, :, i, j])
         out[:, :, a::2, b::2] = acc
     assert torch.allclose(out, ref, atol=1e-10)
+
+
+def test_config5_schedule_is_balanced_on_eight_gpus():
+    """BASELINE config 5: 160 frames = 20 windows = 40 forwards; 8 GPUs take 2 whole windows + 1 single-branch forward
+    each -- balanced without frame shards."""
+    from mmgt_b200.pipeline_pose2vid_long import plan_rank
+    windows = uniform_windows(0, 160)
+    assert len(windows) == 20
+    for rank in range(8):
+        units, need_group = plan_rank(len(windows), 2, rank, 8, 2, True)
+        assert not need_group and [len(b) for _, b, _ in units] == [2, 2, 1] and not any(sh for _, _, sh in units)
