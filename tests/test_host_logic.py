@@ -382,3 +382,41 @@ def test_config5_schedule_is_balanced_on_eight_gpus():
     for rank in range(8):
         units, need_group = plan_rank(len(windows), 2, rank, 8, 2, True)
         assert not need_group and [len(b) for _, b, _ in units] == [2, 2, 1] and not any(sh for _, _, sh in units)
+
+
+def test_engine_wrappers_with_a_mocked_library():
+    """Host side of mmgt_b200.kernels.Engine without a GPU: the ctypes parameter blocks it hands to the C ABI and the work
+    accounting bench.py reports (the library itself is mocked -- compute is covered by the -m gpu tests)."""
+    from unittest import mock
+    import mmgt_b200.kernels as K
+    eng = object.__new__(K.Engine)
+    eng.device, eng.dtype, eng.dt, eng.h, eng.prof, eng.unfused_exchange = torch.device("cpu"), torch.bfloat16, 1, None, None, False
+    eng.lib = mock.MagicMock()
+    for name in ("mmgt_attention", "mmgt_audio_attention", "mmgt_gemm"):
+        getattr(eng.lib, name).return_value = 0
+    seen = {}
+    eng._t1 = lambda ev, key, flops=0.0, nbytes=0.0: seen.update(key=key, flops=flops, nbytes=nbytes)
+    with mock.patch.object(K, "_stream", lambda: None):
+        N, T, C, heads = 4, 64, 64, 8
+        qkv = torch.zeros(N, T, 3 * C, dtype=torch.bfloat16)
+        kv2 = torch.zeros(2, T, 2 * C, dtype=torch.bfloat16)
+        idx = torch.tensor([-1, -1, 1, 1], dtype=torch.int32)
+        idx._n_seg2 = 2                                       # what UNet3DConditionModel._seg2_index records
+        eng.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, k2=kv2[:, :, :C], v2=kv2[:, :, C:], seg2_index=idx)
+        p = eng.lib.mmgt_attention.call_args[0][1]._obj
+        assert (p.N, p.Lq, p.Lk, p.Lk2, p.heads, p.d, p.B2) == (N, T, T, T, heads, C // heads, 2)
+        assert (p.ldq, p.ldk, p.ldk2, p.ldo) == (3 * C, 3 * C, 2 * C, C)
+        assert seen["flops"] == 4.0 * heads * T * (N * T + 2 * T) * (C // heads)      # uncond frames: one key segment
+        # fused MM-HAA attention: output carries 3C gated columns + 8 gate / pad columns
+        q3, kv6 = torch.zeros(N * T, 3 * C, dtype=torch.bfloat16), torch.zeros(N * 32, 6 * C, dtype=torch.bfloat16)
+        masks = [torch.ones(N * T) for _ in range(3)]
+        out = eng.audio_attention(q3, kv6, masks, (1.0, 1.0, 2.0), N, T, heads)
+        a = eng.lib.mmgt_audio_attention.call_args[0][1]._obj
+        assert out.shape == (N * T, 3 * C + 8) and (a.N, a.T, a.M, a.heads, a.d) == (N, T, 32, heads, C // heads)
+        assert (a.ldq, a.ldkv, a.ldo) == (3 * C, 6 * C, 3 * C + 8) and list(a.scale) == [1.0, 1.0, 2.0]
+        # GEMM: strides / GEGLU output width
+        A, W = torch.zeros(10, 32, dtype=torch.bfloat16), torch.zeros(64, 32, dtype=torch.bfloat16)
+        y = eng.gemm(A, W, geglu_block=16)
+        g = eng.lib.mmgt_gemm.call_args[0][1]._obj
+        assert y.shape == (10, 32) and (g.M, g.N, g.K, g.lda, g.ldw, g.ldd, g.geglu_block) == (10, 64, 32, 32, 32, 32, 16)
+        assert not g.exchange
