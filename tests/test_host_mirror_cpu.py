@@ -141,3 +141,56 @@ def test_frame_sharded_unet_on_cpu_matches_unsharded(k):
     assert not errors, errors
     got = torch.stack([o.view(B, Fl, latent, latent, -1) for o in outs], dim=1).reshape(ref.shape)
     assert rel_l2(got, ref) < 1e-5
+
+
+@pytest.mark.parametrize("world,k,remainder,L,latent", [(4, 1, False, 80, 8), (8, 2, True, 80, 16), (2, 2, False, 20, 16)],
+                         ids=["4-ranks-whole", "8-ranks-window+shared-forward", "2-ranks-all-sharded"])
+def test_multi_rank_schedules_sum_to_the_single_rank_step(monkeypatch, world, k, remainder, L, latent):
+    """bench.py's schedules at 4 and 8 GPUs (and the all-sharded mode), rank by rank on the fake engine: the per-rank
+    accumulated predictions (what the per-step all-reduce sums) must add up to the single-rank accumulator.  The ranks of a
+    frame-shard group run in threads and exchange rows through FakeShardGroup, exactly the host code of the GPU run."""
+    from mmgt_b200.pipeline_pose2vid_long import DenoiseLoop
+    from mmgt_b200.scheduling_ddim import DDIMSchedule
+    spec, sd, unet = _tiny_unet()
+    monkeypatch.setattr(unet, "_engine", lambda device: FakeEngine())
+    n_steps = 30
+    inp = make_inputs(spec, L, latent, seed=21)
+    attach_banks(unet, spec, make_banks(spec, latent), cfg=True)
+    args = (inp["latents"], inp["pose_fea"], inp["audio"], inp["full_mask"], inp["face_mask"], inp["lip_mask"],
+            inp["encoder_hidden_states"])
+
+    def make(rank, world_size, group=None):
+        loop = DenoiseLoop(unet, DDIMSchedule.from_config(), n_steps, 3.5, motion_scale=inp["motion_scale"], rank=rank,
+                           world_size=world_size, frame_shards=k if world_size > 1 else 1, shard_group=group,
+                           shard_remainder=remainder and world_size > 1)
+        loop.prepare(*args)
+        loop.t_dev.fill_(float(loop.timesteps[0]))
+        return loop
+    single = make(0, 1)
+    single._units_body()
+    total = torch.zeros_like(single.noise_acc)
+    work = []
+    for g0 in range(0, world, k):
+        groups = FakeShardGroup.make(k) if k > 1 else [None]
+        loops = [make(g0 + s, world, groups[s]) for s in range(k)]
+        errors = []
+
+        def body(lp):
+            try:
+                lp._units_body()
+            except Exception as e:   # noqa: BLE001
+                errors.append(repr(e))
+                if lp.shard_group is not None:
+                    lp.shard_group._barrier.abort()
+        threads = [threading.Thread(target=body, args=(lp,)) for lp in loops]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join(timeout=900)
+        assert not errors, errors
+        for lp in loops:
+            total += lp.noise_acc
+            work.append(sum(len(b) * e["frames"] / 12.0 for (_, b, _), e in zip(lp.units, lp.prepared)))
+    assert rel_l2(total, single.noise_acc) < 1e-5
+    if L == 80:
+        assert max(work) == min(work) == 20.0 / world       # balanced: 5 (4 ranks) / 2.5 (8 ranks) forwards of work per rank
