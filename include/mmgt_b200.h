@@ -54,7 +54,16 @@ MMGT_API const char* mmgt_last_error(void);
  * flag 2: enable (1) / disable (0) the weight-stationary tensor-core GEMM variant for small K (default 1).
  * flag 3: enable (1) / disable (0) programmatic dependent launch: every kernel is launched with programmatic stream
  *         serialization and waits (griddepcontrol.wait) before its first global access, so its scheduling and
- *         prologue overlap the tail of the previous kernel; stream semantics are unchanged. */
+ *         prologue overlap the tail of the previous kernel; stream semantics are unchanged.
+ * flag 4: strict tensor-core mode (default 0): a bf16 GEMM / convolution / attention request that no tcgen05 kernel
+ *         covers returns MMGT_E_UNSUPPORTED instead of running on the CUDA-core kernels (shape cliffs become errors).
+ * flag 5: number of bf16 operator calls that ran on a CUDA-core kernel while flag 0 was on (read with value<0).
+ * flag 6: 1 = the tensor-core GEGLU epilogue evaluates GELU through erf (Abramowitz-Stegun 7.1.26) instead of the
+ *         default logistic-polynomial fit (<= 8.2e-4 relative, 0.4 bf16 half-ulps); A/B switch for tests.
+ * flag 7: GroupNorm as two kernels, statistics then normalise (default 1); 0 = the single kernel with a per-frame
+ *         arrival barrier (grid limited to co-resident CTAs).  A/B switch.
+ * flag 8: stride-2 and upsampling 3x3 convolutions as implicit GEMMs (TMA traversal stride 2; four sub-pixel 2x2-tap
+ *         convolutions) (default 1); 0 = stage an im2col matrix and run the plain GEMM.  A/B switch. */
 MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);
 
 /* Layout ------------------------------------------------------------------------------------- */
@@ -84,6 +93,12 @@ MMGT_API int mmgt_groupnorm(mmgt_ctx*, const void* x1, const void* x2_or_null, v
 MMGT_API int mmgt_layernorm(mmgt_ctx*, const void* x, void* y, const float* gamma, const float* beta,
                    const float* pe_or_null, int64_t rows, int C, int T, int F, float eps, int dtype,
                    void* stream);
+
+/* (mean, rstd) of every row of x (rows, C) with leading dimension ld (0 = C): stats (rows, 2) float32.  The LayerNorm
+ * itself is then applied by the GEMM that consumes x (mmgt_gemm_params.rowstats / colsum), so the normalised tensor
+ * is never written (attention.py:331-362,576-644; motion_module.py:228-244). */
+MMGT_API int mmgt_row_stats(mmgt_ctx*, const void* x, float* stats, int64_t rows, int C, int64_t ld, float eps, int dtype,
+                            void* stream);
 
 /* Frame-shard <-> token-shard row exchange (multi-GPU, SURVEY.md section 8e level 3) ------------------
  * k ranks share one context window: each holds F/k of the F frames ("frame-sharded", rows (b, f_loc, t)).
@@ -125,6 +140,16 @@ typedef struct {
   const mmgt_row_exchange* exchange; /* HOST pointer or NULL.  Non-NULL: the epilogue stores row m of the result to the
                            peer / row given by the exchange instead of D + m*ldd (D is ignored, may be NULL);
                            tensor-core path only (bf16), otherwise MMGT_E_UNSUPPORTED */
+  int64_t ld_rowbias;   /* elements between rowbias rows (0 = N_out): lets one (B, sum of widths) time-embedding
+                           projection serve every resnet as a column slice (resnet.py:226) */
+  int rowbias_mod;      /* > 0: rowbias row = (m / rows_per_group) % rowbias_mod (the motion module's positional
+                           table added per frame of every sample, motion_module.py:365-366) */
+  const float* rowstats;/* (M,2) float32 [mean, rstd] or NULL.  Non-NULL fuses the LayerNorm that feeds this GEMM:
+                           with W' = W diag(gamma), colsum[n] = sum_k W'[n,k] and bias' = bias + W beta the result is
+                           rstd*(A W'^T - mean*colsum) + bias' = LN(A) W^T + bias (attention.py:331-362) */
+  const float* colsum;  /* (N) float32, required with rowstats */
+  int act;              /* 0 none, 1 SiLU, 2 ReLU: applied after bias / rowscale / rowbias, before the residual
+                           (pose_guider.py:47-57, audio_proj.py:96) */
 } mmgt_gemm_params;
 /* Replaces nn.Linear / 1x1 nn.Conv2d + bias + residual adds + GEGLU (diffusers Attention.to_q/k/v/out,
  * FeedForward; transformer_3d.py:176,253; resnet.py:226,243; attention.py:730-767;
@@ -146,6 +171,13 @@ typedef struct {
   int upsample2x;       /* 1: x is nearest-upsampled x2 on the fly before the conv (Upsample3D, resnet.py:70-88) */
   int frames_per_group; /* frames sharing one rowbias row (= F) */
   int dtype;
+  int64_t ld_rowbias;   /* elements between rowbias rows (0 = Cout) */
+  int act;              /* 0 none, 1 SiLU, 2 ReLU (after bias / rowbias, before the residual) */
+  const void* w_subpixel; /* upsample2x only, or NULL: (Cout, 4, 2, 2, Cin) pre-summed taps of the four output parities
+                           (a, b) = (row, column) parity, index 2a + b; tap (ty, tx) of parity (a, b) reads input pixel
+                           (h + ty - (a ? 0 : 1), w + tx - (b ? 0 : 1)).  With it the bf16 tensor-core path runs the
+                           upsampling convolution as four 2x2-tap implicit GEMMs on the low-resolution input (2.25x fewer
+                           FLOPs, nothing staged); without it the operator stages an im2col matrix. */
 } mmgt_conv3x3_params;
 /* Replaces InflatedConv3d k=3 (resnet.py:9-17) incl. the fused epilogue of ResnetBlock3D.
  * workspace: scratch of at least mmgt_conv3x3_workspace_bytes() bytes (may be NULL when that is 0;
@@ -213,6 +245,10 @@ MMGT_API int mmgt_upsample_nearest2x(mmgt_ctx*, const void* x, void* y, int N, i
 /* im2col for 3x3 / pad 1 with stride and optional x2 nearest upsample: (N,H,W,C) -> (N*Ho*Wo, 9*C). */
 MMGT_API int mmgt_im2col3x3(mmgt_ctx*, const void* x, void* col, int N, int H, int W, int C, int stride, int upsample2x,
                    int dtype, void* stream);
+
+/* dst (rows, Cpad) = [src (rows, C) | 0]: pads the 4 latent channels so that conv_in (unet_3d.py:517) runs as a
+ * tensor-core implicit GEMM (its weight is zero-padded to the same width). */
+MMGT_API int mmgt_pad_channels(mmgt_ctx*, const void* src, void* dst, int64_t rows, int C, int Cpad, int dtype, void* stream);
 
 /* dst[i, :] = src[idx[i], :]; rows of row_bytes (multiple of 16) bytes.  Assembles a context window from
  * whole-video tensors (latents[:, :, c], pose_fea[:, :, c], masks.view(2, L, -1)[:, c];

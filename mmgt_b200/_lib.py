@@ -19,14 +19,15 @@ class GemmParams(C.Structure):
                 ("rowbias", c_void_p), ("residual", c_void_p),
                 ("lda", c_int64), ("ldw", c_int64), ("ldd", c_int64), ("ldr", c_int64),
                 ("M", c_int), ("N", c_int), ("K", c_int), ("rows_per_group", c_int), ("alpha", c_float),
-                ("geglu_block", c_int), ("dtype", c_int), ("out_f32", c_int), ("exchange", c_void_p)]
+                ("geglu_block", c_int), ("dtype", c_int), ("out_f32", c_int), ("exchange", c_void_p),
+                ("ld_rowbias", c_int64), ("rowbias_mod", c_int), ("rowstats", c_void_p), ("colsum", c_void_p), ("act", c_int)]
 
 
 class Conv3x3Params(C.Structure):
     _fields_ = [("x", c_void_p), ("w", c_void_p), ("y", c_void_p), ("bias", c_void_p), ("rowbias", c_void_p),
                 ("residual", c_void_p),
                 ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int), ("stride", c_int),
-                ("upsample2x", c_int), ("frames_per_group", c_int), ("dtype", c_int)]
+                ("upsample2x", c_int), ("frames_per_group", c_int), ("dtype", c_int), ("ld_rowbias", c_int64), ("act", c_int), ("w_subpixel", c_void_p)]
 
 
 class AttentionParams(C.Structure):
@@ -70,6 +71,7 @@ SIGNATURES = {
     "mmgt_tokens_to_ncfhw": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "mmgt_groupnorm": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_float, c_int, c_int, c_void_p]),
     "mmgt_layernorm": (c_int, [c_void_p] * 6 + [c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "mmgt_row_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_float, c_int, c_void_p]),
     "mmgt_gemm": (c_int, [c_void_p, C.POINTER(GemmParams), c_void_p]),
     "mmgt_gemm_tc_block_n": (c_int, [c_int]),
     "mmgt_conv3x3_workspace_bytes": (c_int64, [c_void_p, C.POINTER(Conv3x3Params)]),
@@ -81,6 +83,7 @@ SIGNATURES = {
     "mmgt_silu_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mmgt_upsample_nearest2x": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "mmgt_im2col3x3": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "mmgt_pad_channels": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "mmgt_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "mmgt_window_accumulate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "mmgt_cfg_ddim_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_float] * 3 + [c_void_p]),
@@ -163,3 +166,20 @@ class Context:
 
     def launches(self) -> int:
         return int(self.lib.mmgt_ctx_flag(self.handle, 1, -1))
+
+    def set_strict_tensor_cores(self, on: bool) -> bool:
+        """bf16 requests without a tensor-core kernel raise (MMGT_E_UNSUPPORTED) instead of running on CUDA cores."""
+        return bool(self.lib.mmgt_ctx_flag(self.handle, 4, 1 if on else 0))
+
+    def simt_launches(self) -> int:
+        """bf16 operator calls that took a CUDA-core kernel although tensor cores were enabled (shape cliffs)."""
+        return int(self.lib.mmgt_ctx_flag(self.handle, 5, -1))
+
+    def set_geglu_exact(self, on: bool) -> bool:
+        return bool(self.lib.mmgt_ctx_flag(self.handle, 6, 1 if on else 0))
+
+    def set_groupnorm_split(self, on: bool) -> bool:
+        return bool(self.lib.mmgt_ctx_flag(self.handle, 7, 1 if on else 0))
+
+    def set_conv_implicit_all(self, on: bool) -> bool:
+        return bool(self.lib.mmgt_ctx_flag(self.handle, 8, 1 if on else 0))

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from .kernels import Engine
-from .packing import Pack, conv1x1, f32, geglu_interleave, run
+from .packing import Pack, conv1x1, f32, geglu_interleave, ln_fold, run
 
 
 class Attention(nn.Module):
@@ -29,6 +29,25 @@ class Attention(nn.Module):
         self.to_v = nn.Linear(self.kv_dim, inner, bias=False)
         self.to_out = nn.ModuleList([nn.Linear(inner, query_dim, bias=True), nn.Dropout(dropout)])
         self._pack = Pack()
+        self._ln_pack = Pack()
+
+    def packed_ln(self, eng: Engine, ln: nn.LayerNorm, pe: Optional[torch.Tensor] = None):
+        """Self-attention q|k|v projection with the LayerNorm that feeds it folded in (packing.ln_fold):
+        dict(w (3*inner, C) = [Wq;Wk;Wv] diag(gamma), colsum, bias = [Wq;Wk;Wv] beta, pe = pe [Wq;Wk;Wv]^T or None --
+        the positional table of the motion module goes through the projection once, (max_len, 3*inner) float32, and is
+        added per frame as a row bias (motion_module.py:365-366: the PE feeds q, k and v)."""
+        assert self.kv_dim == self.query_dim
+        srcs = [self.to_q.weight, self.to_k.weight, self.to_v.weight, ln.weight, ln.bias] + ([pe] if pe is not None else [])
+
+        def build():
+            w = torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], dim=0)
+            wp, colsum, bias = ln_fold(w, None, ln.weight, ln.bias, eng)
+            d = dict(w=wp, colsum=colsum, bias=bias, pe=None)
+            if pe is not None:
+                tab = pe.detach().to(device=eng.device, dtype=torch.float64) @ w.detach().to(device=eng.device, dtype=torch.float64).t()
+                d["pe"] = tab.float().contiguous()
+            return d
+        return self._ln_pack.get(eng, srcs, build)
 
     def packed(self, eng: Engine):
         """-> dict(qkv (3*inner, C) if self-attention, q, kv (2*inner, kv_dim), o, bo)."""
@@ -64,18 +83,31 @@ class FeedForward(nn.Module):
             raise NotImplementedError(activation_fn)
         self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(dropout), nn.Linear(dim * mult, dim)])
         self._pack = Pack()
+        self._ln_pack = Pack()
 
-    def run(self, eng: Engine, x_norm, residual, exchange=None):
-        """x_norm: (rows, dim) already layer-normed -> ff(x_norm) + residual.  ``exchange`` (frame_shard.Exchange):
-        the output rows are delivered to the shards that own them instead of being returned."""
+    def run(self, eng: Engine, x, residual, exchange=None, ln=None):
+        """ff(LN(x)) + residual.  ``ln`` None: x (rows, dim) is already layer-normed.  With ``ln`` (the nn.LayerNorm in
+        front of the feed-forward) the normalisation is folded into the GEGLU GEMM on the bf16 tensor-core tier (row
+        statistics + epilogue), else it runs as its own pass first.  ``exchange`` (frame_shard.Exchange): the output
+        rows are delivered to the shards that own them instead of being returned."""
         p1, p2 = self.net[0].proj, self.net[2]
+        fold = ln is not None and eng.ln_fused
+        if ln is not None and not fold:
+            x = ln.run(eng, x)
 
         def build():
             gb = eng.geglu_block(p1.weight.shape[0])
             w1, b1 = geglu_interleave(p1.weight.detach(), p1.bias.detach(), gb)
-            return dict(gb=gb, w1=run(w1, eng), b1=f32(b1, eng), w2=run(p2.weight, eng), b2=f32(p2.bias, eng))
-        pk = self._pack.get(eng, [p1.weight, p1.bias, p2.weight, p2.bias], build)
-        h = eng.gemm(x_norm, pk["w1"], bias=pk["b1"], geglu_block=pk["gb"])
+            d = dict(gb=gb, w2=run(p2.weight, eng), b2=f32(p2.bias, eng))
+            if fold:
+                d["w1"], d["colsum"], d["b1"] = ln_fold(w1, b1, ln.weight, ln.bias, eng)
+            else:
+                d["w1"], d["b1"], d["colsum"] = run(w1, eng), f32(b1, eng), None
+            return d
+        srcs = [p1.weight, p1.bias, p2.weight, p2.bias] + ([ln.weight, ln.bias] if fold else [])
+        pk = (self._ln_pack if fold else self._pack).get(eng, srcs, build)
+        stats = eng.row_stats(x, ln.eps) if fold else None
+        h = eng.gemm(x, pk["w1"], bias=pk["b1"], geglu_block=pk["gb"], rowstats=stats, colsum=pk["colsum"])
         return eng.gemm(h, pk["w2"], bias=pk["b2"], residual=residual, exchange=exchange)
 
 
@@ -83,10 +115,28 @@ class _LN(nn.LayerNorm):
     def __init__(self, dim):
         super().__init__(dim)
         self._pack = Pack()
+        self._pe_pack = Pack()
 
     def run(self, eng: Engine, x, pe=None, T=0, F=0):
         g, b = self._pack.get(eng, [self.weight, self.bias], lambda: (f32(self.weight, eng), f32(self.bias, eng)))
         return eng.layernorm(x, g, b, self.eps, pe=pe, T=T, F=F)
+
+
+def ln_qkv(eng: Engine, x, ln: "_LN", attn: Attention, pe=None, T: int = 0, F: int = 0):
+    """LN(x) (+ pe[frame]) -> fused q|k|v projection (rows, 3*inner).  bf16 tensor-core tier: one pass over x for the row
+    statistics, the normalisation itself happens in the GEMM epilogue; otherwise LayerNorm kernel + GEMM."""
+    if eng.ln_fused:
+        f = attn.packed_ln(eng, ln, pe)
+        stats = eng.row_stats(x, ln.eps)
+        if pe is None:
+            return eng.gemm(x, f["w"], bias=f["bias"], rowstats=stats, colsum=f["colsum"])
+        return eng.gemm(x, f["w"], bias=f["bias"], rowstats=stats, colsum=f["colsum"], rowbias=f["pe"][:F],
+                        rows_per_group=T, rowbias_mod=F)
+    pe_tab = None
+    if pe is not None:
+        pe_tab = ln._pe_pack.get(eng, [pe], lambda: f32(pe, eng))
+    n = ln.run(eng, x, pe=pe_tab, T=T, F=F)
+    return eng.gemm(n, attn.packed(eng)["qkv"])
 
 
 class TemporalBasicTransformerBlock(nn.Module):
@@ -117,9 +167,19 @@ class TemporalBasicTransformerBlock(nn.Module):
         self.norm2 = _LN(dim) if cross_attention_dim else None
         self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
         self.norm3 = _LN(dim)
-        self.bank: List[torch.Tensor] = []
-        self._bank_kv = None       # (key, k2, v2) projected reference keys / values
+        self._bank_list: List[torch.Tensor] = []
+        self._bank_gen = 0         # bumped whenever ``bank`` is assigned: a freed bank's address can be handed out again
+        self._bank_kv = None       # (key, k2, v2, buffer) projected reference keys / values
         self._clip_pack = Pack()
+
+    @property
+    def bank(self) -> List[torch.Tensor]:
+        return self._bank_list
+
+    @bank.setter
+    def bank(self, value):
+        self._bank_list = value
+        self._bank_gen += 1
 
     # -- reference K/V: the bank is constant over all steps and windows => project once
     def bank_kv(self, eng: Engine):
@@ -127,13 +187,26 @@ class TemporalBasicTransformerBlock(nn.Module):
             return None
         bank = self.bank[0]
         pk = self.attn1.packed(eng)
-        key = (bank.data_ptr(), bank._version, tuple(bank.shape), pk["kv"].data_ptr(), str(eng.device), eng.dtype)
+        key = (self._bank_gen, bank.data_ptr(), bank._version, tuple(bank.shape), pk["kv"].data_ptr(), str(eng.device),
+               eng.dtype)
         if self._bank_kv is None or self._bank_kv[0] != key:
             Bb, T, C = bank.shape
             b = bank.to(device=eng.device, dtype=eng.dtype).contiguous().view(Bb * T, C)
-            kv = eng.gemm(b, pk["kv"]).view(Bb, T, 2 * C)
-            self._bank_kv = (key, kv[:, :, :C], kv[:, :, C:])
+            old = self._bank_kv
+            if old is not None and tuple(old[3].shape) == (Bb, T, 2 * C) and old[3].dtype == eng.dtype \
+                    and old[3].device == eng.device:
+                # a new reference image of the same shape: project IN PLACE -- a CUDA graph captured for the previous
+                # video reads this storage (DenoiseLoop.reload)
+                kv = old[3]
+                eng.gemm(b, pk["kv"], out=kv.view(Bb * T, 2 * C))
+            else:
+                kv = eng.gemm(b, pk["kv"]).view(Bb, T, 2 * C)
+            self._bank_kv = (key, kv[:, :, :C], kv[:, :, C:], kv)
         return self._bank_kv[1], self._bank_kv[2]
+
+    def bank_kv_storage(self):
+        """data_ptr of the projected reference K/V buffer (None before the first projection)."""
+        return None if self._bank_kv is None else self._bank_kv[3].data_ptr()
 
     def clip_vector(self, eng: Engine, clip_b):
         """attn2 with a single key/value token: (B, 1, 768) -> (B, C) float32 = to_out(to_v(clip))."""
@@ -151,8 +224,7 @@ class TemporalBasicTransformerBlock(nn.Module):
         heads = self.attn1.heads
         x = tok.view(rows, C)
         pk = self.attn1.packed(eng)
-        n1 = self.norm1.run(eng, x)
-        qkv = eng.gemm(n1, pk["qkv"]).view(N, T, 3 * C)
+        qkv = ln_qkv(eng, x, self.norm1, self.attn1).view(N, T, 3 * C)
         bkv = self.bank_kv(eng)
         k2, v2 = bkv if bkv is not None else (None, None)
         a = eng.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, k2=k2, v2=v2,
@@ -164,8 +236,7 @@ class TemporalBasicTransformerBlock(nn.Module):
             x = eng.gemm(a.view(rows, C), pk["o"], bias=pk["bo"], residual=x)
             if self.attn2 is not None:
                 x = self._cross_general(eng, x, clip_b, N, T, frames)
-        n3 = self.norm3.run(eng, x)
-        return self.ff.run(eng, n3, x).view(N, T, C)
+        return self.ff.run(eng, x, x, ln=self.norm3).view(N, T, C)
 
     def _cross_general(self, eng, x, ctx_b, N, T, frames):
         """attn2 for more than one context token (not exercised by the pipeline, kept for API parity)."""
@@ -215,6 +286,7 @@ class AudioTemporalBasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
         self.norm3 = _LN(dim)
         self._pack = Pack()
+        self._q3_pack = Pack()
         self.fuse_regions = True       # bf16 tier: fused three-region kernel + one GEMM (False = per-region operators)
         self._fused_key, self._fused_val = None, None
 
@@ -234,6 +306,17 @@ class AudioTemporalBasicTransformerBlock(nn.Module):
             d["bz"] = [f32(z.bias, eng) for z in zcs]
             return d
         return self._pack.get(eng, params, build)
+
+    def _q3_ln(self, eng: Engine):
+        """The three audio query projections [Wq_full; Wq_face; Wq_lip] with norm2 folded in (packing.ln_fold)."""
+        branches = (self.attn2_0, self.attn2_1, self.attn2_2)
+        srcs = [a.to_q.weight for a in branches] + [self.norm2.weight, self.norm2.bias]
+
+        def build():
+            w, colsum, bias = ln_fold(torch.cat([a.to_q.weight for a in branches], dim=0), None, self.norm2.weight,
+                                      self.norm2.bias, eng)
+            return dict(w=w, colsum=colsum, bias=bias)
+        return self._q3_pack.get(eng, srcs, build)
 
     def _fused_regions(self, eng: Engine, pk, scale):
         """W' = [Wz_0 Wo_0 | Wz_1 Wo_1 | Wz_2 Wo_2 | Wz_0 bo_0, Wz_1 bo_1, Wz_2 bo_2, 0 x 5]  (C, 3C + 8) and
@@ -264,13 +347,16 @@ class AudioTemporalBasicTransformerBlock(nn.Module):
         heads = self.attn1.heads
         x = tok.view(rows, C)
         p1 = self.attn1.packed(eng)
-        n1 = self.norm1.run(eng, x)
-        qkv = eng.gemm(n1, p1["qkv"]).view(N, T, 3 * C)
+        qkv = ln_qkv(eng, x, self.norm1, self.attn1).view(N, T, 3 * C)
         a = eng.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads)
         x = eng.gemm(a.view(rows, C), p1["o"], bias=p1["bo"], residual=x)
         pk = self._packed(eng)
-        n2 = self.norm2.run(eng, x)
-        q3 = eng.gemm(n2, pk["q3"]).view(N, T, 3 * C)
+        if eng.ln_fused:
+            f = self._q3_ln(eng)
+            q3 = eng.gemm(x, f["w"], bias=f["bias"], rowstats=eng.row_stats(x, self.norm2.eps), colsum=f["colsum"]).view(N, T, 3 * C)
+        else:
+            n2 = self.norm2.run(eng, x)
+            q3 = eng.gemm(n2, pk["q3"]).view(N, T, 3 * C)
         M = audio_rows.shape[0] // N
         if self.fuse_regions and eng.audio_attention_supported(M, C // heads):
             # One kernel for the three audio cross-attentions with the mask gate and motion_scale in its epilogue, then
@@ -279,8 +365,7 @@ class AudioTemporalBasicTransformerBlock(nn.Module):
             kv6 = eng.gemm(audio_rows, pk["kv6"])
             gated = eng.audio_attention(q3.view(rows, 3 * C), kv6, masks, scale, N, T, heads)
             x = eng.gemm(gated, fz["w"], bias=fz["bias"], residual=x)
-            n3 = self.norm3.run(eng, x)
-            return self.ff.run(eng, n3, x).view(N, T, C)
+            return self.ff.run(eng, x, x, ln=self.norm3).view(N, T, C)
         kv6 = eng.gemm(audio_rows, pk["kv6"]).view(N, M, 6 * C)
         acc = x
         for r in range(3):
@@ -289,8 +374,7 @@ class AudioTemporalBasicTransformerBlock(nn.Module):
             y = eng.gemm(o.view(rows, C), pk["o"][r], bias=pk["bo"][r], rowscale=masks[r])
             acc = eng.gemm(y, pk["z"][r], bias=pk["bz"][r], alpha=float(scale[r]), residual=acc)
         x = acc
-        n3 = self.norm3.run(eng, x)
-        return self.ff.run(eng, n3, x).view(N, T, C)
+        return self.ff.run(eng, x, x, ln=self.norm3).view(N, T, C)
 
 
 def zero_module(module):

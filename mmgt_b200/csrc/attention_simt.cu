@@ -359,6 +359,7 @@ extern "C" int mmgt_attention(mmgt_ctx* ctx, const mmgt_attention_params* p, voi
                  MMGT_E_INVALID, "attention: bad args");
   MMGT_CHECK_ARG(!p->k2 || (p->v2 && p->Lk2 > 0), MMGT_E_INVALID, "attention: second segment incomplete");
   if (ctx->use_tc && mmgt_attention_tc_supported(ctx, p)) return mmgt_attention_tc(ctx, p, st);
+  if (p->dtype == MMGT_BF16) MMGT_SIMT_FALLBACK(ctx, "attention");
   MMGT_CHECK_ARG(p->d % 4 == 0 && p->d <= 160, MMGT_E_UNSUPPORTED, "attention: head dim %d (need multiple of 4, <= 160)", p->d);
   const int ev = p->dtype == MMGT_F32 ? 16 : 8;
   MMGT_CHECK_ARG(p->ldq % 4 == 0 && p->ldk % 4 == 0 && p->ldv % 4 == 0 && (!p->k2 || (p->ldk2 % 4 == 0 && p->ldv2 % 4 == 0)) &&
@@ -374,12 +375,7 @@ extern "C" int mmgt_attention(mmgt_ctx* ctx, const mmgt_attention_params* p, voi
   const int dpl = (p->d + 31) / 32;
 #define LAUNCH(TT, DPL)                                                                                            \
   do {                                                                                                             \
-    static bool configured = false; /* once per instantiation: keeps the call out of CUDA-graph capture */        \
-    if (!configured) {                                                                                             \
-      MMGT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<TT, DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                        ctx->max_smem_optin));                                                     \
-      configured = true;                                                                                           \
-    }                                                                                                              \
+    MMGT_CUDA_OK(mmgt_smem_optin(ctx, attention_kernel<TT, DPL>, ctx->max_smem_optin));          \
     MMGT_CUDA_OK(mmgt_launch(ctx, attention_kernel<TT, DPL>, grid, dim3(AWARPS * 32), smem, st, *p));            \
   } while (0)
   MMGT_DISPATCH_DTYPE(p->dtype, T_, {
@@ -409,12 +405,7 @@ extern "C" int mmgt_temporal_attention(mmgt_ctx* ctx, const void* qkv, void* out
     const float sl2 = scale * 1.4426950408889634f;
 #define TLAUNCH(DK_)                                                                                                   \
   do {                                                                                                                 \
-    static bool configured = false;                                                                                    \
-    if (!configured) {                                                                                                 \
-      MMGT_CUDA_OK(cudaFuncSetAttribute(temporal_attention_mma_kernel<DK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        ctx->max_smem_optin));                                                         \
-      configured = true;                                                                                               \
-    }                                                                                                                  \
+    MMGT_CUDA_OK(mmgt_smem_optin(ctx, temporal_attention_mma_kernel<DK_>, ctx->max_smem_optin));          \
     MMGT_CUDA_OK(mmgt_launch(ctx, temporal_attention_mma_kernel<DK_>, dim3(blocks), dim3(TMW * 32), smem, st,         \
                              (const bf16*)qkv, (bf16*)out, B, F, T, heads, d, sl2));                                   \
   } while (0)
@@ -434,18 +425,14 @@ extern "C" int mmgt_temporal_attention(mmgt_ctx* ctx, const void* qkv, void* out
     MMGT_LAUNCH_OK(ctx);
     return 0;
   }
+  if (dtype == MMGT_BF16) MMGT_SIMT_FALLBACK(ctx, "temporal_attention");
   const int S = padded_stride(d);
   const size_t smem = sizeof(float) * (size_t)TW * 3 * F * S;
   MMGT_CHECK_ARG((int)smem <= ctx->max_smem_optin, MMGT_E_UNSUPPORTED, "temporal_attention: smem %zu too large", smem);
   const int64_t total = (int64_t)B * T * heads;
   int blocks = (int)std::min<int64_t>((total + TW - 1) / TW, (int64_t)ctx->num_sms * 32);
   MMGT_DISPATCH_DTYPE(dtype, T_, {
-    static bool configured = false;
-    if (!configured) {
-      MMGT_CUDA_OK(cudaFuncSetAttribute(temporal_attention_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        ctx->max_smem_optin));
-      configured = true;
-    }
+    MMGT_CUDA_OK(mmgt_smem_optin(ctx, temporal_attention_kernel<T_>, ctx->max_smem_optin));
     temporal_attention_kernel<T_><<<blocks, TW * 32, smem, st>>>((const T_*)qkv, (T_*)out, B, F, T, heads, d, scale);
   });
   MMGT_LAUNCH_OK(ctx);

@@ -557,11 +557,7 @@ int launch_attn(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaS
   constexpr bool p_tmem = (2 * BN + 2 * 64 * DCH + BN) <= 512;
   constexpr int smem = BQ * 64 * DCH * 2 + (k_stages(DCH) + v_stages(DCH)) * BN * 64 * DCH * 2 + (p_tmem ? 0 : 2 * BQ * BN * 2) + BQ * 8 + 1024 + 256;
   static_assert(smem <= 232448, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    MMGT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<DCH, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  MMGT_CUDA_OK(mmgt_smem_optin(ctx, attention_tc_kernel<DCH, BN>, smem));
   dim3 grid((a.Lq + BQ - 1) / BQ, a.heads, a.N);
   MMGT_CUDA_OK(mmgt_launch(ctx, attention_tc_kernel<DCH, BN>, grid, dim3(NUM_THREADS), smem, st, maps[0], maps[1], maps[2], maps[3],
                            maps[4], a));

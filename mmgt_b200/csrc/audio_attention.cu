@@ -226,12 +226,7 @@ extern "C" int mmgt_audio_attention(mmgt_ctx* ctx, const mmgt_audio_attention_pa
   dim3 grid((p->T + ROWS_PER_CTA - 1) / ROWS_PER_CTA, 3, p->N);
 #define ALAUNCH(DK_)                                                                                                  \
   do {                                                                                                                \
-    static bool configured = false;                                                                                   \
-    if (!configured) {                                                                                                \
-      MMGT_CUDA_OK(cudaFuncSetAttribute(audio_attention_mma_kernel<DK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        ctx->max_smem_optin));                                                        \
-      configured = true;                                                                                              \
-    }                                                                                                                 \
+    MMGT_CUDA_OK(mmgt_smem_optin(ctx, audio_attention_mma_kernel<DK_>, ctx->max_smem_optin));          \
     MMGT_CUDA_OK(mmgt_launch(ctx, audio_attention_mma_kernel<DK_>, grid, dim3(AW * 32), smem, st, a));                \
   } while (0)
   switch (DK) {

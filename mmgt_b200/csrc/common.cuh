@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <unordered_set>
+
 #include "../../include/mmgt_b200.h"
 
 struct mmgt_ctx {
@@ -16,7 +18,36 @@ struct mmgt_ctx {
   int use_pdl;                // launch with programmatic stream serialization (kernel prologues overlap the previous tail)
   long long launches;         // kernels launched through this context
   void* encode_tiled;         // PFN of cuTensorMapEncodeTiled (resolved lazily through the runtime)
+  int strict_tc;              // bf16 requests that no tensor-core kernel covers fail (MMGT_E_UNSUPPORTED) instead of
+                              // running on the CUDA-core kernels
+  int conv_implicit_all;      // stride-2 / upsampling convolutions as implicit GEMMs too (default); 0 = im2col staging (A/B)
+  int gn_split;               // GroupNorm as statistics kernel + normalise kernel (default) instead of the fused spin-barrier kernel
+  int geglu_exact;            // tensor-core GEGLU epilogue uses the erf (Abramowitz-Stegun) form instead of the logistic fit
+  long long simt_launches;    // bf16 operator calls that DID take a CUDA-core kernel while tensor cores were enabled
+  std::unordered_set<const void*> smem_optin_done;   // kernels whose dynamic-smem limit was raised on THIS device
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember it per context, not per process.
+template <typename K>
+inline cudaError_t mmgt_smem_optin(mmgt_ctx* ctx, K* kernel, int bytes) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  if (ctx->smem_optin_done.count(key)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) ctx->smem_optin_done.insert(key);
+  return e;
+}
+
+// A bf16 request is about to run on a CUDA-core kernel although tensor cores are enabled: count it, refuse it in strict mode.
+#define MMGT_SIMT_FALLBACK(ctx, what)                                                                         \
+  do {                                                                                                        \
+    if ((ctx)->use_tc) {                                                                                      \
+      if ((ctx)->strict_tc) {                                                                                 \
+        mmgt_set_error("%s: no tensor-core kernel covers this bf16 request (strict mode, mmgt_ctx_flag 4)", what); \
+        return MMGT_E_UNSUPPORTED;                                                                            \
+      }                                                                                                       \
+      (ctx)->simt_launches++;                                                                                 \
+    }                                                                                                         \
+  } while (0)
 
 void mmgt_set_error(const char* fmt, ...);
 

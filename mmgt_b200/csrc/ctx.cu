@@ -14,7 +14,7 @@ void mmgt_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* mmgt_last_error(void) { return g_err; }
-extern "C" int mmgt_abi_version(void) { return 2; }
+extern "C" int mmgt_abi_version(void) { return 3; }
 
 extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
   MMGT_CHECK_ARG(out != nullptr, MMGT_E_INVALID, "mmgt_ctx_create: out is NULL");
@@ -32,6 +32,11 @@ extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
   c->use_pdl = 0;
   c->launches = 0;
   c->encode_tiled = nullptr;
+  c->strict_tc = 0;
+  c->simt_launches = 0;
+  c->geglu_exact = 0;
+  c->gn_split = 1;
+  c->conv_implicit_all = 1;
   *out = c;
   return 0;
 }
@@ -55,6 +60,23 @@ extern "C" int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value) {
   if (flag == 3) {
     if (value >= 0) ctx->use_pdl = value ? 1 : 0;
     return ctx->use_pdl;
+  }
+  if (flag == 4) {
+    if (value >= 0) ctx->strict_tc = value ? 1 : 0;
+    return ctx->strict_tc;
+  }
+  if (flag == 5) return ctx->simt_launches;
+  if (flag == 8) {
+    if (value >= 0) ctx->conv_implicit_all = value ? 1 : 0;
+    return ctx->conv_implicit_all;
+  }
+  if (flag == 7) {
+    if (value >= 0) ctx->gn_split = value ? 1 : 0;
+    return ctx->gn_split;
+  }
+  if (flag == 6) {
+    if (value >= 0) ctx->geglu_exact = value ? 1 : 0;
+    return ctx->geglu_exact;
   }
   return MMGT_E_INVALID;
 }

@@ -185,6 +185,30 @@ extern "C" int mmgt_gather_rows(mmgt_ctx* ctx, const void* src, const int32_t* i
   return 0;
 }
 
+// ---------------------------------------------------------------- channel padding (conv_in: 4 latent channels -> 64)
+// dst[r, :C] = src[r, :], dst[r, C:Cpad] = 0: gives the first convolution a K the tensor-core implicit GEMM takes.
+template <typename T>
+__global__ void pad_channels_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t rows, int C, int Cpad) {
+  const size_t total = (size_t)rows * Cpad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / Cpad;
+    const int c = (int)(i - r * Cpad);
+    dst[i] = c < C ? src[r * C + c] : from_f32<T>(0.f);
+  }
+}
+extern "C" int mmgt_pad_channels(mmgt_ctx* ctx, const void* src, void* dst, int64_t rows, int C, int Cpad, int dtype,
+                                 void* stream) {
+  MMGT_CHECK_ARG(ctx && src && dst && rows > 0 && C > 0 && Cpad >= C, MMGT_E_INVALID, "pad_channels: bad args");
+  const size_t total = (size_t)rows * Cpad;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->num_sms * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MMGT_F32) pad_channels_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, (float*)dst, rows, C, Cpad);
+  else if (dtype == MMGT_BF16) pad_channels_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)src, (bf16*)dst, rows, C, Cpad);
+  else { mmgt_set_error("pad_channels: bad dtype %d", dtype); return MMGT_E_INVALID; }
+  MMGT_LAUNCH_OK(ctx);
+  return 0;
+}
+
 // ---------------------------------------------------------------- small float32 pieces
 __global__ void silu_f32_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {

@@ -19,7 +19,18 @@ struct Epi {
   int64_t ldr;
   int rows_per_group;
   float alpha;
+  int64_t ld_rowbias;      // 0 = N_out
+  int rowbias_mod;
+  const float* rowstats;   // fused LayerNorm: (M,2) [mean, rstd]
+  const float* colsum;
+  int act;
 };
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return silu_f(v);
+  if (act == 2) return fmaxf(v, 0.f);
+  return v;
+}
 
 template <typename T>
 __device__ __forceinline__ void load4(const T* p, bool vec_ok, int valid, float (&o)[4]) {
@@ -129,7 +140,10 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ Wt, TD* __restri
     const int m = m0 + ty * 4 + i;
     if (m >= M) continue;
     const float rs = ep.rowscale ? ep.rowscale[m] : 1.f;
-    const int grp = ep.rowbias ? m / ep.rows_per_group : 0;
+    int grp = ep.rowbias ? m / ep.rows_per_group : 0;
+    if (ep.rowbias_mod > 0) grp %= ep.rowbias_mod;
+    const int64_t ldrb = ep.ld_rowbias ? ep.ld_rowbias : N_out;
+    const float mean = ep.rowstats ? ep.rowstats[2 * (int64_t)m] : 0.f, rstd = ep.rowstats ? ep.rowstats[2 * (int64_t)m + 1] : 1.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
@@ -137,14 +151,22 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ Wt, TD* __restri
       float v;
       if (GEGLU) {
         const int64_t wv = (int64_t)(n / gb) * 2 * gb + n % gb;
-        float val = acc[i][j] + (ep.bias ? ep.bias[wv] : 0.f);
-        float gate = accg[i][j] + (ep.bias ? ep.bias[wv + gb] : 0.f);
+        float val = acc[i][j], gate = accg[i][j];
+        if (ep.rowstats) {
+          val = rstd * (val - mean * ep.colsum[wv]);
+          gate = rstd * (gate - mean * ep.colsum[wv + gb]);
+        }
+        val += ep.bias ? ep.bias[wv] : 0.f;
+        gate += ep.bias ? ep.bias[wv + gb] : 0.f;
         v = val * gelu_erf_f(gate);
       } else {
-        v = acc[i][j] + (ep.bias ? ep.bias[n] : 0.f);
+        v = acc[i][j];
+        if (ep.rowstats) v = rstd * (v - mean * ep.colsum[n]);
+        v += ep.bias ? ep.bias[n] : 0.f;
       }
       v *= rs * ep.alpha;
-      if (ep.rowbias) v += ep.rowbias[(int64_t)grp * N_out + n];
+      if (ep.rowbias) v += ep.rowbias[grp * ldrb + n];
+      v = apply_act(v, ep.act);
       if (res) v += to_f32(res[(int64_t)m * ep.ldr + n]);
       D[(int64_t)m * ldd + n] = from_f32<TD>(v);
     }
@@ -217,10 +239,16 @@ extern "C" int mmgt_gemm(mmgt_ctx* ctx, const mmgt_gemm_params* p, void* stream)
                    "gemm: N=%d not a multiple of 2*geglu_block=%d", p->N, 2 * p->geglu_block);
   }
   MMGT_CHECK_ARG(p->exchange || p->ldd >= (p->geglu_block ? p->N / 2 : p->N), MMGT_E_INVALID, "gemm: ldd too small");
+  MMGT_CHECK_ARG(!p->rowstats || p->colsum, MMGT_E_INVALID, "gemm: rowstats (fused LayerNorm) needs colsum");
+  MMGT_CHECK_ARG(p->act >= 0 && p->act <= 2, MMGT_E_INVALID, "gemm: act must be 0 (none), 1 (SiLU) or 2 (ReLU)");
   if (p->dtype == MMGT_BF16 && !p->out_f32 && ctx->use_tc && mmgt_gemm_tc_supported(ctx, p)) return mmgt_gemm_tc(ctx, p, st);
+  // batch-sized vectors (time embedding, CLIP: M <= GEMV_MAX_M rows) run on CUDA cores by design; anything larger in
+  // bf16 is a shape the tensor-core kernels do not cover
+  if (p->dtype == MMGT_BF16 && !p->out_f32 && p->M > GEMV_MAX_M) MMGT_SIMT_FALLBACK(ctx, "gemm");
   MMGT_CHECK_ARG(!p->exchange, MMGT_E_UNSUPPORTED,
                  "gemm: the fused row exchange needs the bf16 tensor-core path (use mmgt_row_exchange_copy otherwise)");
   if (p->dtype == MMGT_F32 && p->M <= GEMV_MAX_M && !p->geglu_block && !p->rowscale && !p->rowbias && !p->residual &&
+      !p->rowstats && !p->act &&
       p->K % 4 == 0 && p->lda % 4 == 0 && p->ldw % 4 == 0 && aligned16(p->A) && aligned16(p->W)) {
     int blocks = std::min((p->N + 7) / 8, ctx->num_sms * 8);
     gemv_f32_kernel<<<blocks, 256, 0, st>>>((const float*)p->A, (const float*)p->W, (float*)p->D, p->bias, p->M, p->N, p->K,
@@ -228,7 +256,8 @@ extern "C" int mmgt_gemm(mmgt_ctx* ctx, const mmgt_gemm_params* p, void* stream)
     MMGT_LAUNCH_OK(ctx);
     return 0;
   }
-  Epi ep{p->bias, p->rowscale, p->rowbias, p->residual, p->ldr, p->rows_per_group, p->alpha};
+  Epi ep{p->bias, p->rowscale, p->rowbias, p->residual, p->ldr, p->rows_per_group, p->alpha,
+         p->ld_rowbias, p->rowbias_mod, p->rowstats, p->colsum, p->act};
   ConvGeom cg{};
   if (p->dtype == MMGT_F32) return launch<float, float, false>(ctx, p->A, p->W, p->D, p->M, p->N, p->K, p->lda, p->ldw, p->ldd, ep, p->geglu_block, cg, st);
   if (p->dtype == MMGT_BF16) {
@@ -248,6 +277,7 @@ static int conv_out_dims(const mmgt_conv3x3_params* p, int* Ho, int* Wo) {
 
 extern "C" int64_t mmgt_conv3x3_workspace_bytes(mmgt_ctx* ctx, const mmgt_conv3x3_params* p) {
   if (!ctx || !p) return MMGT_E_INVALID;
+  if (p->dtype == MMGT_BF16 && ctx->use_tc && ctx->conv_implicit_all && mmgt_conv3x3_tc_supported(ctx, p)) return 0;
   if (p->dtype == MMGT_BF16 && ctx->use_tc && (p->stride != 1 || p->upsample2x) && p->Cin % 64 == 0 && p->Cout % 8 == 0) {
     int Ho, Wo;
     conv_out_dims(p, &Ho, &Wo);
@@ -264,11 +294,14 @@ extern "C" int mmgt_conv3x3(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, void* w
                  "conv3x3: bad args");
   MMGT_CHECK_ARG(p->stride == 1 || p->stride == 2, MMGT_E_INVALID, "conv3x3: stride must be 1 or 2");
   MMGT_CHECK_ARG(!p->rowbias || p->frames_per_group > 0, MMGT_E_INVALID, "conv3x3: rowbias needs frames_per_group");
+  MMGT_CHECK_ARG(p->act >= 0 && p->act <= 2, MMGT_E_INVALID, "conv3x3: act must be 0 (none), 1 (SiLU) or 2 (ReLU)");
   int Ho, Wo;
   conv_out_dims(p, &Ho, &Wo);
   const int M = p->N * Ho * Wo, K = 9 * p->Cin;
   if (p->dtype == MMGT_BF16 && ctx->use_tc) {
-    if (p->stride == 1 && !p->upsample2x && mmgt_conv3x3_tc_supported(ctx, p)) return mmgt_conv3x3_tc(ctx, p, st);
+    if (ctx->conv_implicit_all ? mmgt_conv3x3_tc_supported(ctx, p)
+                               : (p->stride == 1 && !p->upsample2x && mmgt_conv3x3_tc_supported(ctx, p)))
+      return mmgt_conv3x3_tc(ctx, p, st);
     const int64_t need = mmgt_conv3x3_workspace_bytes(ctx, p);
     if (need > 0) {
       // stride-2 / upsampling convs: stage an im2col matrix, then the tensor-core GEMM with the same epilogue
@@ -276,6 +309,7 @@ extern "C" int mmgt_conv3x3(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, void* w
       g.A = workspace; g.W = p->w; g.D = p->y; g.bias = p->bias; g.rowbias = p->rowbias; g.residual = p->residual;
       g.lda = K; g.ldw = K; g.ldd = p->Cout; g.ldr = p->Cout; g.M = M; g.N = p->Cout; g.K = K;
       g.rows_per_group = p->frames_per_group * Ho * Wo; g.alpha = 1.f; g.dtype = MMGT_BF16;
+      g.ld_rowbias = p->ld_rowbias; g.act = p->act;
       if (mmgt_gemm_tc_supported(ctx, &g)) {
         MMGT_CHECK_ARG(workspace && workspace_bytes >= need, MMGT_E_INVALID, "conv3x3: workspace too small (%lld < %lld)",
                        (long long)workspace_bytes, (long long)need);
@@ -286,7 +320,9 @@ extern "C" int mmgt_conv3x3(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, void* w
     }
   }
   MMGT_CHECK_ARG(p->Cin % 4 == 0, MMGT_E_UNSUPPORTED, "conv3x3: Cin must be a multiple of 4");
-  Epi ep{p->bias, nullptr, p->rowbias, p->residual, p->Cout, p->frames_per_group * Ho * Wo, 1.f};
+  if (p->dtype == MMGT_BF16) MMGT_SIMT_FALLBACK(ctx, "conv3x3");
+  Epi ep{p->bias, nullptr, p->rowbias, p->residual, p->Cout, p->frames_per_group * Ho * Wo, 1.f,
+         p->ld_rowbias, 0, nullptr, nullptr, p->act};
   ConvGeom cg{p->H, p->W, p->Cin, p->stride, p->upsample2x, Ho, Wo};
   if (p->dtype == MMGT_F32) return launch<float, float, true>(ctx, p->x, p->w, p->y, M, p->Cout, K, 0, K, p->Cout, ep, 0, cg, st);
   if (p->dtype == MMGT_BF16) return launch<bf16, bf16, true>(ctx, p->x, p->w, p->y, M, p->Cout, K, 0, K, p->Cout, ep, 0, cg, st);

@@ -38,8 +38,18 @@ struct TcArgs {
   int64_t ldd, ldr;
   int rows_per_group;
   float alpha;
-  // conv geometry (CONV only)
+  int64_t ld_rowbias;       // elements between rowbias rows
+  int rowbias_mod;          // > 0: rowbias row = (m / rows_per_group) % rowbias_mod
+  const float* rowstats;    // fused LayerNorm: (M, 2) [mean, rstd]; D = rstd * (acc - mean * colsum[n]) + bias[n]
+  const float* colsum;
+  int act;                  // 0 none, 1 SiLU, 2 ReLU
+  // conv geometry (CONV only).  H, W span the TILE space: the output image for conv_mode 0 (3x3, stride 1: same as the
+  // input) and 1 (stride 2: A boxes are fetched with a TMA traversal stride of 2 from coordinate 2*o + tap - 1); the
+  // INPUT image for conv_mode 2 (nearest x2 upsample + 3x3 = four 2x2-tap convolutions on the low-resolution input with
+  // pre-summed weights, one per output parity (a, b); tile index = 4 * input tile + parity, K = 4 taps x Cin, output row
+  // (n, 2h + a, 2w + b)).
   int H, W, cin_blocks;
+  int conv_mode;
   // CONV, patch tiles: when no run of 128 consecutive (n, h, w) rows is a TMA box (W = 96, 48, 24, 12: the 768^2 / 384^2
   // latents of config 5) an M tile is a (pf frames) x (ph rows) x (pw columns) patch, pw * ph * pf = 128.  pw == 0:
   // tiles are 128 consecutive rows.
@@ -214,6 +224,32 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return 0.5f * x * cdf2;
 }
 
+// GEGLU epilogue of the bf16 tier: x * Phi(x) with Phi(x) = 1 / (1 + exp(-x (c1 + c3 z + c5 z^2))), z = min(x^2, 42):
+// an odd polynomial fit of logit(Phi) (least squares on the relative error of x Phi(x) over |x| <= 12).  |error| <=
+// 6.3e-5 absolute and <= 8.2e-4 relative (0.4 bf16 half-ulps) against the erf form, correct tails (Phi -> 0 / 1 with
+// relative accuracy), 2 MUFU + 8 FP32 operations per element instead of 2 + ~17: at C = 320 the GEGLU GEMM is paced by
+// the issue slots of its epilogue (128 x 128 outputs per tile against 5 k-blocks of MMA), not by the tensor pipe.
+// Coefficients are pre-multiplied by -log2(e).  gelu_erf_fast() above stays for reference / A-B (MMGT_GEGLU_EXACT).
+__device__ __forceinline__ float gelu_logistic(float x) {
+  const float z = fminf(x * x, 42.f);
+  float p = fmaf(0.0011339103803038597f, z, -0.10764378309249878f);
+  p = fmaf(p, z, -2.300089120864868f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return x * r;
+}
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == 1) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return v * r;
+  }
+  if (act == 2) return fmaxf(v, 0.f);
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------- kernel
 // BRES ("weight-stationary"): for small K the whole (BN x K) weight tile of this CTA stays resident in shared
 // memory, every CTA keeps one n-block for its lifetime and only A tiles stream through the ring.  The
@@ -289,16 +325,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < args.num_k_blocks; ++kb) tma_load_2d(smem_b + kb * B_STAGE_BYTES, &tmB, b_full, kb * BK, n_blk * BN);
     }
     for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
-      int cn = 0, ch = 0, cw = 0;
+      int cn = 0, ch = 0, cw = 0, par = 0;
       if (CONV) {
+        int mb = m_blk;
+        if (args.conv_mode == 2) { par = mb & 3; mb >>= 2; }
         if (args.pw) {
           const int tiles_w = args.W / args.pw, per_group = tiles_w * (args.H / args.ph);
-          const int ng = m_blk / per_group, r = m_blk - ng * per_group;
+          const int ng = mb / per_group, r = mb - ng * per_group;
           cn = ng * args.pf;
           ch = (r / tiles_w) * args.ph;
           cw = (r - (r / tiles_w) * tiles_w) * args.pw;
         } else {
-          const int m0 = m_blk * BM, hw = args.H * args.W;
+          const int m0 = mb * BM, hw = args.H * args.W;
           cn = m0 / hw;
           const int rem = m0 - cn * hw;
           ch = rem / args.W;
@@ -311,11 +349,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
         if (CONV) {
           const int tap = kb / args.cin_blocks, cb = kb - tap * args.cin_blocks;
-          tma_load_4d(sa, &tmA, &full_bar[stage], cb * BK, cw + tap % 3 - 1, ch + tap / 3 - 1, cn);
+          int x, y;
+          if (args.conv_mode == 0) { x = cw + tap % 3 - 1; y = ch + tap / 3 - 1; }
+          else if (args.conv_mode == 1) { x = 2 * cw + tap % 3 - 1; y = 2 * ch + tap / 3 - 1; }
+          else { x = cw + (tap & 1) - ((par & 1) ? 0 : 1); y = ch + (tap >> 1) - ((par & 2) ? 0 : 1); }
+          tma_load_4d(sa, &tmA, &full_bar[stage], cb * BK, x, y, cn);
         } else {
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
         }
-        if (!BRES) tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+        if (!BRES) tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], (par * args.num_k_blocks + kb) * BK, n_blk * BN);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -370,15 +412,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int m_blk, n_blk;
     // output row of this thread in M tile mb (>= M: none).  Patch tiles (CONV, args.pw != 0) are not consecutive rows.
     auto row_of = [&](int mb) -> int {
-      if (CONV && args.pw) {
-        const int tiles_w = args.W / args.pw, per_group = tiles_w * (args.H / args.ph);
-        const int ng = mb / per_group, r = mb - ng * per_group;
-        const int per_frame = args.pw * args.ph;
-        const int dn = row_in_tile / per_frame, rr = row_in_tile - dn * per_frame;
-        const int dh = rr / args.pw, dw = rr - dh * args.pw;
-        const int fr = ng * args.pf + dn;
+      int par = 0;
+      if (CONV && args.conv_mode == 2) { par = mb & 3; mb >>= 2; }
+      if (CONV && (args.pw || args.conv_mode == 2)) {
+        int fr, hh, ww;
+        if (args.pw) {
+          const int tiles_w = args.W / args.pw, per_group = tiles_w * (args.H / args.ph);
+          const int ng = mb / per_group, r = mb - ng * per_group;
+          const int per_frame = args.pw * args.ph;
+          const int dn = row_in_tile / per_frame, rr = row_in_tile - dn * per_frame;
+          const int dh = rr / args.pw, dw = rr - dh * args.pw;
+          fr = ng * args.pf + dn;
+          hh = (r / tiles_w) * args.ph + dh;
+          ww = (r - (r / tiles_w) * tiles_w) * args.pw + dw;
+        } else {
+          const int r = mb * BM + row_in_tile, hw = args.H * args.W;
+          fr = r / hw;
+          const int rem = r - fr * hw;
+          hh = rem / args.W;
+          ww = rem - hh * args.W;
+        }
         if (fr >= args.n_frames) return args.M;
-        return (fr * args.H + (r / tiles_w) * args.ph + dh) * args.W + (r - (r / tiles_w) * tiles_w) * args.pw + dw;
+        if (args.conv_mode == 2) return (fr * 2 * args.H + 2 * hh + (par >> 1)) * 2 * args.W + 2 * ww + (par & 1);
+        return (fr * args.H + hh) * args.W + ww;
       }
       return mb * BM + row_in_tile;
     };
@@ -404,7 +460,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bf16* drow = args.D + (int64_t)m * args.ldd;
       if (args.ex.direction != 0 && m_ok) drow = exchange_row_ptr<bf16>(args.ex, m);
       const float rs = (args.rowscale && m_ok ? args.rowscale[m] : 1.f) * args.alpha;
-      const float* rb = (args.rowbias && m_ok) ? args.rowbias + (int64_t)(m / args.rows_per_group) * args.N_out : nullptr;
+      const float* rb = nullptr;
+      if (args.rowbias && m_ok) {
+        int grp = m / args.rows_per_group;
+        if (args.rowbias_mod > 0) grp %= args.rowbias_mod;
+        rb = args.rowbias + (int64_t)grp * args.ld_rowbias;
+      }
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (args.rowstats && m_ok) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(args.rowstats) + m);
+        ln_mean = st.x; ln_rstd = st.y;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(lane_grp * 32) << 16);
@@ -424,16 +490,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               load16_f32(args.bias + n_blk * BN + 2 * c + 16, bg);
             }
             tmem_ld_wait();
+            if (args.rowstats) {          // fused LayerNorm (warp-uniform branch)
+              float sv[16], sg[16];
+              load16_f32(args.colsum + n_blk * BN + 2 * c, sv);
+              load16_f32(args.colsum + n_blk * BN + 2 * c + 16, sg);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                r[e] = __float_as_uint(ln_rstd * fmaf(-ln_mean, sv[e], __uint_as_float(r[e])));
+                g[e] = __float_as_uint(ln_rstd * fmaf(-ln_mean, sg[e], __uint_as_float(g[e])));
+              }
+            }
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               float val = __uint_as_float(r[e]), gate = __uint_as_float(g[e]);
               if (args.bias) { val += bv[e]; gate += bg[e]; }
-              v[e] = val * gelu_erf_fast(gate);
+              v[e] = val * (args.act == 3 ? gelu_erf_fast(gate) : gelu_logistic(gate));
             }
           } else {
             float bv[16];
             if (args.bias) load16_f32(args.bias + n_out0 + c, bv);
             tmem_ld_wait();
+            if (args.rowstats) {
+              float sv[16];
+              load16_f32(args.colsum + n_out0 + c, sv);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(ln_rstd * fmaf(-ln_mean, sv[e], __uint_as_float(r[e])));
+            }
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               v[e] = __uint_as_float(r[e]);
@@ -448,6 +530,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               load16_f32(rb + n_out0 + c, rv);
 #pragma unroll
               for (int e = 0; e < 16; ++e) v[e] += rv[e];
+            }
+            if (!GEGLU && args.act) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = act_apply(v[e], args.act);
             }
             if (has_res) {
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&resv[i].w[0]);
@@ -497,11 +583,13 @@ int resolve_encode(mmgt_ctx* ctx, EncodeTiledFn* fn) {
 }
 
 int make_map(mmgt_ctx* ctx, CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-             const uint32_t* box) {
+             const uint32_t* box, const uint32_t* elem_strides = nullptr) {
   EncodeTiledFn fn;
   int rc = resolve_encode(ctx, &fn);
   if (rc) return rc;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides)
+    for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -538,11 +626,7 @@ template <int BN, bool CONV, bool GEGLU>
 int launch_tc(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
   constexpr int STAGES = num_stages(BN);
   constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
-    MMGT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, GEGLU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  MMGT_CUDA_OK(mmgt_smem_optin(ctx, gemm_tc_kernel<BN, CONV, GEGLU, false>, smem));
   const int tiles = a.num_m_tiles * a.num_n_tiles;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   MMGT_CUDA_OK(mmgt_launch(ctx, gemm_tc_kernel<BN, CONV, GEGLU, false>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, a));
@@ -600,12 +684,7 @@ bool plan_bres(int M, int N, int K, bool geglu, int num_sms, BresPlan* out) {
 
 template <int BN, bool GEGLU>
 int launch_bres(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    MMGT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, false, GEGLU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      SMEM_OPTIN));
-    configured = true;
-  }
+  MMGT_CUDA_OK(mmgt_smem_optin(ctx, gemm_tc_kernel<BN, false, GEGLU, true>, SMEM_OPTIN));
   const int smem = BRES_OVERHEAD + a.num_k_blocks * BN * BK * 2 + a.stages * A_STAGE_BYTES;
   MMGT_CUDA_OK(mmgt_launch(ctx, gemm_tc_kernel<BN, false, GEGLU, true>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, a));
   MMGT_LAUNCH_OK(ctx);
@@ -650,6 +729,9 @@ bool mmgt_gemm_tc_supported(const mmgt_ctx* ctx, const mmgt_gemm_params* p) {
   if (n_out % 16) return false;
   if (p->residual && (!aligned16(p->residual) || p->ldr % 8)) return false;
   if ((p->bias && !aligned16(p->bias)) || (p->rowbias && !aligned16(p->rowbias))) return false;   // float4 epilogue loads
+  if (p->rowbias && p->ld_rowbias % 4) return false;
+  if (p->rowstats && (!aligned16(p->colsum) || (reinterpret_cast<uintptr_t>(p->rowstats) & 7u))) return false;
+  if (p->geglu_block && p->act) return false;
   if (p->M < 1) return false;
   return true;
 }
@@ -682,6 +764,9 @@ int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
   a.bias = p->bias; a.rowscale = p->rowscale; a.rowbias = p->rowbias;
   a.residual = (const bf16*)p->residual; a.D = (bf16*)p->D;
   a.ldd = p->ldd; a.ldr = p->ldr; a.rows_per_group = p->rows_per_group > 0 ? p->rows_per_group : 1; a.alpha = p->alpha;
+  a.ld_rowbias = p->ld_rowbias ? p->ld_rowbias : a.N_out; a.rowbias_mod = p->rowbias_mod;
+  a.rowstats = p->rowstats; a.colsum = p->colsum;
+  a.act = p->geglu_block ? (ctx->geglu_exact ? 3 : 0) : p->act;
   a.wide_io = aligned32(p->D) && p->ldd % 16 == 0 && (!p->residual || (aligned32(p->residual) && p->ldr % 16 == 0));
   if (p->exchange) {
     int rc = mmgt_row_exchange_check(p->exchange, p->M, "gemm");
@@ -698,8 +783,7 @@ int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
   return dispatch_tc<false>(ctx, bn, p->geglu_block != 0, tmA, tmB, a, st);
 }
 
-static bool conv_box(const mmgt_conv3x3_params* p, uint32_t* bw, uint32_t* bh, uint32_t* bn_frames) {
-  const int W = p->W, H = p->H;
+static bool conv_box(int W, int H, uint32_t* bw, uint32_t* bh, uint32_t* bn_frames) {
   if (W >= BM) {
     if (W % BM) return false;
     *bw = BM; *bh = 1; *bn_frames = 1;
@@ -719,12 +803,12 @@ static bool conv_box(const mmgt_conv3x3_params* p, uint32_t* bw, uint32_t* bh, u
 
 // Patch tile for widths that conv_box cannot cover with consecutive rows: the widest pw | W with 128 % pw == 0, then
 // the tallest ph | H with ph | 128 / pw; the rest of the 128 rows are consecutive frames.
-static bool conv_patch(const mmgt_conv3x3_params* p, uint32_t* pw, uint32_t* ph, uint32_t* pf) {
+static bool conv_patch(int W, int H, uint32_t* pw, uint32_t* ph, uint32_t* pf) {
   for (int w = 64; w >= 1; w >>= 1) {
-    if (p->W % w) continue;
+    if (W % w) continue;
     const int rest = BM / w;
     for (int h = rest; h >= 1; h >>= 1) {
-      if (p->H % h) continue;
+      if (H % h) continue;
       if (rest / h > 256) return false;
       *pw = w; *ph = h; *pf = rest / h;
       return true;
@@ -733,55 +817,82 @@ static bool conv_patch(const mmgt_conv3x3_params* p, uint32_t* pw, uint32_t* ph,
   return false;
 }
 
+// conv_mode: 0 = 3x3 stride 1, 1 = 3x3 stride 2 (TMA traversal stride), 2 = nearest x2 upsample + 3x3 as four 2x2-tap
+// sub-pixel convolutions (needs p->w_subpixel).  Tile space: output image for 0 / 1, input image for 2.
+static int conv_mode_of(const mmgt_conv3x3_params* p) { return p->upsample2x ? 2 : (p->stride == 2 ? 1 : 0); }
+static void conv_tile_space(const mmgt_conv3x3_params* p, int* Ht, int* Wt) {
+  if (p->stride == 2 && !p->upsample2x) { *Ht = p->H / 2; *Wt = p->W / 2; }
+  else { *Ht = p->H; *Wt = p->W; }
+}
+
 bool mmgt_conv3x3_tc_supported(const mmgt_ctx* ctx, const mmgt_conv3x3_params* p) {
   (void)ctx;
-  if (p->dtype != MMGT_BF16 || p->stride != 1 || p->upsample2x) return false;
+  if (p->dtype != MMGT_BF16) return false;
+  if (p->upsample2x && (p->stride != 1 || !p->w_subpixel || !aligned16(p->w_subpixel))) return false;
+  if (p->stride == 2 && ((p->H | p->W) & 1)) return false;
   if (p->Cin % BK || !pick_bn(p->Cout) || p->Cout % 16) return false;
+  int Ht, Wt;
+  conv_tile_space(p, &Ht, &Wt);
   uint32_t bw, bh, bf;
-  if (!conv_box(p, &bw, &bh, &bf) && !conv_patch(p, &bw, &bh, &bf)) return false;
+  if (!conv_box(Wt, Ht, &bw, &bh, &bf) && !conv_patch(Wt, Ht, &bw, &bh, &bf)) return false;
+  if (p->stride == 2 && (2 * bw > 256 || 2 * bh > 256)) return false;
   if (!aligned16(p->x) || !aligned16(p->w) || !aligned16(p->y) || (p->residual && !aligned16(p->residual))) return false;
   if ((p->bias && !aligned16(p->bias)) || (p->rowbias && !aligned16(p->rowbias))) return false;
+  if (p->rowbias && p->ld_rowbias % 4) return false;
   return true;
 }
 
 int mmgt_conv3x3_tc(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, cudaStream_t st) {
-  const int bn = pick_bn_for(p->Cout, p->N * p->H * p->W, ctx->num_sms);
+  const int mode = conv_mode_of(p);
+  int Ht, Wt;
+  conv_tile_space(p, &Ht, &Wt);
+  const int Ho = mode == 2 ? 2 * p->H : Ht, Wo = mode == 2 ? 2 * p->W : Wt;
+  const int bn = pick_bn_for(p->Cout, p->N * Ho * Wo, ctx->num_sms);
   uint32_t bw, bh, bf;
-  const bool patch = !conv_box(p, &bw, &bh, &bf);
-  if (patch) conv_patch(p, &bw, &bh, &bf);
+  const bool patch = !conv_box(Wt, Ht, &bw, &bh, &bf);
+  if (patch) conv_patch(Wt, Ht, &bw, &bh, &bf);
+  const int taps = mode == 2 ? 4 : 9;
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
     uint64_t str[3] = {(uint64_t)p->Cin * 2, (uint64_t)p->W * p->Cin * 2, (uint64_t)p->H * p->W * p->Cin * 2};
     uint32_t box[4] = {BK, bw, bh, bf};
-    int rc = make_map(ctx, &tmA, p->x, 4, dims, str, box);
+    uint32_t estr[4] = {1, 1, 1, 1};
+    if (mode == 1) { box[1] = 2 * bw; box[2] = 2 * bh; estr[1] = 2; estr[2] = 2; }
+    int rc = make_map(ctx, &tmA, p->x, 4, dims, str, box, estr);
     if (rc) return rc;
   }
   {
-    uint64_t dims[2] = {(uint64_t)9 * p->Cin, (uint64_t)p->Cout};
-    uint64_t str[1] = {(uint64_t)9 * p->Cin * 2};
+    const uint64_t kw = (uint64_t)(mode == 2 ? 16 : 9) * p->Cin;      // mode 2: (Cout, 4 parities, 2, 2, Cin)
+    uint64_t dims[2] = {kw, (uint64_t)p->Cout};
+    uint64_t str[1] = {kw * 2};
     uint32_t box[2] = {BK, (uint32_t)bn};
-    int rc = make_map(ctx, &tmB, p->w, 2, dims, str, box);
+    int rc = make_map(ctx, &tmB, mode == 2 ? p->w_subpixel : p->w, 2, dims, str, box);
     if (rc) return rc;
   }
   TcArgs a{};
-  a.M = p->N * p->H * p->W;
+  a.M = p->N * Ho * Wo;
   a.N_out = p->Cout;
-  a.num_m_tiles = (a.M + BM - 1) / BM;
+  const int m_tile_space = p->N * Ht * Wt;
+  a.num_m_tiles = (m_tile_space + BM - 1) / BM;
   a.n_frames = p->N;
   if (patch) {
     a.pw = (int)bw; a.ph = (int)bh; a.pf = (int)bf;
-    a.num_m_tiles = ((p->N + (int)bf - 1) / (int)bf) * (p->H / (int)bh) * (p->W / (int)bw);
+    a.num_m_tiles = ((p->N + (int)bf - 1) / (int)bf) * (Ht / (int)bh) * (Wt / (int)bw);
   }
+  if (mode == 2) a.num_m_tiles *= 4;
   a.num_n_tiles = p->Cout / bn;
   a.cin_blocks = p->Cin / BK;
-  a.num_k_blocks = 9 * a.cin_blocks;
+  a.num_k_blocks = taps * a.cin_blocks;
+  a.conv_mode = mode;
   a.bias = p->bias; a.rowscale = nullptr; a.rowbias = p->rowbias;
   a.residual = (const bf16*)p->residual; a.D = (bf16*)p->y;
   a.ldd = p->Cout; a.ldr = p->Cout;
   a.wide_io = aligned32(p->y) && p->Cout % 16 == 0 && (!p->residual || aligned32(p->residual));
-  a.rows_per_group = p->rowbias ? p->frames_per_group * p->H * p->W : 1;
+  a.rows_per_group = p->rowbias ? p->frames_per_group * Ho * Wo : 1;
+  a.ld_rowbias = p->ld_rowbias ? p->ld_rowbias : p->Cout;
+  a.act = p->act;
   a.alpha = 1.f;
-  a.H = p->H; a.W = p->W;
+  a.H = Ht; a.W = Wt;
   return dispatch_tc<true>(ctx, bn, false, tmA, tmB, a, st);
 }

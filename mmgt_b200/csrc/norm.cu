@@ -212,6 +212,170 @@ gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restric
   }
 }
 
+// ---- Two-kernel GroupNorm (default): statistics, then normalise (+SiLU).  No cross-CTA wait inside a kernel, so both
+// run at full occupancy with every CTA streaming independently; the second read of the tensor is served by the 126 MB
+// L2 (a level-0 activation is 63 MB, the deeper levels 4-31 MB).  Measured against the single fused kernel above
+// (spin barrier per frame, 35 % occupancy, 26 % of HBM peak at C = 320): profiles/r2_*.
+__device__ __forceinline__ float silu_fast(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return v * r;
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __restrict__ stats, int T_tok, int C1, int C2,
+                int groups, int tok_per_block) {
+  constexpr int VEC = VecOf<T>::N;
+  typedef typename VecOf<T>::type Raw;
+  constexpr int UNR = 8 / NV < 1 ? 1 : 8 / NV;
+  pdl_prologue();
+  extern __shared__ float sm[];   // [2][rows_per_pass][C] per-thread partial sums
+  const int C = C1 + C2, Cv = C / VEC, C1v = C1 / VEC, cpg = C / groups;
+  const int lanes = Cv < GN_THREADS ? Cv : GN_THREADS;
+  const int rows_per_pass = GN_THREADS / lanes;
+  const int lane = threadIdx.x % lanes, rip = threadIdx.x / lanes;
+  const bool active = rip < rows_per_pass;
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tok_per_block;
+  const int t1 = min(T_tok, t0 + tok_per_block);
+  const Raw zero_raw = {};
+  auto src = [&](size_t row, int cv) -> const Raw* {
+    return reinterpret_cast<const Raw*>(cv < C1v ? x1 + row * C1 + (size_t)cv * VEC : x2 + row * C2 + (size_t)(cv - C1v) * VEC);
+  };
+  if (active) {
+    float s[NV][VEC], ss[NV][VEC];
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) s[j][e] = ss[j][e] = 0.f;
+    for (int t = t0 + rip; t < t1; t += UNR * rows_per_pass) {
+      Raw raw[UNR][NV];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int tt = t + u * rows_per_pass;
+        const size_t row = (size_t)n * T_tok + tt;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int cv = lane + j * lanes;
+          raw[u][j] = (tt < t1 && cv < Cv) ? *src(row, cv) : zero_raw;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          float v[VEC];
+          unpack_vec<T>(raw[u][j], v);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) { s[j][e] += v[e]; ss[j][e] = fmaf(v[e], v[e], ss[j][e]); }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int cv = lane + j * lanes;
+      if (cv < Cv) {
+        float* d0 = sm + (size_t)rip * C + cv * VEC;
+        float* d1 = sm + (size_t)(rows_per_pass + rip) * C + cv * VEC;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { d0[e] = s[j][e]; d1[e] = ss[j][e]; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += GN_THREADS) {
+    const int g = i >> 1, which = i & 1;
+    float a = 0.f;
+    for (int r = 0; r < rows_per_pass; ++r) {
+      const float* srcp = sm + (size_t)(which * rows_per_pass + r) * C + g * cpg;
+      for (int c = 0; c < cpg; ++c) a += srcp[c];
+    }
+    atomicAdd(&stats[((size_t)n * groups + g) * 2 + which], (double)a);
+  }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restrict__ y, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const double* __restrict__ stats, int T_tok, int C1, int C2, int groups,
+                float eps, int silu, int tok_per_block) {
+  constexpr int VEC = VecOf<T>::N;
+  typedef typename VecOf<T>::type Raw;
+  constexpr int UNR = 8 / NV < 1 ? 1 : 8 / NV;
+  pdl_prologue();
+  extern __shared__ float sm[];   // scale[C], shift[C]
+  const int C = C1 + C2, Cv = C / VEC, C1v = C1 / VEC, cpg = C / groups;
+  const int lanes = Cv < GN_THREADS ? Cv : GN_THREADS;
+  const int rows_per_pass = GN_THREADS / lanes;
+  const int lane = threadIdx.x % lanes, rip = threadIdx.x / lanes;
+  const bool active = rip < rows_per_pass;
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * tok_per_block;
+  const int t1 = min(T_tok, t0 + tok_per_block);
+  const double cnt = (double)T_tok * cpg;
+  float* scale = sm;
+  float* shift = sm + C;
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    const int g = c / cpg;
+    const double mean = stats[((size_t)n * groups + g) * 2] / cnt;
+    double var = stats[((size_t)n * groups + g) * 2 + 1] / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = rstd * gamma[c];
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+  }
+  __syncthreads();
+  auto src = [&](size_t row, int cv) -> const Raw* {
+    return reinterpret_cast<const Raw*>(cv < C1v ? x1 + row * C1 + (size_t)cv * VEC : x2 + row * C2 + (size_t)(cv - C1v) * VEC);
+  };
+  if (!active) return;
+  // this thread's channels never change: keep their scale / shift in registers
+  float sc[NV][VEC], sh[NV][VEC];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int cv = lane + j * lanes;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      sc[j][e] = cv < Cv ? scale[cv * VEC + e] : 0.f;
+      sh[j][e] = cv < Cv ? shift[cv * VEC + e] : 0.f;
+    }
+  }
+  for (int t = t0 + rip; t < t1; t += UNR * rows_per_pass) {
+    Raw raw[UNR][NV];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int tt = t + u * rows_per_pass;
+      const size_t row = (size_t)n * T_tok + tt;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int cv = lane + j * lanes;
+        if (tt < t1 && cv < Cv) raw[u][j] = *src(row, cv);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int tt = t + u * rows_per_pass;
+      const size_t row = (size_t)n * T_tok + tt;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int cv = lane + j * lanes;
+        if (tt < t1 && cv < Cv) {
+          float v[VEC];
+          unpack_vec<T>(raw[u][j], v);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            v[e] = fmaf(v[e], sc[j][e], sh[j][e]);
+            if (silu) v[e] = silu_fast(v[e]);
+          }
+          store_vec<T>(y + row * C + (size_t)cv * VEC, v);
+        }
+      }
+    }
+  }
+}
+
 // one warp per row; the row lives in registers (two-pass mean / variance like torch)
 template <typename T, int MAXIT>
 __global__ void __launch_bounds__(256)
@@ -353,7 +517,107 @@ bool try_ln_grp(mmgt_ctx* ctx, const void* x, void* y, const float* gamma, const
   return false;
 }
 
+// Row statistics only: (mean, rstd) per row for a LayerNorm that is fused into the GEMM consuming it (mmgt_gemm
+// rowstats / colsum): one read of the tensor, 8 bytes written per row -- the normalised tensor is never materialised.
+// Same two-pass (mean, centred sum of squares) arithmetic and lane layout as layernorm_grp_kernel.
+template <typename T, int VPL, int G>
+__global__ void __launch_bounds__(256)
+row_stats_grp_kernel(const T* __restrict__ x, float2* __restrict__ stats, int64_t rows, int C, int64_t ld, float eps) {
+  constexpr int VEC = VecOf<T>::N;
+  pdl_prologue();
+  const int gl = threadIdx.x % G;
+  const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t ngrp = (int64_t)gridDim.x * blockDim.x / G;
+  const float inv_c = 1.f / (float)C;
+  for (int64_t row = grp; row < rows; row += ngrp) {
+    float v[VPL][VEC];
+    const T* xr = x + row * ld;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) load_vec<T>(xr + (size_t)(gl + j * G) * VEC, v[j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) sum += v[j][e];
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { const float d = v[j][e] - mean; sq += d * d; }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (gl == 0) stats[row] = make_float2(mean, rsqrtf(sq * inv_c + eps));
+  }
+}
+
+// generic widths: one warp per row
+template <typename T>
+__global__ void __launch_bounds__(256)
+row_stats_kernel(const T* __restrict__ x, float2* __restrict__ stats, int64_t rows, int C, int64_t ld, float eps) {
+  constexpr int VEC = VecOf<T>::N;
+  const int Cv = C / VEC, lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = warp; row < rows; row += nwarps) {
+    float sum = 0.f;
+    for (int cv = lane; cv < Cv; cv += 32) {
+      float v[VEC];
+      load_vec<T>(x + row * ld + (size_t)cv * VEC, v);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) sum += v[e];
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+    for (int cv = lane; cv < Cv; cv += 32) {
+      float v[VEC];
+      load_vec<T>(x + row * ld + (size_t)cv * VEC, v);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { const float d = v[e] - mean; sq += d * d; }
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) stats[row] = make_float2(mean, rsqrtf(sq / (float)C + eps));
+  }
+}
+
+template <typename T>
+int launch_row_stats(mmgt_ctx* ctx, const void* x, float* stats, int64_t rows, int C, int64_t ld, float eps, cudaStream_t st) {
+  const int Cv = C / VecOf<T>::N;
+#define RS_CASE(VPL_, G_)                                                                                              \
+  if (Cv == VPL_ * G_) {                                                                                               \
+    const int rpb = 256 / G_;                                                                                          \
+    const int64_t blocks = std::min<int64_t>((rows + rpb - 1) / rpb, (int64_t)ctx->num_sms * 16);                      \
+    MMGT_CUDA_OK(mmgt_launch(ctx, row_stats_grp_kernel<T, VPL_, G_>, dim3((int)blocks), dim3(256), 0, st, (const T*)x, \
+                             reinterpret_cast<float2*>(stats), rows, C, ld, eps));                                     \
+    return 0;                                                                                                          \
+  }
+  RS_CASE(5, 8) RS_CASE(5, 16) RS_CASE(5, 32) RS_CASE(10, 32) RS_CASE(1, 8) RS_CASE(2, 8) RS_CASE(4, 8)
+#undef RS_CASE
+  const int64_t blocks = std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->num_sms * 16);
+  row_stats_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)x, reinterpret_cast<float2*>(stats), rows, C, ld, eps);
+  return 0;
+}
+
 }  // namespace
+
+extern "C" int mmgt_row_stats(mmgt_ctx* ctx, const void* x, float* stats, int64_t rows, int C, int64_t ld, float eps,
+                              int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MMGT_CHECK_ARG(ctx && x && stats && rows > 0 && C > 0, MMGT_E_INVALID, "row_stats: bad args");
+  if (ld <= 0) ld = C;
+  const int vec = dtype == MMGT_F32 ? 4 : 8;
+  MMGT_CHECK_ARG(C % vec == 0 && ld % vec == 0 && ld >= C, MMGT_E_ALIGN, "row_stats: C and ld must be multiples of %d", vec);
+  MMGT_CHECK_ARG(aligned16(x) && (reinterpret_cast<uintptr_t>(stats) & 7u) == 0, MMGT_E_ALIGN, "row_stats: alignment");
+  int rc;
+  if (dtype == MMGT_F32) rc = launch_row_stats<float>(ctx, x, stats, rows, C, ld, eps, st);
+  else if (dtype == MMGT_BF16) rc = launch_row_stats<bf16>(ctx, x, stats, rows, C, ld, eps, st);
+  else { mmgt_set_error("row_stats: bad dtype %d", dtype); return MMGT_E_INVALID; }
+  if (rc) return rc;
+  MMGT_LAUNCH_OK(ctx);
+  return 0;
+}
 
 extern "C" int mmgt_groupnorm(mmgt_ctx* ctx, const void* x1, const void* x2, void* y, const float* gamma,
                               const float* beta, double* stats_ws, int N, int T, int C1, int C2, int groups, float eps,
@@ -374,6 +638,33 @@ extern "C" int mmgt_groupnorm(mmgt_ctx* ctx, const void* x1, const void* x2, voi
   const int lanes = std::min(Cv, GN_THREADS);
   const int rpp = GN_THREADS / lanes;
   const size_t smem = sizeof(float) * 2 * C;
+  if (ctx->gn_split) {
+    // statistics kernel + normalise kernel: grid (token chunks, frames), ~8 CTAs per SM worth of chunks
+    const int want = std::max(1, (ctx->num_sms * 8 + N - 1) / N);
+    const int unr = std::max(1, 8 / nv);
+    int tok_per_block = std::max((T + want - 1) / want, rpp * unr);
+    tok_per_block = (tok_per_block + rpp - 1) / rpp * rpp;
+    const int chunks = (T + tok_per_block - 1) / tok_per_block;
+    const size_t smem_stats = sizeof(float) * 2 * (size_t)rpp * C;
+    MMGT_CHECK_ARG(chunks <= 65535 * 16, MMGT_E_INVALID, "groupnorm: too many token chunks");
+    MMGT_CUDA_OK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * N * groups, st));
+    dim3 grid(chunks, N);
+#define GN2_LAUNCH(T_, NV_)                                                                                                  \
+  do {                                                                                                                       \
+    if (smem_stats > 48 * 1024) MMGT_CUDA_OK(mmgt_smem_optin(ctx, gn_stats_kernel<T_, NV_>, ctx->max_smem_optin));            \
+    MMGT_CUDA_OK(mmgt_launch(ctx, gn_stats_kernel<T_, NV_>, grid, dim3(GN_THREADS), smem_stats, st, (const T_*)x1,           \
+                             (const T_*)x2, stats_ws, T, C1, C2, groups, tok_per_block));                                    \
+    (ctx)->launches++;                                                                                                       \
+    MMGT_CUDA_OK(mmgt_launch(ctx, gn_apply_kernel<T_, NV_>, grid, dim3(GN_THREADS), smem, st, (const T_*)x1, (const T_*)x2,  \
+                             (T_*)y, gamma, beta, (const double*)stats_ws, T, C1, C2, groups, eps, silu, tok_per_block));    \
+  } while (0)
+    if (dtype == MMGT_F32) { if (nv == 1) GN2_LAUNCH(float, 1); else if (nv == 2) GN2_LAUNCH(float, 2); else GN2_LAUNCH(float, 3); }
+    else if (dtype == MMGT_BF16) { if (nv == 1) GN2_LAUNCH(bf16, 1); else if (nv == 2) GN2_LAUNCH(bf16, 2); else GN2_LAUNCH(bf16, 3); }
+    else { mmgt_set_error("groupnorm: bad dtype %d", dtype); return MMGT_E_INVALID; }
+#undef GN2_LAUNCH
+    MMGT_LAUNCH_OK(ctx);
+    return 0;
+  }
   // co-resident blocks (the frame barrier inside the kernel relies on it)
   int per_sm = 0;
 #define GN_OCC(T_, NV_) MMGT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel<T_, NV_>, GN_THREADS, smem))

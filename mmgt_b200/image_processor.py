@@ -44,3 +44,45 @@ class MaskPyramid:
     def full_mask_from_lips(self, lips_masks_list: Sequence) -> List[torch.Tensor]:
         """``full = 1.0 + lips`` per level (the recipe that survives in scripts/audio2vid.py:470-476)."""
         return self.levels(lips_masks_list, offset=1.0)
+
+
+class VaeImageProcessor:
+    """PIL / tensor -> (B, 3, H, W) float32, the subset of diffusers==0.24.0 ``VaeImageProcessor.preprocess`` that
+    ``Pose2VideoPipeline`` uses (pipeline_pose2vid_long.py:72-79,424-437): optional RGB conversion, Lanczos resize to
+    (height, width) rounded down to multiples of ``vae_scale_factor``, ``uint8 / 255``, optional ``2x - 1``.  Host-side
+    PIL / torch code (one-shot conditioning, not on the timed path)."""
+
+    def __init__(self, vae_scale_factor: int = 8, do_resize: bool = True, do_normalize: bool = True,
+                 do_convert_rgb: bool = False):
+        self.vae_scale_factor, self.do_resize = vae_scale_factor, do_resize
+        self.do_normalize, self.do_convert_rgb = do_normalize, do_convert_rgb
+
+    def preprocess(self, image, height: int = None, width: int = None) -> torch.Tensor:
+        from PIL import Image
+        if isinstance(image, (Image.Image, np.ndarray, torch.Tensor)):
+            image = [image]
+        if isinstance(image[0], Image.Image):
+            if self.do_convert_rgb:
+                image = [i.convert("RGB") for i in image]
+            if self.do_resize:
+                height = image[0].height if height is None else height
+                width = image[0].width if width is None else width
+                width, height = (x - x % self.vae_scale_factor for x in (width, height))
+                image = [i.resize((width, height), resample=Image.LANCZOS) for i in image]
+            arr = np.stack([np.array(i).astype(np.float32) / 255.0 for i in image], axis=0)
+            if arr.ndim == 3:
+                arr = arr[..., None]
+            out = torch.from_numpy(arr.transpose(0, 3, 1, 2))
+        elif isinstance(image[0], np.ndarray):
+            arr = np.concatenate(image, axis=0) if image[0].ndim == 4 else np.stack(image, axis=0)
+            if arr.ndim == 3:
+                arr = arr[..., None]
+            out = torch.from_numpy(arr.transpose(0, 3, 1, 2)).float()
+        elif torch.is_tensor(image[0]):
+            out = torch.cat(image, dim=0) if image[0].dim() == 4 else torch.stack(image, dim=0)
+            out = out.float()
+        else:
+            raise ValueError(f"unsupported image type {type(image[0])}")
+        if self.do_normalize and float(out.min()) >= 0:
+            out = 2.0 * out - 1.0
+        return out

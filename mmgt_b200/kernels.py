@@ -46,6 +46,7 @@ class Engine:
         self._stats_ws = None
         self._conv_ws = None
         self.unfused_exchange = False   # A/B switch: GEMM + mmgt_row_exchange_copy instead of the fused epilogue
+        self.fuse_layernorm = True      # bf16 tensor-core tier: LayerNorm applied in the consuming GEMM's epilogue
         self.prof = None          # optional: dict key -> [events..., flops, bytes] filled by bench.py's roofline pass
 
     # ------------------------------------------------------------------ per-launch timing (bench.py only)
@@ -68,6 +69,16 @@ class Engine:
         rec["calls"] += 1
 
     # ------------------------------------------------------------------ helpers
+    @property
+    def ln_fused(self) -> bool:
+        """LayerNorm is folded into the GEMM that consumes it (row statistics + epilogue) on the bf16 tensor-core tier."""
+        return self.fuse_layernorm and self.dtype == torch.bfloat16 and self.ctx.tensor_cores()
+
+    @property
+    def subpixel_upsample(self) -> bool:
+        """Upsample3D as four 2x2-tap sub-pixel convolutions (needs the pre-summed weight pack): bf16 tensor-core tier."""
+        return self.dtype == torch.bfloat16 and self.ctx.tensor_cores()
+
     def empty(self, *shape, dtype=None):
         return torch.empty(shape, device=self.device, dtype=dtype or self.dtype)
 
@@ -111,6 +122,8 @@ class Engine:
         N = x1.shape[0]
         C1 = x1.shape[-1]
         C2 = x2.shape[-1] if x2 is not None else 0
+        if x2 is not None and tuple(x2.shape[:-1]) != tuple(x1.shape[:-1]):
+            raise ValueError(f"groupnorm: x2 {tuple(x2.shape)} must share the leading dimensions of x1 {tuple(x1.shape)}")
         T = x1.numel() // (N * C1)
         out = self.empty(*x1.shape[:-1], C1 + C2)
         ws = self._stats(2 * N * groups + (N + 1) // 2)
@@ -132,9 +145,13 @@ class Engine:
 
     # ------------------------------------------------------------------ gemm / conv
     def gemm(self, A, W, bias=None, rowscale=None, rowbias=None, rows_per_group: int = 0, residual=None,
-             alpha: float = 1.0, geglu_block: int = 0, out=None, out_f32: bool = False, dtype=None, exchange=None):
-        """D = alpha * rowscale * (A @ W^T + bias) + rowbias[row // rows_per_group] + residual (then GEGLU).
+             alpha: float = 1.0, geglu_block: int = 0, out=None, out_f32: bool = False, dtype=None, exchange=None,
+             rowbias_mod: int = 0, rowstats=None, colsum=None, act: int = 0):
+        """D = act(alpha * rowscale * (A @ W^T + bias) + rowbias[row // rows_per_group]) + residual (then GEGLU).
         A: (..., K) rows with an arbitrary leading stride on the last-but-one dim; W: (N, K).
+        ``rowbias`` may be a column slice of a wider float32 matrix (its row stride is passed on); ``rowbias_mod`` wraps
+        the group index.  ``rowstats`` (rows, 2) + ``colsum`` (N): the LayerNorm feeding this GEMM is applied in the
+        epilogue (W must then be W diag(gamma), bias = bias + W beta).  ``act``: 0 none, 1 SiLU, 2 ReLU.
         ``exchange``: a frame_shard.Exchange -- the result rows go to the shards that own them (peer stores from
         the GEMM epilogue on the tensor-core path, GEMM + row-exchange copy otherwise); returns None."""
         K = A.shape[-1]
@@ -148,7 +165,8 @@ class Engine:
             and not self.unfused_exchange and self.lib.mmgt_gemm_tc_block_n(int(N)) > 0 and K % 8 == 0 and n_out % 16 == 0
         if exchange is not None and not fused_exchange:
             tmp = self.gemm(A, W, bias=bias, rowscale=rowscale, rowbias=rowbias, rows_per_group=rows_per_group,
-                            residual=residual, alpha=alpha, geglu_block=geglu_block)
+                            residual=residual, alpha=alpha, geglu_block=geglu_block, rowbias_mod=rowbias_mod,
+                            rowstats=rowstats, colsum=colsum, act=act)
             self.row_exchange_copy(tmp.view(-1, n_out), exchange)
             return None
         if fused_exchange:
@@ -171,6 +189,13 @@ class Engine:
         p.geglu_block = geglu_block
         p.dtype = dt
         p.out_f32 = int(out_f32)
+        if rowbias is not None:
+            assert rowbias.dtype == torch.float32 and rowbias.stride(-1) == 1
+            p.ld_rowbias = rowbias.stride(0) if rowbias.dim() > 1 else 0
+        p.rowbias_mod = rowbias_mod
+        p.rowstats = rowstats.data_ptr() if rowstats is not None else None
+        p.colsum = colsum.data_ptr() if colsum is not None else None
+        p.act = act
         ev = self._t0()
         check(self.lib.mmgt_gemm(self.h, C.byref(p), _stream()), "mmgt_gemm")
         self._t1(ev, ("gemm_exchange" if fused_exchange else "gemm", N, K, bool(geglu_block)), 2.0 * M * N * K,
@@ -185,8 +210,21 @@ class Engine:
                                                _stream()), "mmgt_row_exchange_copy")
         self._t1(ev, ("row_exchange_copy", Cc), 0.0, 2.0 * src.numel() * src.element_size())
 
+    def row_stats(self, x, eps: float = 1e-5):
+        """(mean, rstd) per row of x (rows, C) -> (rows, 2) float32: the LayerNorm statistics a GEMM applies in its
+        epilogue (``gemm(..., rowstats=, colsum=)``)."""
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc if x.is_contiguous() else x.shape[0]
+        ld = Cc if x.is_contiguous() else x.stride(-2)
+        out = torch.empty((rows, 2), device=self.device, dtype=torch.float32)
+        ev = self._t0()
+        check(self.lib.mmgt_row_stats(self.h, _p(x), _p(out), rows, Cc, ld, float(eps), dt_code(x.dtype), _stream()),
+              "mmgt_row_stats")
+        self._t1(ev, ("row_stats", Cc), 0.0, float(rows) * Cc * x.element_size())
+        return out
+
     def conv3x3(self, x, w_krsc, bias=None, rowbias=None, frames_per_group: int = 0, residual=None, stride: int = 1,
-                upsample2x: bool = False):
+                upsample2x: bool = False, w_subpixel=None, act: int = 0):
         N, H, W, Cin = x.shape
         Cout = w_krsc.shape[0]
         Hi, Wi = (2 * H, 2 * W) if upsample2x else (H, W)
@@ -199,6 +237,11 @@ class Engine:
         p.residual = residual.data_ptr() if residual is not None else None
         p.N, p.H, p.W, p.Cin, p.Cout = N, H, W, Cin, Cout
         p.stride, p.upsample2x, p.frames_per_group, p.dtype = stride, int(upsample2x), frames_per_group, self.dt
+        if rowbias is not None:
+            assert rowbias.dtype == torch.float32 and rowbias.stride(-1) == 1
+            p.ld_rowbias = rowbias.stride(0) if rowbias.dim() > 1 else 0
+        p.act = act
+        p.w_subpixel = w_subpixel.data_ptr() if (w_subpixel is not None and upsample2x) else None
         need = self.lib.mmgt_conv3x3_workspace_bytes(self.h, C.byref(p))
         ws = None
         if need > 0:
@@ -291,6 +334,15 @@ class Engine:
         out = self.empty(N, 2 * H, 2 * W, Cc)
         check(self.lib.mmgt_upsample_nearest2x(self.h, _p(x), _p(out), N, H, W, Cc, self.dt, _stream()),
               "mmgt_upsample_nearest2x")
+        return out
+
+    def pad_channels(self, x, c_pad: int):
+        """(..., C) -> (..., c_pad), zero-filled."""
+        Cc = x.shape[-1]
+        x = x.contiguous()
+        out = torch.empty(tuple(x.shape[:-1]) + (c_pad,), device=self.device, dtype=x.dtype)
+        check(self.lib.mmgt_pad_channels(self.h, _p(x), _p(out), x.numel() // Cc, Cc, c_pad, dt_code(x.dtype), _stream()),
+              "mmgt_pad_channels")
         return out
 
     def gather_rows(self, src, idx_i32, out=None):

@@ -10,7 +10,7 @@ import math
 import torch
 import torch.nn as nn
 
-from .attention import Attention, FeedForward, _LN
+from .attention import Attention, FeedForward, _LN, ln_qkv
 from .kernels import Engine
 from .packing import Pack, f32, run
 from .resnet import GroupNorm2d
@@ -85,13 +85,15 @@ class TemporalTransformerBlock(nn.Module):
         (token-sharded rows); ``exchange`` sends the block output back to the frame shards."""
         for attn, norm in zip(self.attention_blocks, self.norms):
             pk = attn.packed(eng)
+            pe = attn.pos_encoder.pe[0] if attn.pos_encoder is not None else None
+            if pe is not None and F > pe.shape[0]:
+                raise ValueError(f"{F} frames per window exceed temporal_position_encoding_max_len={pe.shape[0]} "
+                                 "(motion_module.py:275-277 fails the same way)")
             # LayerNorm, then + pe[frame]: the PE feeds q, k AND v (motion_module.py:365-366)
-            n = norm.run(eng, x, pe=attn.pe_table(eng), T=T, F=F)
-            qkv = eng.gemm(n, pk["qkv"])
+            qkv = ln_qkv(eng, x, norm, attn, pe=pe, T=T, F=F)
             a = eng.temporal_attention(qkv, B, F, T, attn.heads)
             x = eng.gemm(a, pk["o"], bias=pk["bo"], residual=x)
-        n = self.ff_norm.run(eng, x)
-        return self.ff.run(eng, n, x, exchange=exchange)
+        return self.ff.run(eng, x, x, exchange=exchange, ln=self.ff_norm)
 
 
 class TemporalTransformer3DModel(nn.Module):

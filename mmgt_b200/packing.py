@@ -59,8 +59,8 @@ def subpixel_upsample_weights(weight: torch.Tensor):
     out[2y+a, 2x+b] only ever sees a 2x2 neighbourhood of the LOW-resolution input, so the operator is four 2x2-tap
     convolutions on the input with pre-summed weights: rows {y-1, y} for a = 0 and {y, y+1} for a = 1 (same for columns),
     zero outside the image -- 16 tap-GEMMs at input resolution instead of 9 at output resolution (2.25x fewer FLOPs) and
-    no upsampled / im2col tensor.  Not wired into the kernels yet; the identity is checked in
-    tests/test_host_logic.py.
+    no upsampled / im2col tensor.  ``subpixel_pack`` lays the result out for mmgt_conv3x3 (w_subpixel); the identity is
+    checked in tests/test_host_logic.py.
 
     weight (Cout, Cin, 3, 3) -> dict[(a, b)] = (taps (Cout, Cin, 2, 2), row offsets (2,), column offsets (2,))."""
     w = weight.detach()
@@ -75,3 +75,26 @@ def subpixel_upsample_weights(weight: torch.Tensor):
                 taps.append(torch.stack(cols, dim=-1))
             out[(a, b)] = (torch.stack(taps, dim=-2), rows[1], (-1, 0) if b == 0 else (0, 1))
     return out
+
+
+def subpixel_pack(weight: torch.Tensor, eng) -> torch.Tensor:
+    """(Cout, Cin, 3, 3) -> (Cout, 4, 2, 2, Cin) in the run dtype: parity index 2a + b, then tap (ty, tx), channels last
+    (the ``w_subpixel`` operand of mmgt_conv3x3, include/mmgt_b200.h).  The taps are summed in float32 and rounded once."""
+    sp = subpixel_upsample_weights(weight.detach().float())
+    per_parity = [sp[(a, b)][0].permute(0, 2, 3, 1) for a in (0, 1) for b in (0, 1)]      # 4 x (Cout, 2, 2, Cin)
+    return torch.stack(per_parity, dim=1).to(device=eng.device, dtype=eng.dtype).contiguous()
+
+
+def ln_fold(weight: torch.Tensor, bias, gamma: torch.Tensor, beta: torch.Tensor, eng):
+    """Fold the affine LayerNorm that feeds ``y = LN(x) W^T + bias`` into the GEMM (mmgt_gemm rowstats / colsum):
+    LN(x) W^T + bias = rstd * (x W'^T - mean * colsum) + bias'  with  W' = W diag(gamma), colsum = W' 1, bias' = bias + W beta.
+    colsum is taken from the ROUNDED W' (what the tensor cores multiply), in float64.  -> (W' run dtype, colsum f32, bias' f32)"""
+    w = weight.detach().to(device=eng.device, dtype=torch.float64)
+    g = gamma.detach().to(device=eng.device, dtype=torch.float64)
+    b = beta.detach().to(device=eng.device, dtype=torch.float64)
+    wp = (w * g[None, :]).to(eng.dtype).contiguous()
+    colsum = wp.double().sum(dim=1).float().contiguous()
+    bp = w @ b
+    if bias is not None:
+        bp = bp + bias.detach().to(device=eng.device, dtype=torch.float64)
+    return wp, colsum, bp.float().contiguous()

@@ -2,8 +2,9 @@
 
 ``DenoiseLoop`` is the hot loop (:491-646): per DDIM step, one UNet forward per 12-frame context window with
 CFG, overlap-averaged, CFG-combined and DDIM-updated -- everything on the sm_100a kernels.
-``Pose2VideoPipeline`` keeps the reference's constructor and ``__call__`` signature; the one-shot conditioning
-passes (CLIP, VAE, ReferenceNet write pass, pose guider) remain the caller's PyTorch modules.
+``Pose2VideoPipeline`` keeps the reference's constructor and ``__call__`` signature and argument types; the one-shot
+conditioning passes (CLIP, VAE encode, ReferenceNet write pass, pose guider) run on the PyTorch modules handed to the
+constructor, exactly where the reference runs them.
 
 Multi-GPU (one process per GPU): the (window, CFG-branch) forwards of a step are independent
  and are dealt round-robin to the rank groups; the only exchange between groups is one
@@ -18,6 +19,7 @@ from typing import Callable, List, Optional, Sequence, Union
 import torch
 
 from .context import get_context_scheduler
+from .image_processor import VaeImageProcessor
 from .kernels import Engine
 from .mutual_self_attention import ReferenceAttentionControl
 from .scheduling_ddim import DDIMSchedule
@@ -53,6 +55,8 @@ class DenoiseLoop:
         self.timesteps = schedule.timesteps(num_inference_steps)
         self._graph = None
         self.graph_launches = 0
+        self._made_group = False
+        self._bank_ptrs = None
 
     # ------------------------------------------------------------------ one-off preparation per video
     def prepare(self, latents, pose_fea, audio, full_mask, face_mask, lip_mask, encoder_hidden_states):
@@ -77,6 +81,7 @@ class DenoiseLoop:
             bad = [len(c) for c in self.windows if len(c) % k]
             if bad:
                 raise ValueError(f"frame_shards={k} needs every context window to hold a multiple of {k} frames, got {bad}")
+            self._made_group = self.shard_group is None
             if self.shard_group is None:
                 from .frame_shard import FrameShardGroup, max_exchange_bytes
                 esize = torch.empty((), dtype=eng.dtype).element_size()
@@ -106,7 +111,20 @@ class DenoiseLoop:
                                       shard=self.shard_group if sharded else None))
         self._fill_conditioning(pose_fea, audio, full_mask, face_mask, lip_mask, encoder_hidden_states, first=True)
         self._signature = self._conditioning_signature(latents, pose_fea, audio, full_mask, encoder_hidden_states)
+        self._owns_shard_group = need_group and self.shard_group is not None and self._made_group
         return self
+
+    def close(self):
+        """Release the peer buffers of a frame-shard group this loop created in prepare() (collective over the ranks)."""
+        self._graph = None
+        if getattr(self, "_owns_shard_group", False) and self.shard_group is not None:
+            self.shard_group.close(self.group)
+            self.shard_group, self._owns_shard_group = None, False
+
+    def _project_banks(self):
+        """Project the reference banks of all spatial blocks (eagerly, outside any graph) and return the storage
+        pointers a captured graph depends on."""
+        return tuple(b.bank_kv_storage() if b.bank_kv(self.eng) is not None else None for b in self.unet.spatial_blocks())
 
     @staticmethod
     def _conditioning_signature(latents, pose_fea, audio, full_mask, ehs):
@@ -141,12 +159,19 @@ class DenoiseLoop:
 
     def reload(self, latents, pose_fea, audio, full_mask, face_mask, lip_mask, encoder_hidden_states):
         """The next video of the same shape: refill the latents and the per-unit conditioning in place, so the CUDA
-        graph captured for the first video (and the peer buffers of a frame-shard group) keep serving."""
+        graph captured for the first video (and the peer buffers of a frame-shard group) keep serving.  The reference
+        banks currently attached to the UNet (ReferenceAttentionControl.update / set_banks for the NEW reference image)
+        are re-projected into the K/V buffers the graph reads; a bank whose shape changed cannot be served by the
+        captured graph and raises."""
         sig = self._conditioning_signature(latents, pose_fea, audio, full_mask, encoder_hidden_states)
         if sig != self._signature:
             raise ValueError(f"reload() needs the shapes prepare() saw: {self._signature}, got {sig}")
         self.latents.copy_(latents.to(torch.float32))
         self._fill_conditioning(pose_fea, audio, full_mask, face_mask, lip_mask, encoder_hidden_states, first=False)
+        ptrs = self._project_banks()
+        if self._graph is not None and ptrs != self._bank_ptrs:
+            raise ValueError("reload(): the reference banks changed shape (or appeared / disappeared) since the CUDA graph "
+                             "was captured; build a new DenoiseLoop for this video")
         return self
 
     # ------------------------------------------------------------------ the hot loop
@@ -156,7 +181,8 @@ class DenoiseLoop:
             x = eng.gather_rows(lat_tok, e["x_idx"])
             nbr, F_ = len(e["branches"]), e["frames"]
             out = u.forward_tokens(eng, x, self.t_dev, e["ehs"], e["audio"], e["pose"], e["masks"][0], e["masks"][1],
-                                   e["masks"][2], self.motion_scale, nbr, F_, ref_index=e["ref"], shard=e["shard"])
+                                   e["masks"][2], self.motion_scale, nbr, F_, ref_index=e["ref"], shard=e["shard"],
+                                   time_proj=self._time_proj)
             pred = eng.tokens_to_ncfhw(out, nbr, F_, torch.float32)
             eng.window_accumulate(self.noise_acc, pred, e["idx"], e["branches"][0])
 
@@ -165,6 +191,8 @@ class DenoiseLoop:
         run this rank's (window, branch) forwards and scatter-add their predictions."""
         self.noise_acc.zero_()
         lat_tok = self.eng.ncfhw_to_tokens(self.latents)[: self.L]      # (L,h,w,4) run dtype
+        # the timestep is the same for every window of a step: time embedding + all 22 time_emb_proj once per step
+        self._time_proj = self.unet.time_projections(self.eng, self.t_dev, self.nb)
         self._forward_units(lat_tok)
 
     def capture_graph(self):
@@ -179,6 +207,7 @@ class DenoiseLoop:
             self.graph_launches = self.eng.ctx.launches() - n0
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        self._bank_ptrs = self._project_banks()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._units_body()
@@ -205,6 +234,8 @@ class DenoiseLoop:
             self.step(i)
             if callback is not None and i % callback_steps == 0:
                 callback(i, self.timesteps[i], self.latents)
+        if self.shard_group is not None:
+            self.shard_group.check()      # a peer-barrier timeout means rows were missing: never return such latents
         return self.latents
 
 
@@ -276,17 +307,28 @@ def _pad16(m: torch.Tensor) -> torch.Tensor:
 
 
 class Pose2VideoPipeline:
-    """Same constructor / ``__call__`` signature as the reference (pipeline_pose2vid_long.py:38-56,337-366)."""
+    """Same constructor / ``__call__`` signature as the reference (pipeline_pose2vid_long.py:38-56,337-366), and the same
+    argument types: ``ref_image`` a PIL image, ``pose_images`` a list of PIL images, masks as lists of 4 ``(L, T_l)``
+    tensors, ``audio_tensor`` (1, L, 32, 768) -- so ``scripts/pose2vid.py:284-296`` / ``scripts/audio2vid.py:484-498``
+    call it unchanged.  The one-shot conditioning passes run on the modules handed to the constructor (CLIP image
+    encoder, VAE encoder, ReferenceNet, PoseGuider: the reference's PyTorch); the 30-step loop runs
+    on the sm_100a kernels through a ``DenoiseLoop`` whose CUDA graph is cached on the pipeline per video shape, so a
+    second call of the same shape only refills the conditioning (``DenoiseLoop.reload``)."""
 
     def __init__(self, vae, image_encoder, reference_unet, denoising_unet, pose_guider, scheduler, image_proj_model=None,
                  tokenizer=None, text_encoder=None):
         self.vae, self.image_encoder, self.reference_unet = vae, image_encoder, reference_unet
         self.denoising_unet, self.pose_guider, self.scheduler = denoising_unet, pose_guider, scheduler
         self.image_proj_model, self.tokenizer, self.text_encoder = image_proj_model, tokenizer, text_encoder
-        self.vae_scale_factor = 8
+        boc = getattr(getattr(vae, "config", None), "block_out_channels", None)
+        self.vae_scale_factor = 2 ** (len(boc) - 1) if boc is not None else 8
+        self.ref_image_processor = VaeImageProcessor(self.vae_scale_factor, do_convert_rgb=True)
+        self.cond_image_processor = VaeImageProcessor(self.vae_scale_factor, do_convert_rgb=True, do_normalize=False)
         self.rank, self.world_size, self.process_group = 0, 1, None     # set by the launcher for multi-GPU runs
         self.frame_shards = 1                                           # k ranks split the frames of a window
         self.shard_remainder = False                                    # only the forwards left over by the whole deal
+        self.use_cuda_graph = True
+        self._loops = {}                                                # video shape -> captured DenoiseLoop
 
     def to(self, *a, **k):
         for m in (self.vae, self.image_encoder, self.reference_unet, self.denoising_unet, self.pose_guider):
@@ -295,16 +337,39 @@ class Pose2VideoPipeline:
         return self
 
     @property
+    def device(self):
+        return self.denoising_unet.device
+
+    @property
     def _execution_device(self):
         return self.denoising_unet.device
+
+    def enable_vae_slicing(self):
+        self.vae.enable_slicing()
+
+    def disable_vae_slicing(self):
+        self.vae.disable_slicing()
+
+    def close(self):
+        """Drop the cached loops (CUDA graphs, peer buffers)."""
+        for loop in self._loops.values():
+            loop.close()
+        self._loops = {}
 
     def prepare_latents(self, batch_size, num_channels_latents, width, height, video_length, dtype, device, generator,
                         latents=None):
         shape = (batch_size, num_channels_latents, video_length, height // self.vae_scale_factor,
                  width // self.vae_scale_factor)
+        if isinstance(generator, list) and len(generator) != batch_size:
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an effective "
+                             f"batch size of {batch_size}.")
         if latents is None:
+            if isinstance(generator, list):
+                generator = generator[0]
             gdev = generator.device if generator is not None else torch.device("cpu")
             latents = torch.randn(shape, generator=generator, device=gdev, dtype=torch.float32).to(device)
+        else:
+            latents = latents.to(device)
         return latents * 1.0   # init_noise_sigma == 1 for DDIM
 
     def decode_latents(self, latents):
@@ -317,60 +382,143 @@ class Pose2VideoPipeline:
         video = torch.stack(frames, dim=2)
         return ((video / 2 + 0.5).clamp(0, 1)).cpu().float().numpy()
 
+    def interpolate_latents(self, latents: torch.Tensor, interpolation_factor: int, device=None):
+        """pipeline_pose2vid_long.py:292-332 with the linear method of src/pipelines/utils.py:15-16."""
+        if interpolation_factor < 2:
+            return latents
+        L = latents.shape[2]
+        out = torch.zeros(latents.shape[:2] + ((L - 1) * interpolation_factor + 1,) + latents.shape[3:],
+                          device=latents.device, dtype=latents.dtype)
+        rate = [i / interpolation_factor for i in range(interpolation_factor)][1:]
+        k = 0
+        for i0 in range(L - 1):
+            v0, v1 = latents[:, :, i0], latents[:, :, i0 + 1]
+            out[:, :, k] = v0
+            k += 1
+            for f in rate:
+                out[:, :, k] = (1.0 - f) * v0 + f * v1
+                k += 1
+        out[:, :, k] = latents[:, :, L - 1]
+        return out
+
+    # ------------------------------------------------------------------ one-shot conditioning (reference PyTorch modules)
+    def _clip_embeds(self, ref_image, device):
+        from transformers import CLIPImageProcessor
+        if not hasattr(self, "clip_image_processor"):
+            self.clip_image_processor = CLIPImageProcessor()
+        clip_image = self.clip_image_processor.preprocess(ref_image.resize((224, 224)), return_tensors="pt").pixel_values
+        return self.image_encoder(clip_image.to(device, dtype=self.image_encoder.dtype)).image_embeds
+
+    def _reference_banks(self, reader, ref_image, ehs, width, height, cfg, device):
+        """VAE-encode the reference image, run the ReferenceNet once in write mode, hand its banks to the reader
+        (pipeline_pose2vid_long.py:403-448,510-520)."""
+        writer = ReferenceAttentionControl(self.reference_unet, do_classifier_free_guidance=cfg, mode="write", batch_size=1,
+                                           fusion_blocks="full")
+        try:
+            ref = self.ref_image_processor.preprocess(ref_image, height=height, width=width)
+            vdev = getattr(self.vae, "device", device)
+            ref = ref.to(dtype=self.vae.dtype, device=vdev)
+            ref_latents = self.vae.encode(ref).latent_dist.mean * 0.18215                  # (1, 4, h, w)
+            rdt = getattr(self.reference_unet, "dtype", ref_latents.dtype)
+            self.reference_unet(ref_latents.to(device=device, dtype=rdt).repeat(2 if cfg else 1, 1, 1, 1),
+                                torch.zeros((), device=device, dtype=torch.long),
+                                encoder_hidden_states=ehs.to(device=device, dtype=rdt), return_dict=False)
+            reader.update(writer)
+        finally:
+            writer.clear()
+            writer.remove()
+
+    def _pose_features(self, pose_images, width, height, device):
+        if torch.is_tensor(pose_images):               # already (1, 3, L, H, W) in [0, 1]
+            cond = pose_images
+        else:
+            frames = [self.cond_image_processor.preprocess(p, height=height, width=width).unsqueeze(2) for p in pose_images]
+            cond = torch.cat(frames, dim=2)                                                 # (1, 3, L, H, W)
+        return self.pose_guider(cond.to(device=device, dtype=self.pose_guider.dtype))
+
     @torch.no_grad()
     def __call__(self, ref_image, pose_images, audio_tensor, pixel_values_full_mask, pixel_values_face_mask,
                  pixel_values_lip_mask, width, height, video_length, num_inference_steps, guidance_scale,
                  num_images_per_prompt=1, eta: float = 0.0, motion_scale=None, generator=None, output_type="tensor",
                  return_dict: bool = True, callback=None, callback_steps=1, context_schedule="uniform", context_frames=12,
                  context_stride=1, context_overlap=4, context_batch_size=1, interpolation_factor=1, **kwargs):
+        """Extra keyword arguments (all optional, none used by the reference scripts): ``latents`` initial noise;
+        ``clip_image_embeds`` / ``reference_banks`` / ``pose_fea`` precomputed conditioning that replaces the
+        corresponding one-shot pass."""
         if eta != 0.0:
-            raise NotImplementedError("eta != 0")
+            raise NotImplementedError("eta != 0 (the reference scripts use the DDIM default eta = 0)")
+        if num_images_per_prompt != 1:
+            raise NotImplementedError("num_images_per_prompt != 1 (the reference hard-codes batch_size = 1)")
+        sample_size = getattr(getattr(self.denoising_unet, "config", None), "sample_size", None)
+        height = height or sample_size * self.vae_scale_factor
+        width = width or sample_size * self.vae_scale_factor
         device = self._execution_device
         cfg = guidance_scale > 1.0
-        # --- one-shot conditioning: the reference's own modules (PyTorch), or precomputed tensors via kwargs
+        # context_batch_size only batches independent windows in the reference (:546-552); windows run one by one here
+        # with identical results, so the value is accepted and ignored.
+        # --- CLIP image embedding (:380-394)
         clip_embeds = kwargs.get("clip_image_embeds")
         if clip_embeds is None:
-            from transformers import CLIPImageProcessor
-            clip_image = CLIPImageProcessor().preprocess(ref_image.resize((224, 224)), return_tensors="pt").pixel_values
-            clip_embeds = self.image_encoder(clip_image.to(device, dtype=self.image_encoder.dtype)).image_embeds
+            clip_embeds = self._clip_embeds(ref_image, device)
         ehs = clip_embeds.unsqueeze(1) if clip_embeds.dim() == 2 else clip_embeds
         if cfg:
             ehs = torch.cat([torch.zeros_like(ehs), ehs], dim=0)
+        # --- reference features (:396-409, 439-448, 510-520)
         reader = ReferenceAttentionControl(self.denoising_unet, do_classifier_free_guidance=cfg, mode="read", batch_size=1,
                                            fusion_blocks="full")
-        latents = self.prepare_latents(num_images_per_prompt, self.denoising_unet.in_channels, width, height, video_length,
-                                       torch.float32, device, generator, kwargs.get("latents"))
         banks = kwargs.get("reference_banks")
         if banks is not None:
             reader.set_banks(banks)
+        elif kwargs.get("reference_control_writer") is not None:      # a writer the caller already ran
+            reader.update(kwargs["reference_control_writer"])
         else:
-            writer = kwargs.get("reference_control_writer")
-            if writer is None:
-                raise ValueError("pass reference_banks=[...] or reference_control_writer=<the reference's writer control> "
-                                 "(the ReferenceNet write pass is the reference's PyTorch)")
-            ref_latents = kwargs["ref_image_latents"]
-            self.reference_unet(ref_latents.repeat(2 if cfg else 1, 1, 1, 1), torch.zeros((), device=device),
-                                encoder_hidden_states=ehs.to(ref_latents.dtype), return_dict=False)
-            reader.update(writer)
+            self._reference_banks(reader, ref_image, ehs, width, height, cfg, device)
+        latents = self.prepare_latents(num_images_per_prompt, self.denoising_unet.in_channels, width, height, video_length,
+                                       torch.float32, device, generator, kwargs.get("latents"))
+        # --- pose features (:450-464)
         pose_fea = kwargs.get("pose_fea")
         if pose_fea is None:
-            pose_fea = self.pose_guider(pose_images.to(device=device, dtype=self.pose_guider.dtype))
+            pose_fea = self._pose_features(pose_images, width, height, device)
+        # --- masks and audio, duplicated for CFG (:466-488)
         dup = (lambda ms: [torch.cat([m] * 2) for m in ms]) if cfg else (lambda ms: list(ms))
         audio = audio_tensor.to(device)
         if cfg:
             audio = torch.cat([torch.zeros_like(audio), audio], dim=0)
+        full, face, lip = dup(pixel_values_full_mask), dup(pixel_values_face_mask), dup(pixel_values_lip_mask)
+        # --- the denoising loop (:491-646): cached per video shape
         sched = self.scheduler if isinstance(self.scheduler, DDIMSchedule) else DDIMSchedule.from_scheduler(self.scheduler)
-        loop = DenoiseLoop(self.denoising_unet, sched, num_inference_steps, guidance_scale, context_frames, context_stride,
-                           context_overlap, context_schedule, motion_scale, self.rank, self.world_size, self.process_group,
-                           self.frame_shards, shard_remainder=self.shard_remainder)
-        loop.prepare(latents, pose_fea, audio, dup(pixel_values_full_mask), dup(pixel_values_face_mask),
-                     dup(pixel_values_lip_mask), ehs)
-        latents = loop.run(callback, callback_steps)
-        reader.clear()
+        ms_key = None if motion_scale is None else tuple(float(m) for m in motion_scale)
+        key = (tuple(latents.shape), num_inference_steps, float(guidance_scale), context_schedule, context_frames,
+               context_stride, context_overlap, ms_key, self.rank, self.world_size, self.frame_shards, self.shard_remainder,
+               tuple(audio.shape), str(self.denoising_unet._engine(device).dtype))
+        loop = self._loops.get(key)
+        try:
+            if loop is None:
+                loop = DenoiseLoop(self.denoising_unet, sched, num_inference_steps, guidance_scale, context_frames,
+                                   context_stride, context_overlap, context_schedule, motion_scale, self.rank, self.world_size,
+                                   self.process_group, self.frame_shards, shard_remainder=self.shard_remainder)
+                loop.prepare(latents, pose_fea, audio, full, face, lip, ehs)
+                if self.use_cuda_graph and latents.is_cuda:
+                    loop.capture_graph()
+                self._loops[key] = loop
+            else:
+                loop.reload(latents, pose_fea, audio, full, face, lip, ehs)
+            latents = loop.run(callback, callback_steps).clone()
+        except Exception:
+            bad = self._loops.pop(key, None)
+            if bad is not None:
+                bad.close()
+            raise
+        finally:
+            reader.clear()
+        if interpolation_factor > 0:
+            latents = self.interpolate_latents(latents, interpolation_factor, device)
         if output_type == "latent" or self.vae is None:
             images = latents
         else:
-            images = torch.from_numpy(self.decode_latents(latents))
+            images = self.decode_latents(latents)
+            if output_type == "tensor":
+                images = torch.from_numpy(images)
         if not return_dict:
             return images
         return Pose2VideoPipelineOutput(videos=images)

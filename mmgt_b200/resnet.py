@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from .kernels import Engine, get_engine
-from .packing import Pack, conv1x1, conv_krsc, f32
+from .packing import Pack, conv1x1, conv_krsc, f32, subpixel_pack
 
 
 def _engine_for(module: nn.Module, x: torch.Tensor) -> Engine:
@@ -26,6 +26,7 @@ class InflatedConv3d(nn.Conv2d):
     def __init__(self, *a, **k):
         super().__init__(*a, **k)
         self._pack = Pack()
+        self._sp_pack = Pack()
 
     def packed(self, eng: Engine):
         def build():
@@ -33,6 +34,12 @@ class InflatedConv3d(nn.Conv2d):
             if self.kernel_size == (3, 3):
                 w = conv_krsc(self.weight, eng)
                 cout = w.shape[0]
+                if eng.dtype == torch.bfloat16 and w.shape[-1] < 64:
+                    # conv_in (4 -> 320): zero-pad the input channels to 64 so the tensor-core implicit GEMM takes it
+                    # (run() pads the activation to match)
+                    wp = torch.zeros(tuple(w.shape[:-1]) + (64,), device=w.device, dtype=w.dtype)
+                    wp[..., : w.shape[-1]] = w
+                    w = wp
                 if eng.dtype == torch.bfloat16 and cout < 32 and w.shape[-1] % 64 == 0:
                     # conv_out (320 -> 4): pad the output channels to 32 so the tensor-core implicit GEMM takes it
                     wp = torch.zeros((32,) + tuple(w.shape[1:]), device=w.device, dtype=w.dtype)
@@ -47,19 +54,29 @@ class InflatedConv3d(nn.Conv2d):
             return w, b
         return self._pack.get(eng, [self.weight] + ([self.bias] if self.bias is not None else []), build)
 
-    def run(self, eng: Engine, x, rowbias=None, frames_per_group=0, residual=None, upsample2x=False):
+    def subpixel(self, eng: Engine):
+        """Pre-summed 2x2 taps of the four output parities for the x2-upsampling form (Upsample3D), bf16 tier only."""
+        if not eng.subpixel_upsample:
+            return None
+        return self._sp_pack.get(eng, [self.weight], lambda: subpixel_pack(self.weight, eng))
+
+    def run(self, eng: Engine, x, rowbias=None, frames_per_group=0, residual=None, upsample2x=False, act=0):
         w, b = self.packed(eng)
         if self.kernel_size == (3, 3):
             if self.padding != (1, 1):
                 raise NotImplementedError("InflatedConv3d: only padding=1 is implemented for 3x3 kernels")
+            if x.shape[-1] < w.shape[-1]:
+                x = eng.pad_channels(x, w.shape[-1])
             y = eng.conv3x3(x, w, bias=b, rowbias=rowbias, frames_per_group=frames_per_group, residual=residual,
-                            stride=self.stride[0], upsample2x=upsample2x)
+                            stride=self.stride[0], upsample2x=upsample2x, act=act,
+                            w_subpixel=self.subpixel(eng) if upsample2x else None)
             # padded output channels: return the real ones as a strided view (consumers take a channel stride)
             return y if y.shape[-1] == self.out_channels else y[..., : self.out_channels]
         if self.kernel_size != (1, 1) or self.stride != (1, 1):
             raise NotImplementedError("InflatedConv3d: only 3x3 and 1x1 kernels are implemented")
         N, H, W, C = x.shape
-        out = eng.gemm(x.view(N * H * W, C), w, bias=b, residual=None if residual is None else residual.view(N * H * W, -1))
+        out = eng.gemm(x.view(N * H * W, C), w, bias=b, residual=None if residual is None else residual.view(N * H * W, -1),
+                       act=act)
         return out.view(N, H, W, -1)
 
     def forward(self, x):
@@ -149,14 +166,21 @@ class ResnetBlock3D(nn.Module):
             if use_in_shortcut else None
         self._tpack = Pack()
 
-    def run(self, eng: Engine, x1, x2: Optional[torch.Tensor], temb_silu: torch.Tensor, frames: int):
+    def run(self, eng: Engine, x1, x2: Optional[torch.Tensor], temb, frames: int):
         """x1 (+ optional skip x2, the virtual channel concat of unet_3d_blocks.py:894) -> (N,H,W,Cout).
-        temb_silu: (B, temb_channels) float32 = silu(emb)."""
+        temb: TimeProjections (unet_3d.py) -- this block's time_emb_proj(silu(emb)) is a column slice of ONE projection
+        computed per DDIM step for all 22 resnets -- or a (B, temb_channels) float32 tensor silu(emb)."""
         N, H, W, C1 = x1.shape
         rows = N * H * W
-        wt, bt = self._tpack.get(eng, [self.time_emb_proj.weight, self.time_emb_proj.bias],
-                                 lambda: (f32(self.time_emb_proj.weight, eng), f32(self.time_emb_proj.bias, eng)))
-        tproj = eng.gemm(temb_silu, wt, bias=bt, dtype=torch.float32)          # (B, Cout) fp32
+        if x2 is not None and tuple(x2.shape[:-1]) != (N, H, W):
+            raise ValueError(f"skip connection {tuple(x2.shape)} does not match the hidden state {tuple(x1.shape)} "
+                             "(latent sizes must be divisible by 2**num_upsamplers)")
+        if torch.is_tensor(temb):
+            wt, bt = self._tpack.get(eng, [self.time_emb_proj.weight, self.time_emb_proj.bias],
+                                     lambda: (f32(self.time_emb_proj.weight, eng), f32(self.time_emb_proj.bias, eng)))
+            tproj = eng.gemm(temb, wt, bias=bt, dtype=torch.float32)          # (B, Cout) fp32
+        else:
+            tproj = temb.of(self)                                             # (B, Cout) fp32 view, row stride = total width
         h = self.norm1.run(eng, x1, x2, silu=True)
         h = self.conv1.run(eng, h, rowbias=tproj, frames_per_group=frames)
         h = self.norm2.run(eng, h, None, silu=True)

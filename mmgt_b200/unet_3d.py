@@ -64,6 +64,23 @@ class TimestepEmbedding(nn.Module):
         return eng.gemm(h, w2, bias=b2, dtype=torch.float32)
 
 
+class TimeProjections:
+    """silu(time embedding) pushed through the ``time_emb_proj`` of ALL resnets by one GEMV: (B, sum of widths) float32.
+    A resnet's (B, Cout) rowbias is a column slice (``of``); ``rows`` selects batch rows for single-branch forwards.
+    Computed once per DDIM step (the timestep is the same for every context window, pipeline_pose2vid_long.py:554-620)
+    instead of 2 + 22 GEMVs per window forward."""
+
+    def __init__(self, all_proj: torch.Tensor, offsets: dict):
+        self.all_proj, self.offsets = all_proj, offsets
+
+    def of(self, resnet) -> torch.Tensor:
+        o, n = self.offsets[id(resnet)]
+        return self.all_proj[:, o:o + n]
+
+    def rows(self, B: int) -> "TimeProjections":
+        return self if B == self.all_proj.shape[0] else TimeProjections(self.all_proj[:B], self.offsets)
+
+
 _INIT_DEFAULTS = dict(
     sample_size=None, in_channels=4, out_channels=4, flip_sin_to_cos=True, freq_shift=0,
     down_block_types=("CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "DownBlock3D"),
@@ -163,6 +180,7 @@ class UNet3DConditionModel(nn.Module):
         # `self.training and gradient_checkpointing`; True/False force it.
         self.apply_motion_scale: Optional[bool] = None
         self._idx_cache = {}
+        self._time_pack = Pack()
 
     # ------------------------------------------------------------------ diffusers-style plumbing
     @property
@@ -274,6 +292,36 @@ class UNet3DConditionModel(nn.Module):
             dt = torch.bfloat16
         return get_engine(device, dt)
 
+    def time_projections(self, eng: Engine, timestep, B: int) -> TimeProjections:
+        """unet_3d.py:481-502 + resnet.py:226 for every resnet at once; float32 end to end.  ``timestep``: python number,
+        0-d / (1,) / (B,) tensor (a device tensor keeps the call CUDA-graph capturable)."""
+        from .resnet import ResnetBlock3D
+        dev = eng.device
+        if torch.is_tensor(timestep):
+            t = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
+        else:
+            t = torch.tensor([float(timestep)], device=dev, dtype=torch.float32)
+        if t.numel() == 1:
+            t = t.expand(B).contiguous()
+        tp = self.time_proj
+        emb = self.time_embedding.run(eng, eng.timestep_embedding(t, tp.num_channels, tp.flip_sin_to_cos,
+                                                                  tp.downscale_freq_shift))
+        temb_silu = eng.silu_f32(emb)
+        resnets = [m for m in self.modules() if isinstance(m, ResnetBlock3D)]
+        params = [p for r in resnets for p in (r.time_emb_proj.weight, r.time_emb_proj.bias)]
+
+        def build():
+            w = torch.cat([f32(r.time_emb_proj.weight, eng) for r in resnets], dim=0).contiguous()
+            b = torch.cat([f32(r.time_emb_proj.bias, eng) for r in resnets], dim=0).contiguous()
+            offs, o = {}, 0
+            for r in resnets:
+                n = r.time_emb_proj.weight.shape[0]
+                offs[id(r)] = (o, n)
+                o += n
+            return w, b, offs
+        w, b, offs = self._time_pack.get(eng, params, build)
+        return TimeProjections(eng.gemm(temb_silu, w, bias=b, dtype=torch.float32), offs)
+
     def spatial_blocks(self):
         """The 16 spatial transformer blocks in module order (what torch_dfs + isinstance finds)."""
         from .attention import TemporalBasicTransformerBlock
@@ -323,23 +371,19 @@ class UNet3DConditionModel(nn.Module):
         return UNet3DConditionOutput(sample=res)
 
     def forward_tokens(self, eng: Engine, x, timestep, encoder_hidden_states, audio_embedding, pose, full_mask, face_mask,
-                       body_mask, motion_scale, B: int, F: int, ref_index=None, shard=None):
+                       body_mask, motion_scale, B: int, F: int, ref_index=None, shard=None, time_proj=None):
         """Channels-last core: x (N,H,W,4), pose (N,H,W,320) or None -> (N,H,W,4) in the run dtype.
         ``shard`` (frame_shard.FrameShardGroup): x / pose / audio / masks hold only this rank's F frames of a window
-        whose k*F frames are spread over k ranks; the motion modules exchange rows with the peers."""
+        whose k*F frames are spread over k ranks; the motion modules exchange rows with the peers.
+        ``time_proj``: TimeProjections of this timestep computed by the caller (once per DDIM step)."""
         N, H, W, _ = x.shape
         dev = eng.device
-        # --- time embedding (unet_3d.py:481-502), float32 end to end
-        if torch.is_tensor(timestep):
-            t = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
-        else:
-            t = torch.tensor([float(timestep)], device=dev, dtype=torch.float32)
-        if t.numel() == 1:
-            t = t.expand(B).contiguous()
-        tp = self.time_proj
-        emb = self.time_embedding.run(eng, eng.timestep_embedding(t, tp.num_channels, tp.flip_sin_to_cos,
-                                                                  tp.downscale_freq_shift))
-        temb_silu = eng.silu_f32(emb)
+        down = 2 ** self.num_upsamplers
+        if H % down or W % down:
+            raise ValueError(f"latent size {H}x{W} must be divisible by {down} (the reference's upsample_size path for "
+                             "other sizes, unet_3d.py:458-475, is not implemented)")
+        # --- time embedding (unet_3d.py:481-502) and every resnet's time_emb_proj, float32 end to end
+        temb_silu = time_proj.rows(B) if time_proj is not None else self.time_projections(eng, timestep, B)
         # --- conditioning
         if ref_index is None:
             ctl = getattr(self, "_reference_control", None)

@@ -30,9 +30,11 @@ class _Lib:
 
 
 class FakeEngine:
-    def __init__(self, fuse_audio: bool = True, interleaved_geglu: bool = True):
+    def __init__(self, fuse_audio: bool = True, interleaved_geglu: bool = True, ln_fused: bool = False):
         self.device = torch.device("cpu")
         self.dtype = torch.float32
+        self.subpixel_upsample = ln_fused   # and the sub-pixel form of Upsample3D (packing.subpixel_pack)
+        self.ln_fused = ln_fused        # exercise the host's LayerNorm folding (packing.ln_fold) against plain LayerNorm
         self.ctx, self.lib, self.h, self.prof = _Ctx(), _Lib(), None, None
         self.unfused_exchange = False
         self.fuse_audio, self.interleaved_geglu = fuse_audio, interleaved_geglu
@@ -79,12 +81,26 @@ class FakeEngine:
         return y.contiguous()
 
     # ------------------------------------------------------------------ gemm / conv
+    def row_stats(self, x, eps=1e-5):
+        self._count("row_stats")
+        x2 = x.reshape(-1, x.shape[-1]).float()
+        mean = x2.mean(dim=1)
+        var = x2.var(dim=1, unbiased=False)
+        return torch.stack([mean, torch.rsqrt(var + eps)], dim=1).contiguous()
+
+    def pad_channels(self, x, c_pad):
+        out = torch.zeros(tuple(x.shape[:-1]) + (c_pad,), dtype=x.dtype)
+        out[..., : x.shape[-1]] = x
+        return out
+
     def gemm(self, A, W, bias=None, rowscale=None, rowbias=None, rows_per_group=0, residual=None, alpha=1.0, geglu_block=0,
-             out=None, out_f32=False, dtype=None, exchange=None):
+             out=None, out_f32=False, dtype=None, exchange=None, rowbias_mod=0, rowstats=None, colsum=None, act=0):
         self._count("gemm")
         K = A.shape[-1]
         a2 = A.reshape(-1, K).float()
         y = a2 @ W.float().t()
+        if rowstats is not None:
+            y = rowstats[:, 1:2] * (y - rowstats[:, 0:1] * colsum[None, :])
         if bias is not None:
             y = y + bias
         if geglu_block:
@@ -95,7 +111,14 @@ class FakeEngine:
             y = y * rowscale[:, None]
         y = y * alpha
         if rowbias is not None:
-            y = y + rowbias[torch.arange(y.shape[0]) // rows_per_group]
+            grp = torch.arange(y.shape[0]) // rows_per_group
+            if rowbias_mod:
+                grp = grp % rowbias_mod
+            y = y + rowbias[grp]
+        if act == 1:
+            y = F.silu(y)
+        elif act == 2:
+            y = F.relu(y)
         if residual is not None:
             y = y + residual.reshape(y.shape)
         if exchange is not None:
@@ -107,14 +130,35 @@ class FakeEngine:
             return out
         return y
 
-    def conv3x3(self, x, w_krsc, bias=None, rowbias=None, frames_per_group=0, residual=None, stride=1, upsample2x=False):
+    def conv3x3(self, x, w_krsc, bias=None, rowbias=None, frames_per_group=0, residual=None, stride=1, upsample2x=False,
+                w_subpixel=None, act=0):
         self._count("conv3x3")
         xin = x.float().permute(0, 3, 1, 2)
-        if upsample2x:
-            xin = F.interpolate(xin, scale_factor=2.0, mode="nearest")
-        y = F.conv2d(xin, w_krsc.float().permute(0, 3, 1, 2), bias, stride=stride, padding=1).permute(0, 2, 3, 1)
+        if upsample2x and w_subpixel is not None:
+            # the four 2x2-tap parity convolutions of mmgt_conv3x3 (w_subpixel layout: include/mmgt_b200.h)
+            N, Cin, H, W = xin.shape
+            y = torch.zeros(N, w_subpixel.shape[0], 2 * H, 2 * W)
+            xp = F.pad(xin, (1, 1, 1, 1))
+            for a in (0, 1):
+                for b in (0, 1):
+                    for ty in (0, 1):
+                        for tx in (0, 1):
+                            oy, ox = ty - (0 if a else 1), tx - (0 if b else 1)
+                            patch = xp[:, :, 1 + oy:1 + oy + H, 1 + ox:1 + ox + W]
+                            y[:, :, a::2, b::2] += torch.einsum("nchw,oc->nohw", patch, w_subpixel[:, 2 * a + b, ty, tx].float())
+            if bias is not None:
+                y = y + bias[None, :, None, None]
+            y = y.permute(0, 2, 3, 1)
+        else:
+            if upsample2x:
+                xin = F.interpolate(xin, scale_factor=2.0, mode="nearest")
+            y = F.conv2d(xin, w_krsc.float().permute(0, 3, 1, 2), bias, stride=stride, padding=1).permute(0, 2, 3, 1)
         if rowbias is not None:
             y = y + rowbias[torch.arange(y.shape[0]) // frames_per_group][:, None, None, :]
+        if act == 1:
+            y = F.silu(y)
+        elif act == 2:
+            y = F.relu(y)
         if residual is not None:
             y = y + residual
         return y.contiguous()

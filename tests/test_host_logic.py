@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/mmgt_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == syms, "ctypes SIGNATURES and the header disagree"
-    assert _lib.load_library().mmgt_abi_version() == 2
+    assert _lib.load_library().mmgt_abi_version() == 3
 
 
 def test_library_is_sm100a_tensor_core_code(lib_built):

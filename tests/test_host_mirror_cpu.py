@@ -37,9 +37,10 @@ def _forward(unet, eng, win, t, B, frames, shard=None):
     return y
 
 
-@pytest.mark.parametrize("fuse_audio,interleaved", [(True, True), (False, False)], ids=["fused-mmhaa", "per-region"])
+@pytest.mark.parametrize("fuse_audio,interleaved,ln_fused", [(True, True, True), (True, True, False), (False, False, False)],
+                         ids=["fused-mmhaa-foldedLN-subpixel", "fused-mmhaa", "per-region"])
 @pytest.mark.parametrize("branch", ["scripts", "eval"])
-def test_host_mirror_matches_reference_golden_on_cpu(fuse_audio, interleaved, branch):
+def test_host_mirror_matches_reference_golden_on_cpu(fuse_audio, interleaved, ln_fused, branch):
     """UNet3DConditionModel.forward_tokens on the fake engine vs the outputs of the reference's own modules."""
     g = np.load(os.path.join(GOLD, "unet_tiny.npz"))
     latent, frames, t = int(g["latent"]), int(g["frames"]), int(g["timestep"])
@@ -47,12 +48,14 @@ def test_host_mirror_matches_reference_golden_on_cpu(fuse_audio, interleaved, br
     inp = make_inputs(spec, frames, latent)
     attach_banks(unet, spec, make_banks(spec, latent), cfg=True)
     win = window_inputs(inp, list(range(frames)))
-    eng = FakeEngine(fuse_audio=fuse_audio, interleaved_geglu=interleaved)
+    eng = FakeEngine(fuse_audio=fuse_audio, interleaved_geglu=interleaved, ln_fused=ln_fused)
     y = _forward(unet, eng, win, t, 2, frames)
     out = eng.tokens_to_ncfhw(y, 2, frames, torch.float32)
     err = rel_l2(out, torch.from_numpy(g[f"out_{branch}"]))
     assert err < 2e-5, err
     assert (eng.calls.get("audio_attention", 0) > 0) == fuse_audio          # the fused three-region path really ran
+    # LayerNorm folded into the consuming GEMMs (row statistics only) vs LayerNorm passes
+    assert (eng.calls.get("row_stats", 0) > 0) == ln_fused and (eng.calls.get("layernorm", 0) == 0) == ln_fused
 
 
 def test_denoise_loop_and_pipeline_call_on_cpu(monkeypatch):
@@ -101,6 +104,218 @@ def test_denoise_loop_and_pipeline_call_on_cpu(monkeypatch):
                motion_scale=inp["motion_scale"], output_type="latent", clip_image_embeds=inp["encoder_hidden_states"][1],
                pose_fea=inp["pose_fea"], reference_banks=[banks[p] for p in bank_pairing_order(spec)], latents=inp["latents"])
     assert rel_l2(out.videos, refs[0]) < 2e-5
+
+
+class _Out:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class _StubClip(torch.nn.Module):
+    """CLIPVisionModelWithProjection stand-in: (1, 3, 224, 224) -> .image_embeds (1, 768)."""
+
+    def __init__(self):
+        super().__init__()
+        self.proj = torch.nn.Linear(3, 768)
+
+    @property
+    def dtype(self):
+        return self.proj.weight.dtype
+
+    def forward(self, pixel_values):
+        return _Out(image_embeds=self.proj(pixel_values.mean(dim=(2, 3))))
+
+
+class _StubVae(torch.nn.Module):
+    """AutoencoderKL stand-in: 8x average pool to 4 channels; records what it was asked to encode."""
+
+    def __init__(self):
+        super().__init__()
+        self.mix = torch.nn.Conv2d(3, 4, 1)
+        self.config = _Out(block_out_channels=[128, 256, 512, 512])
+        self.seen = None
+
+    @property
+    def dtype(self):
+        return self.mix.weight.dtype
+
+    @property
+    def device(self):
+        return self.mix.weight.device
+
+    def encode(self, x):
+        self.seen = x
+        return _Out(latent_dist=_Out(mean=torch.nn.functional.avg_pool2d(self.mix(x), 8)))
+
+
+class BasicTransformerBlock(torch.nn.Module):
+    """Named like the reference's 2-D block (attention.py:12): the write-mode controller finds it by name + norm1."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.norm1 = torch.nn.LayerNorm(dim)
+        self.lin = torch.nn.Linear(dim, dim)
+
+    def forward(self, hidden_states, encoder_hidden_states=None):
+        return hidden_states + self.lin(self.norm1(hidden_states))
+
+
+class _StubReferenceNet(torch.nn.Module):
+    """2-D UNet stand-in with the SD-1.5 transformer-block layout (widths / token counts of the denoising UNet's 16
+    spatial blocks, in module order down -> up -> mid like the reference's UNet2DConditionModel)."""
+
+    def __init__(self, layout):
+        super().__init__()
+        self.layout = layout                               # [(width, tokens)] in module order
+        self.inp = torch.nn.ModuleList([torch.nn.Linear(4, c) for c, _ in layout])
+        self.blocks = torch.nn.ModuleList([BasicTransformerBlock(c) for c, _ in layout])
+        self.calls = []
+
+    @property
+    def dtype(self):
+        return self.blocks[0].lin.weight.dtype
+
+    def forward(self, latents, timestep, encoder_hidden_states=None, return_dict=True):
+        self.calls.append((tuple(latents.shape), float(timestep), tuple(encoder_hidden_states.shape)))
+        B = latents.shape[0]
+        for (c, t), inp, blk in zip(self.layout, self.inp, self.blocks):
+            side = int(round(t ** 0.5))
+            x = torch.nn.functional.adaptive_avg_pool2d(latents, side).flatten(2).transpose(1, 2)      # (B, t, 4)
+            x = inp(x) + encoder_hidden_states.mean(dim=(1, 2)).view(B, 1, 1)                           # cond rows differ
+            blk(x, encoder_hidden_states=encoder_hidden_states)
+        return (latents,)
+
+
+class _StubPoseGuider(torch.nn.Module):
+    def __init__(self, width):
+        super().__init__()
+        self.conv = torch.nn.Conv3d(3, width, 1)
+        self.seen = None
+
+    @property
+    def dtype(self):
+        return self.conv.weight.dtype
+
+    def forward(self, cond):
+        self.seen = cond
+        B, C, L, H, W = cond.shape
+        y = torch.nn.functional.avg_pool3d(cond, (1, 8, 8))
+        return 0.1 * self.conv(y)
+
+
+def test_pipeline_call_with_the_reference_scripts_argument_list_on_cpu(monkeypatch):
+    """Pose2VideoPipeline.__call__ exactly as scripts/pose2vid.py:284-296 calls it -- PIL reference image, list of PIL pose
+    images, mask lists, zero audio -- with stub CLIP / VAE / ReferenceNet / PoseGuider modules: CLIP embedding, VAE
+    encode, ReferenceNet write pass (pre-hook banks), update(), pose features, CFG duplication and the loop, vs the
+    oracle loop fed with the same conditioning.  A second call (new reference image) must reuse the cached loop."""
+    from PIL import Image
+    from mmgt_b200.image_processor import VaeImageProcessor
+    from mmgt_b200.mutual_self_attention import _reader_blocks
+    from mmgt_b200.pipeline_pose2vid_long import Pose2VideoPipeline
+    from mmgt_b200.scheduling_ddim import DDIMSchedule
+    spec, sd, unet = _tiny_unet()
+    eng = FakeEngine()
+    monkeypatch.setattr(unet, "_engine", lambda device: eng)
+    L, latent, n_steps = 16, 8, 2
+    size = latent * 8
+    torch.manual_seed(5)
+    # reference-net layout = the reader blocks in MODULE order (the controllers sort both sides the same stable way)
+    readers_module_order = unet.spatial_blocks()
+    tok = {TINY[0]: latent ** 2, TINY[1]: (latent // 2) ** 2}
+    names = {id(m): n for n, m in unet.named_modules()}
+    layout = []
+    for b in readers_module_order:
+        c = b.norm1.normalized_shape[0]
+        n = names[id(b)]
+        if c in tok and c != TINY[2]:
+            t = tok[c]
+        else:   # widest level: 8x8 -> 2x2 at the third level, 1x1 at the mid block
+            t = (latent // 8) ** 2 if n.startswith("mid_block") else (latent // 4) ** 2
+        layout.append((c, t))
+    vae, clip, refnet, guider = _StubVae(), _StubClip(), _StubReferenceNet(layout), _StubPoseGuider(TINY[0])
+    pipe = Pose2VideoPipeline(vae=vae, image_encoder=clip, reference_unet=refnet, denoising_unet=unet, pose_guider=guider,
+                              scheduler=DDIMSchedule.from_config())
+    rng = np.random.default_rng(0)
+
+    def pil(seed_shift=0):
+        return Image.fromarray(rng.integers(0, 256, (size + 8 * seed_shift, size, 3), dtype=np.uint8), "RGB")
+    ref_image, pose_list = pil(1), [pil() for _ in range(L)]        # the reference image gets resized to (size, size)
+    inp = make_inputs(spec, L, latent, seed=3)
+    cond = lambda ms: [m[L:] for m in ms]   # noqa: E731  (the cond half = what a script passes before CFG duplication)
+    gen = torch.Generator().manual_seed(42)
+    zero_audio = torch.zeros(1, L, 32, 768)
+
+    def call(image):
+        return pipe(ref_image=image, pose_images=pose_list, audio_tensor=zero_audio,
+                    pixel_values_full_mask=cond(inp["full_mask"]), pixel_values_face_mask=cond(inp["face_mask"]),
+                    pixel_values_lip_mask=cond(inp["lip_mask"]), width=size, height=size, video_length=L,
+                    num_inference_steps=n_steps, guidance_scale=3.5, generator=gen, motion_scale=[1.0, 1.0, 2.0],
+                    output_type="latent").videos
+
+    def expected(image, latents0):
+        """The same conditioning computed by hand, pushed through the oracle loop."""
+        with torch.no_grad():
+            from transformers import CLIPImageProcessor
+            px = CLIPImageProcessor().preprocess(image.resize((224, 224)), return_tensors="pt").pixel_values
+            e = clip(px).image_embeds.unsqueeze(1)
+            ehs = torch.cat([torch.zeros_like(e), e])
+            ref = VaeImageProcessor(8, do_convert_rgb=True).preprocess(image, height=size, width=size)
+            ref_lat = vae.encode(ref).latent_dist.mean * 0.18215
+            feats = []
+            for (c, t), inp_l, blk in zip(refnet.layout, refnet.inp, refnet.blocks):
+                side = int(round(t ** 0.5))
+                x = torch.nn.functional.adaptive_avg_pool2d(ref_lat.repeat(2, 1, 1, 1), side).flatten(2).transpose(1, 2)
+                feats.append(blk.norm1(inp_l(x) + ehs.mean(dim=(1, 2)).view(2, 1, 1)).half().float())
+            # pair like the controllers: both sides stable-sorted by descending width
+            order = sorted(range(len(feats)), key=lambda i: -layout[i][0])
+            sorted_readers = _reader_blocks(unet, "full")
+            banks = {}
+            for i, r in zip(order, sorted_readers):
+                banks[names[id(r)].replace(".transformer_blocks.0", "")] = feats[i]
+            poses = torch.cat([VaeImageProcessor(8, do_convert_rgb=True, do_normalize=False)
+                               .preprocess(p, height=size, width=size).unsqueeze(2) for p in pose_list], dim=2)
+            pose_fea = guider(poses)
+        dup = lambda ms: [torch.cat([m, m]) for m in cond(ms)]   # noqa: E731
+        audio = torch.cat([zero_audio, zero_audio])
+
+        def unet_fn(sample, t, ehs_, aud, pose, full, face, lip, ms):
+            with torch.no_grad():
+                return unet3d_forward(sd, spec, sample, t, ehs_, aud, pose, full, face, lip, ms, banks, ref_index=[None, 1],
+                                      apply_motion_scale=True)
+        ddim, lat = DDIM(), latents0.clone()
+        for t in ddim.timesteps(n_steps):
+            lat, _ = denoise_step(unet_fn, lat, t, n_steps, ddim, 3.5, uniform_windows(0, L), pose_fea, audio,
+                                  dup(inp["full_mask"]), dup(inp["face_mask"]), dup(inp["lip_mask"]), ehs, [1.0, 1.0, 2.0])
+        return lat
+    lat0 = torch.randn((1, 4, L, latent, latent), generator=torch.Generator().manual_seed(42))
+    out1 = call(ref_image)
+    assert tuple(vae.seen.shape) == (1, 3, size, size) and float(vae.seen.min()) < 0        # resized, normalised to [-1, 1]
+    assert tuple(guider.seen.shape) == (1, 3, L, size, size) and float(guider.seen.min()) >= 0
+    assert refnet.calls == [((2, 4, latent, latent), 0.0, (2, 1, 768))]
+    assert all(len(b.bank) == 0 for b in refnet.blocks) and not any(b._forward_pre_hooks for b in refnet.blocks)
+    assert rel_l2(out1, expected(ref_image, lat0)) < 2e-5
+    # second video of the same shape, another reference image: the cached loop is reloaded (new banks, new CLIP vector)
+    ref2 = pil(2)
+    lat1 = torch.randn((1, 4, L, latent, latent), generator=gen.manual_seed(7))
+    gen.manual_seed(7)
+    assert len(pipe._loops) == 1
+    loop = next(iter(pipe._loops.values()))
+    out2 = call(ref2)
+    assert len(pipe._loops) == 1 and next(iter(pipe._loops.values())) is loop
+    assert rel_l2(out2, expected(ref2, lat1)) < 2e-5
+    with pytest.raises(NotImplementedError):
+        pipe(ref_image, pose_list, zero_audio, [], [], [], size, size, L, n_steps, 3.5, eta=0.5)
+
+
+def test_interpolate_latents_matches_the_reference_recipe():
+    from mmgt_b200.pipeline_pose2vid_long import Pose2VideoPipeline
+    pipe = Pose2VideoPipeline(None, None, None, None, None, None)
+    x = torch.randn(1, 4, 5, 3, 3)
+    assert pipe.interpolate_latents(x, 1) is x
+    y = pipe.interpolate_latents(x, 3)
+    assert y.shape[2] == 4 * 3 + 1
+    assert torch.equal(y[:, :, 0], x[:, :, 0]) and torch.equal(y[:, :, -1], x[:, :, -1]) and torch.equal(y[:, :, 3], x[:, :, 1])
+    assert torch.allclose(y[:, :, 4], (1 - 1 / 3) * x[:, :, 1] + (1 / 3) * x[:, :, 2])
 
 
 @pytest.mark.parametrize("k", [2, 4])
