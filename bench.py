@@ -27,6 +27,12 @@ import torch  # noqa: E402
 VIDEO_LENGTH, LATENT, N_STEPS, GUIDANCE = 80, 64, 30, 3.5
 FLOP_PER_UNIT = 31.595e12 / 2       # algorithmic FLOPs of one (window, CFG-branch) forward, SURVEY section 8d (B=2 window / 2)
 UNITS_PER_STEP = 20
+# BASELINE.json configs (1-based like SURVEY section 8d).  2 / 3 = the headline (N = 1 / N > 1); 4 = one independent
+# audio2vid clip per GPU (replicas, non-zero audio); 5 = 768x768, 160 frames (20 windows, 86.67 TFLOP per window forward).
+CONFIGS = {2: dict(frames=80, latent=64, flop_per_unit=31.595e12 / 2, name="pose2vid 512x512 (64x64 latent), 80 frames"),
+           4: dict(frames=80, latent=64, flop_per_unit=31.595e12 / 2,
+                   name="audio2vid 512x512 (64x64 latent), one independent 80-frame clip per GPU, non-zero audio tokens"),
+           5: dict(frames=160, latent=96, flop_per_unit=86.67e12 / 2, name="long video 768x768 (96x96 latent), 160 frames")}
 
 
 def log(*a):
@@ -101,9 +107,9 @@ def build_unet(device, compute_dtype):
     return unet
 
 
-def synthetic_video(L, latent, pinned=True):
+def synthetic_video(L, latent, pinned=True, seed=42):
     """Host-side (pinned) whole-video inputs in the layout Pose2VideoPipeline holds before the loop."""
-    g = torch.Generator().manual_seed(42)
+    g = torch.Generator().manual_seed(seed)
     pin = (lambda t: t.pin_memory()) if pinned and torch.cuda.is_available() else (lambda t: t)
     latents = pin(torch.randn(1, 4, L, latent, latent, generator=g))
     clip = torch.randn(1, 1, 768, generator=g)
@@ -157,8 +163,7 @@ def _describe(world, shards, remainder, loop):
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch.distributed as dist
-    from mmgt_b200.mutual_self_attention import ReferenceAttentionControl
-    from mmgt_b200.pipeline_pose2vid_long import DenoiseLoop
+    from mmgt_b200.pipeline_pose2vid_long import DenoiseLoop, Pose2VideoPipeline
     from mmgt_b200.scheduling_ddim import DDIMSchedule
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -170,78 +175,103 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    L = args.frames
+    conf = CONFIGS[args.config]
+    L = args.frames or conf["frames"]
+    latent = conf["latent"]
+    replicas = args.config == 4            # one independent clip per GPU: no data-path collective at all
     t0 = time.time()
     unet = build_unet(dev, cdt)
-    host = synthetic_video(L, LATENT)
+    host = synthetic_video(L, latent, seed=42 + (rank if replicas else 0))
+    host2 = synthetic_video(L, latent, seed=1042 + (rank if replicas else 0))    # the NEXT video (another reference image)
     log(f"[rank {rank}] model + inputs built in {time.time() - t0:.1f}s")
-    ctl = ReferenceAttentionControl(unet, do_classifier_free_guidance=True, mode="read", fusion_blocks="full")
-    ctl.set_banks([b.to(dev) for b in host["banks"]])
     sched = DDIMSchedule.from_config()
 
     # Schedule.  Default ("auto"): whole windows (B=2), then single-branch forwards, dealt evenly to the ranks; forwards that
     # still do not divide (10 windows on 8 GPUs: one window each, 4 forwards left) are shared by pairs of ranks as frame
     # shards (2.5 forwards of work per rank instead of 3 / 2).
+    loop_world, loop_rank = (1, 0) if replicas else (world, rank)
     shards, remainder = args.frame_shards, args.shard_remainder
+    from mmgt_b200.context import get_context_scheduler
+    n_windows = len(list(get_context_scheduler("uniform")(0, N_STEPS, L, 12, 1, 4)))
+    units_per_step = 2 * n_windows
     if shards == 0:
-        from mmgt_b200.context import get_context_scheduler
         from mmgt_b200.pipeline_pose2vid_long import plan_units_mixed
-        n_windows = len(list(get_context_scheduler("uniform")(0, N_STEPS, L, 12, 1, 4)))
         shards, remainder = 1, False
-        if world % 2 == 0 and any(plan_units_mixed(n_windows, 2, world, 2)[1]):
+        if loop_world % 2 == 0 and any(plan_units_mixed(n_windows, 2, loop_world, 2)[1]):
             shards, remainder = 2, True
-    if world % shards:
-        raise SystemExit(f"bench.py: --frame-shards {shards} must divide the number of ranks {world}")
-    shared = {"shards": shards, "remainder": remainder}
+    if loop_world % shards:
+        raise SystemExit(f"bench.py: --frame-shards {shards} must divide the number of ranks {loop_world}")
 
-    def make_loop(d):
-        for attempt in range(2):
-            loop = DenoiseLoop(unet, sched, N_STEPS, GUIDANCE, motion_scale=[1.0, 1.0, 2.0], rank=rank, world_size=world,
-                               frame_shards=shared["shards"], shard_group=shared.get("group"),
-                               shard_remainder=shared["remainder"])
-            try:
-                loop.prepare(d["latents"], d["pose"], d["audio"], d["full"], d["face"], d["lip"], d["ehs"])
-            except RuntimeError as e:
-                if attempt == 0 and args.frame_shards == 0 and "peer memory" in str(e):   # raised on every rank together
-                    log(f"[rank {rank}] {e}; falling back to whole forwards only")
-                    shared.update(shards=1, remainder=False)
-                    continue
-                raise
-            shared["group"] = loop.shard_group        # one set of peer buffers serves every loop of this process
-            return loop
-
-    torch.cuda.synchronize()
-    t_first0 = time.perf_counter()
-    d = to_device(host, dev)
-    loop = make_loop(d)
-    eng = loop.eng
+    # Everything goes through the reference-facing plugin call, Pose2VideoPipeline.__call__ (output_type="latent": the VAE
+    # is out of the hot path).  The one-shot conditioning passes (CLIP, VAE encode, ReferenceNet, PoseGuider) are outside the
+    # metric: their results are handed in as HOST tensors through the optional keyword arguments.
+    pipe = Pose2VideoPipeline(vae=None, image_encoder=None, reference_unet=None, denoising_unet=unet, pose_guider=None,
+                              scheduler=sched)
+    pipe.rank, pipe.world_size, pipe.process_group = loop_rank, loop_world, None
+    pipe.frame_shards, pipe.shard_remainder = shards, remainder
+    pipe.use_cuda_graph = not args.no_graph
+    eng = unet._engine(dev)
     if args.no_tc:
         eng.ctx.set_tensor_cores(False)
+    if args.strict:
+        eng.ctx.set_strict_tensor_cores(True)
     eng.unfused_exchange = args.unfused_exchange
     if args.pdl is not None:
         eng.ctx.set_pdl(bool(args.pdl))
-    if not args.no_graph:
-        t0 = time.time()
-        loop.capture_graph()
-        log(f"[rank {rank}] CUDA graph of one step captured in {time.time() - t0:.1f}s ({loop.graph_launches} kernel launches)")
-    torch.cuda.synchronize()
-    first_video_prepare_s = time.perf_counter() - t_first0      # one-off per process and video shape (includes graph capture)
+    for name, setter in (("gn_split", eng.ctx.set_groupnorm_split), ("conv_implicit", eng.ctx.set_conv_implicit_all),
+                         ("geglu_exact", eng.ctx.set_geglu_exact)):
+        v = getattr(args, name)
+        if v is not None:
+            setter(bool(v))
+    if args.fuse_ln is not None:
+        eng.fuse_layernorm = bool(args.fuse_ln)
+
+    def call_pipeline(h, steps, callback=None):
+        cond = lambda ms: [m[:L] for m in ms]   # noqa: E731  (the pipeline duplicates the masks for CFG itself)
+        return pipe(ref_image=None, pose_images=None, audio_tensor=h["audio"][1:2], pixel_values_full_mask=cond(h["full"]),
+                    pixel_values_face_mask=cond(h["face"]), pixel_values_lip_mask=cond(h["lip"]), width=latent * 8,
+                    height=latent * 8, video_length=L, num_inference_steps=steps, guidance_scale=GUIDANCE,
+                    motion_scale=[1.0, 1.0, 2.0], output_type="latent", callback=callback, callback_steps=1,
+                    clip_image_embeds=h["ehs"][1], reference_banks=h["banks"], pose_fea=h["pose"], latents=h["latents"]).videos
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- first video: builds the weight packs, projects the reference banks, captures the CUDA graph of one DDIM step
+    torch.cuda.synchronize()
+    t_first0 = time.perf_counter()
+    for attempt in range(2):
+        try:
+            first = call_pipeline(host, 2 if args.ncu_step else N_STEPS)   # (a profiling run only needs the captured loop)
+            break
+        except RuntimeError as e:
+            if attempt == 0 and args.frame_shards == 0 and "peer memory" in str(e):   # raised on every rank together
+                log(f"[rank {rank}] {e}; falling back to whole forwards only")
+                pipe.frame_shards, pipe.shard_remainder = 1, False
+                shards, remainder = 1, False
+                continue
+            raise
+    torch.cuda.synchronize()
+    first_video_s = time.perf_counter() - t_first0      # one-off per process and video shape (packs, graph capture) + 30 steps
+    loop = next(iter(pipe._loops.values()))
+    assert torch.isfinite(first).all(), "non-finite latents after the first video"
+    log(f"[rank {rank}] first video through Pose2VideoPipeline.__call__: {first_video_s:.1f}s "
+        f"({loop.graph_launches} kernel launches per DDIM step in the graph)")
+
     # ---- device-resident timing: W warm-up + K timed steps, CUDA events, max over ranks
+    d = to_device(host, dev)
+    loop.reload(d["latents"], d["pose"], d["audio"], d["full"], d["face"], d["lip"], d["ehs"])
     for i in range(args.warmup):
-        loop.step(i % N_STEPS)
+        loop.step(i % len(loop.timesteps))
     barrier()
     if args.ncu_step:
         # `ncu --profile-from-start off --metrics gpu__time_duration.sum ... python bench.py --ncu-step`: exactly one DDIM
         # step (eager launches) between cudaProfilerStart / Stop -> the launch list under profiles/; prints no bench line.
         graph, loop._graph = loop._graph, None
         torch.cuda.cudart().cudaProfilerStart()
-        loop.step(args.warmup % N_STEPS)
+        loop.step(args.warmup % len(loop.timesteps))
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         loop._graph = graph
@@ -249,7 +279,7 @@ def run_ours(args):
         return
     sampler = ClockSampler(local)
     sampler.start()
-    n0 = eng.ctx.launches()
+    n0, s0 = eng.ctx.launches(), eng.ctx.simt_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -262,35 +292,73 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms) / args.steps
-    value = L / (N_STEPS * ms_per_step / 1e3)
+    n_videos = world if replicas else 1
+    value = n_videos * L / (N_STEPS * ms_per_step / 1e3)
 
-    # ---- end-to-end through the public loop API with HOST buffers: a NEW video of the same shape.  Its conditioning is
-    #      uploaded from pinned host memory and written into the loop's static buffers (DenoiseLoop.reload: the CUDA graph
-    #      captured for the first video keeps serving) -- timed and amortised over the 30 steps; every step then does the
-    #      H2D copy of the latents and the D2H read of the updated latents.
-    barrier()
-    t_prep0 = time.perf_counter()
-    d2 = to_device(host, dev)
-    loop2 = loop.reload(d2["latents"], d2["pose"], d2["audio"], d2["full"], d2["face"], d2["lip"], d2["ehs"])
-    torch.cuda.synchronize()
-    prep_s = time.perf_counter() - t_prep0
-    lat_host = host["latents"]
-    out_host = torch.empty_like(lat_host).pin_memory()
-    e_steps = max(1, min(args.steps, 3))
+    # ---- parity of the multi-GPU schedule, asserted in the run itself: two DDIM steps from the same latents through the
+    #      distributed loop (every rank ends with the same latents after the all-reduce) and, on rank 0, through a local
+    #      single-GPU loop that runs all 20 forwards of a step as whole B=2 windows.
+    parity = None
+    if world > 1 and not replicas:
+        loop.latents.copy_(d["latents"])
+        for i in (3, 17):
+            loop.step(i)
+        lat_dist = loop.latents.clone()
+        if rank == 0:
+            solo = DenoiseLoop(unet, sched, N_STEPS, GUIDANCE, motion_scale=[1.0, 1.0, 2.0])
+            solo.prepare(d["latents"], d["pose"], d["audio"], d["full"], d["face"], d["lip"], d["ehs"])
+            for i in (3, 17):
+                solo.step(i)
+            torch.cuda.synchronize()
+            err = float((lat_dist.double() - solo.latents.double()).norm() / solo.latents.double().norm())
+            parity = dict(latents_rel_l2_vs_n1=err, steps=2, tolerance=1e-2,
+                          what="2 DDIM steps: this run's schedule over all ranks vs all 20 forwards on rank 0 alone")
+            del solo
+        barrier()
+        flag = torch.tensor([0.0 if parity is None or parity["latents_rel_l2_vs_n1"] < 1e-2 else 1.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if float(flag) != 0.0:
+            raise SystemExit(f"bench.py: multi-GPU latents differ from the single-GPU result: {parity}")
+    elif loop._graph is not None:
+        # N = 1: the graph replay against the same two steps launched eagerly (must be bit-identical)
+        loop.latents.copy_(d["latents"])
+        for i in (3, 17):
+            loop.step(i)
+        lat_graph = loop.latents.clone()
+        graph, loop._graph = loop._graph, None
+        loop.latents.copy_(d["latents"])
+        for i in (3, 17):
+            loop.step(i)
+        loop._graph = graph
+        err = float((lat_graph.double() - loop.latents.double()).norm() / loop.latents.double().norm())
+        parity = dict(latents_rel_l2_graph_vs_eager=err, steps=2,
+                      vs_reference="tests/test_config2_gpu.py: this workload's shapes against the reference's own modules "
+                                   "(tests/golden/config2_step.npz)")
+
+    # ---- end-to-end through the plugin call with HOST buffers: a NEW video (other latents, reference banks, CLIP vector,
+    #      pose, audio, masks, all in pinned host memory) through Pose2VideoPipeline.__call__.  Inside the timed region:
+    #      the H2D upload of the conditioning and its re-layout into the loop's static buffers, the re-projection of the
+    #      reference banks, all 30 DDIM steps (CUDA-graph replays), a D2H read of the latents after EVERY step (callback)
+    #      and of the final result.
+    out_host = torch.empty_like(host2["latents"]).pin_memory()
+    n_cb = [0]
+
+    def on_step(i, t, lat):
+        out_host.copy_(lat, non_blocking=True)
+        n_cb[0] += 1
     barrier()
     t_e0 = time.perf_counter()
-    for i in range(e_steps):
-        loop2.latents.copy_(lat_host, non_blocking=True)
-        loop2.step(i % N_STEPS)
-        out_host.copy_(loop2.latents, non_blocking=True)
-        torch.cuda.synchronize()
-    e2e_step = (time.perf_counter() - t_e0) / e_steps
-    e2e_t = torch.tensor([e2e_step + prep_s / N_STEPS], device=dev)
+    res = call_pipeline(host2, N_STEPS, callback=on_step)
+    out_host.copy_(res, non_blocking=True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t_e0
+    assert n_cb[0] == N_STEPS and len(pipe._loops) == 1, "the second video must reuse the captured loop"
+    e2e_t = torch.tensor([e2e_s], device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = L / (N_STEPS * float(e2e_t))
-    lat_bytes = lat_host.numel() * 4
-    del d2
+    e2e_value = n_videos * L / float(e2e_t)
+    lat_bytes = host2["latents"].numel() * 4
+    cond_bytes = h2d_bytes(host2) + sum(b.numel() * b.element_size() for b in host2["banks"])
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launch stream over one more step
     roof = None
@@ -338,40 +406,57 @@ def run_ours(args):
             roof = dict(bound="hbm", kernel=str(key), achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
                         traffic=traffic, peak_source=pk["src"], launches=r["calls"], avg_launch_ms=tms / r["calls"],
                         share_of_step=tms / tot)
-        whole = UNITS_PER_STEP * (L / 80.0) * FLOP_PER_UNIT / (ms_per_step * 1e-3) / 1e12 / world
+        whole = units_per_step * conf["flop_per_unit"] * n_videos / (ms_per_step * 1e-3) / 1e12 / world
         roof["whole_step_tflops_per_gpu"] = whole
         roof["whole_step_frac_of_peak"] = whole / pk["tf_sustained"]
 
-    if shared.get("group") is not None:
-        shared["group"].check()                   # raises if any peer barrier timed out during the run
+    if loop.shard_group is not None:
+        loop.shard_group.check()                   # raises if any peer barrier timed out during the run
+    simt = eng.ctx.simt_launches() - s0
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 2:
         cpu = cpu_reference(unet, steps=1, warmup=0, budget_s=args.cpu_budget)
 
     if rank == 0:
-        line = dict(metric="UNet3D denoise frames/s @512x512 80f (30-step CFG DDIM, 10 windows x 12 frames)", value=value,
+        metric = "UNet3D denoise frames/s @512x512 80f (30-step CFG DDIM, 10 windows x 12 frames)"
+        if args.config != 2:
+            metric = f"UNet3D denoise frames/s, BASELINE config {args.config}: {conf['name']} (30-step CFG DDIM, {n_windows} windows x 12 frames)"
+        line = dict(metric=metric, value=value,
                     unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
-                    higher_is_better=True, scaling="strong", vs_baseline=None, dtype=args.dtype, data="synthetic",
-                    config=dict(workload=f"pose2vid 512x512 (64x64 latent), {L} frames, 30 DDIM steps, CFG 3.5, full-width "
-                                         "UNet3D random-init; step = 1 DDIM step = 10 windows x 2 CFG branches",
-                                parallelism=_describe(world, shared["shards"], shared["remainder"], loop),
+                    higher_is_better=True, scaling="weak" if replicas else "strong", vs_baseline=None, dtype=args.dtype,
+                    data="synthetic",
+                    config=dict(workload=f"{conf['name']}, {L} frames, 30 DDIM steps, CFG 3.5, full-width UNet3D random-init, "
+                                         f"non-zero audio tokens and three motion masks; step = 1 DDIM step = {n_windows} "
+                                         f"windows x 2 CFG branches" + (" per clip, one clip per GPU" if replicas else ""),
+                                baseline_config=args.config,
+                                parallelism=("independent replicas: one clip per GPU, no collective" if replicas else
+                                             _describe(world, shards, remainder, loop)),
                                 l2_policy="per-step working set (weights 2.8 GB + activations) exceeds the 126 MB L2",
-                                tensor_cores=not args.no_tc, programmatic_dependent_launch=eng.ctx.pdl()),
-                    clocks=clocks, gpu_launches=launches,
-                    e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=lat_bytes + h2d_bytes(host) // N_STEPS,
-                             d2h_bytes_per_step=lat_bytes, prepare_s=prep_s, step_s=e2e_step,
-                             first_video_prepare_s=first_video_prepare_s),
-                    roofline=roof, cpu_baseline=cpu, frame_evals_per_s=UNITS_PER_STEP * 12 * (L / 80.0) / (ms_per_step / 1e3))
+                                tensor_cores=not args.no_tc, strict_tensor_cores=bool(args.strict),
+                                programmatic_dependent_launch=eng.ctx.pdl(), layernorm_in_gemm_epilogue=eng.ln_fused,
+                                psnr_note="parity / PSNR are asserted on LATENTS (tests/): the VAE is outside the hot path"),
+                    clocks=clocks, gpu_launches=launches, simt_launches=simt,
+                    e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=(lat_bytes + cond_bytes) // N_STEPS,
+                             d2h_bytes_per_step=lat_bytes + lat_bytes // N_STEPS, video_s=float(e2e_t),
+                             through="Pose2VideoPipeline.__call__(output_type='latent') on a new video with pinned host "
+                                     "inputs: conditioning upload + reload + 30 graph-replayed DDIM steps + per-step D2H",
+                             first_video_s=first_video_s),
+                    parity=parity, roofline=roof, cpu_baseline=cpu,
+                    frame_evals_per_s=n_videos * units_per_step * 12 / (ms_per_step / 1e3))
         print(json.dumps(line), flush=True)
+    pipe.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------ CPU arm (oracle port)
 def cpu_reference(unet_or_none, steps, warmup, budget_s):
-    """Times the oracle (CPU restatement of the reference algorithm, plain PyTorch fp32) on the host cores.
+    """Times the reference algorithm on the host cores (all of them, float32): the reference's OWN modules
+    (/root/reference/src/models/*.py imported unchanged through oracle/reference_loader.py) where the checkout exists
+    (kind "reference"), else the oracle port (kind "port": the GPU box has no /root/reference).
     One sample = one (window, CFG-branch) forward of config 2: B=1, F=12, 64x64 latent; 600 of them make a video."""
-    from oracle.unet3d import UNetSpec, unet3d_forward, spatial_block_prefixes, spatial_block_width
+    from oracle import reference_loader as RL
+    from oracle.unet3d import UNetSpec, bank_pairing_order, unet3d_forward, spatial_block_prefixes, spatial_block_width
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     spec = UNetSpec()
@@ -389,39 +474,73 @@ def cpu_reference(unet_or_none, steps, warmup, budget_s):
         c = spatial_block_width(spec, pre)
         lvl = {320: 0, 640: 1}.get(c, 3 if pre.startswith("mid") else 2)
         banks[pre] = torch.randn(2, (lat >> lvl) ** 2, c, generator=g).half().float()
+    kind = "port"
+
+    def unit():
+        return unet3d_forward(sd, spec, sample, 500, ehs, aud, pose, masks[0], masks[1], masks[2], [1.0, 1.0, 2.0], banks,
+                              ref_index=[1], apply_motion_scale=True)
+    if RL.reference_available():
+        try:
+            ref_unet, mods = RL.build_reference_unet()
+            ref_unet.load_state_dict(sd, strict=True)
+            msa, attn_mod = mods["mutual_self_attention"], mods["attention"]
+            msa.ReferenceAttentionControl(ref_unet, do_classifier_free_guidance=False, mode="read", batch_size=1,
+                                          fusion_blocks="full")
+            blocks = sorted([m for m in msa.torch_dfs(ref_unet) if isinstance(m, attn_mod.TemporalBasicTransformerBlock)],
+                            key=lambda m: -m.norm1.normalized_shape[0])
+            for blk, pre in zip(blocks, bank_pairing_order(spec)):
+                blk.bank = [banks[pre][1:2].clone()]
+            ref_unet.train()
+            ref_unet.enable_gradient_checkpointing()        # the scripts' branch (scripts/pose2vid.py:151-156,183-184)
+            kind = "reference"
+
+            def unit():   # noqa: F811
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    return ref_unet(sample, torch.tensor(500), encoder_hidden_states=ehs, audio_embedding=aud, pose_cond_fea=pose,
+                                    full_mask=masks[0], face_mask=masks[1], body_mask=masks[2], motion_scale=[1.0, 1.0, 2.0],
+                                    return_dict=False)[0]
+        except Exception as e:   # noqa: BLE001
+            log(f"[cpu] reference modules not usable here ({type(e).__name__}: {e}); timing the oracle port")
+            kind = "port"
     times = []
     t_start = time.perf_counter()
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            unet3d_forward(sd, spec, sample, 500, ehs, aud, pose, masks[0], masks[1], masks[2], [1.0, 1.0, 2.0], banks,
-                           ref_index=[1], apply_motion_scale=True)
+            unit()
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-            log(f"[cpu] unit forward {i}: {dt:.1f}s")
+            log(f"[cpu:{kind}] unit forward {i}: {dt:.1f}s")
             if time.perf_counter() - t_start > budget_s and times:
                 break
     t_unit = sum(times) / len(times)
     units_per_video = N_STEPS * UNITS_PER_STEP
-    return dict(value=VIDEO_LENGTH / (units_per_video * t_unit), unit="frames/s", cores=cores, kind="port",
+    return dict(value=VIDEO_LENGTH / (units_per_video * t_unit), unit="frames/s", cores=cores, kind=kind,
                 sample=f"{len(times)} x one (window, CFG-branch) UNet3D forward of the same workload (B=1, 12 frames, 64x64 "
                        f"latent, fp32) = 1/{units_per_video} of the 30-step video, extrapolated; {t_unit:.1f}s each",
                 seconds_per_unit=t_unit, steps_done=len(times))
 
 
 def run_reference(args):
+    """The CPU arm.  One STEP of this arm = one bounded sample = ONE (window, CFG-branch) UNet3D forward (1/20 of a DDIM
+    step of the workload, 1/600 of the video): `steps` and `ms_per_step` are both in that unit, `value` extrapolates
+    frames/s = 80 / (600 x seconds per sample)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cpu = cpu_reference(None, steps=args.steps, warmup=min(args.warmup, 1), budget_s=args.cpu_budget)
-    t_step = cpu["seconds_per_unit"] * UNITS_PER_STEP
     line = dict(impl="reference", metric="UNet3D denoise frames/s @512x512 80f (30-step CFG DDIM, 10 windows x 12 frames)",
                 value=cpu["value"], unit="frames/s", n_gpus=int(os.environ.get("WORLD_SIZE", "1")), steps=cpu["steps_done"],
-                warmup=min(args.warmup, 1), ms_per_step=t_step * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
-                dtype="f32", data="synthetic",
+                warmup=min(args.warmup, 1), ms_per_step=cpu["seconds_per_unit"] * 1e3, higher_is_better=True, scaling="strong",
+                vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload="pose2vid 512x512 (64x64 latent), 80 frames, 30 DDIM steps, CFG 3.5, full-width UNet3D "
-                                     "random-init; CPU arm times a bounded sample (one window x one CFG branch) and extrapolates"),
+                                     "random-init; CPU arm: one step = one bounded sample = one (window, CFG-branch) forward "
+                                     "= 1/20 of a DDIM step; value extrapolates x600",
+                            step_is="one (window, CFG-branch) UNet3D forward (1/20 DDIM step)",
+                            ddim_step_ms_extrapolated=cpu["seconds_per_unit"] * UNITS_PER_STEP * 1e3),
                 cpu_baseline=cpu, e2e=dict(value=cpu["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -433,7 +552,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
-    ap.add_argument("--frames", type=int, default=VIDEO_LENGTH)
+    ap.add_argument("--frames", type=int, default=0, help="video length (default: the config's)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="BASELINE.json config (1-based): 2 = headline (3 = the same at N > 1), 4 = one independent audio2vid "
+                         "clip per GPU, 5 = 768x768 / 160 frames")
+    ap.add_argument("--strict", action="store_true",
+                    help="strict tensor-core mode: a bf16 operator without a tcgen05 kernel is an error, not a CUDA-core fallback")
+    ap.add_argument("--gn-split", type=int, default=None, help="A/B: 1 / 0 two-kernel / fused spin-barrier GroupNorm")
+    ap.add_argument("--conv-implicit", type=int, default=None, help="A/B: 1 / 0 implicit-GEMM / im2col stride-2 + upsample convs")
+    ap.add_argument("--geglu-exact", type=int, default=None, help="A/B: 1 = erf GELU in the GEGLU epilogue")
+    ap.add_argument("--fuse-ln", type=int, default=None, help="A/B: 1 / 0 LayerNorm in the GEMM epilogue / as its own pass")
     ap.add_argument("--no-tc", action="store_true", help="debug: CUDA-core kernels only")
     ap.add_argument("--no-graph", action="store_true", help="debug: eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -1,9 +1,11 @@
-"""torchrun --nproc-per-node 2 tests/multigpu_frame_shard.py  (one process per GPU, NCCL + CUDA IPC peer memory)
+"""torchrun --nproc-per-node N tests/multigpu_frame_shard.py  (N = 2, 4 or 8: one process per GPU, NCCL + CUDA IPC peer memory)
 
-Two DDIM steps of a 20-frame video (3 overlapping windows, CFG) with every window's frames split over the two
-GPUs (DenoiseLoop(frame_shards=2)): the motion modules exchange rows through peer stores from the GEMM epilogue.
-Checked on every rank against the oracle's denoise loop (north-star tolerances) and against the window-parallel
-schedule (frame_shards=1) of the same two ranks.  Prints FRAME-SHARD PARITY OK on rank 0."""
+Two DDIM steps of a short video (CFG, overlapping windows) under every schedule DenoiseLoop / bench.py can pick at N ranks:
+every window as k frame shards (k = 2, 4 where it divides: the motion modules exchange rows through peer stores from
+the GEMM epilogue), whole forwards dealt over the ranks, and the mixed "whole + leftovers shared by pairs" schedule
+(bench.py's default at 4 and 8 GPUs).  Checked on every rank against the oracle's denoise loop (north-star tolerances)
+and against each other.  Prints FRAME-SHARD PARITY OK on rank 0.  Collected by pytest through
+tests/test_frame_shard_gpu.py::test_multi_gpu_schedules_match_oracle."""
 import os
 import sys
 
@@ -29,7 +31,8 @@ def main():
     from mmgt_b200.scheduling_ddim import DDIMSchedule
     spec = UNetSpec(block_out_channels=TINY)
     sd = synthetic_state_dict("tiny")
-    L, latent, n_steps = 20, 16, 30
+    # 20 frames = 3 windows (6 forwards); 44 frames = 6 windows: on 8 ranks 12 forwards = 1 each + 4 shared by the 4 pairs
+    L, latent, n_steps = (20 if world <= 4 else 44), 16, 30
     inp = make_inputs(spec, L, latent, seed=11)
     banks = make_banks(spec, latent)
     windows = uniform_windows(0, L)
@@ -52,7 +55,8 @@ def main():
         attach_banks(unet, spec, banks, cfg=True)
         d = to_dev(inp, dev)
         res = {}
-        for shards in (world, 1):
+        shard_opts = [k for k in (2, 4) if world % k == 0] + [1]
+        for shards in shard_opts:
             loop = DenoiseLoop(unet, DDIMSchedule.from_config(), n_steps, 3.5, motion_scale=inp["motion_scale"], rank=rank,
                                world_size=world, frame_shards=shards)
             loop.prepare(d["latents"], d["pose_fea"], d["audio"], d["full_mask"], d["face_mask"], d["lip_mask"],
@@ -69,9 +73,28 @@ def main():
             ok = ok and err < tol
             if loop.shard_group is not None:
                 loop.shard_group.close()
-        diff = rel_l2(res[world], res[1])
-        print(f"[rank {rank}] {dtype}: frame-sharded vs window-parallel rel-L2 {diff:.3e}", flush=True)
-        ok = ok and diff < (1e-5 if dtype == torch.float32 else 5e-3)
+        for k in shard_opts[:-1]:
+            diff = rel_l2(res[k], res[1])
+            print(f"[rank {rank}] {dtype}: {k} frame shards vs window-parallel rel-L2 {diff:.3e}", flush=True)
+            ok = ok and diff < (1e-5 if dtype == torch.float32 else 5e-3)
+        # the CFG schedule bench.py picks by default at this world size (plan_units_mixed: whole forwards + leftovers
+        # shared by pairs), through the CUDA graph in bf16
+        loop = DenoiseLoop(unet, DDIMSchedule.from_config(), n_steps, 3.5, motion_scale=inp["motion_scale"], rank=rank,
+                           world_size=world, frame_shards=2, shard_remainder=True)
+        loop.prepare(d["latents"], d["pose_fea"], d["audio"], d["full_mask"], d["face_mask"], d["lip_mask"],
+                     d["encoder_hidden_states"])
+        if dtype == torch.bfloat16:
+            loop.capture_graph()
+        loop.step(0)
+        lat = loop.step(1).clone()
+        n_shared = sum(1 for _, _, sh in loop.units if sh)
+        err = rel_l2(lat, lat_ref)
+        print(f"[rank {rank}] {dtype} default mixed schedule ({len(loop.units) - n_shared} whole + {n_shared} shared units on "
+              f"this rank): latents rel-L2 vs oracle {err:.3e} (tol {tol})", flush=True)
+        ok = ok and err < tol
+        if loop.shard_group is not None:
+            loop.shard_group.check()
+        loop.close()
         # Mixed schedule (what bench.py uses when the forwards do not divide over the ranks): without CFG the 3 windows
         # are 3 forwards for 2 ranks -> one whole forward each + one shared as two frame shards; vs all-whole dealing.
         attach_banks(unet, spec, banks, cfg=False)
@@ -80,10 +103,10 @@ def main():
         mixed = {}
         for remainder in (True, False):
             loop = DenoiseLoop(unet, DDIMSchedule.from_config(), n_steps, 1.0, motion_scale=inp["motion_scale"], rank=rank,
-                               world_size=world, frame_shards=world if remainder else 1, shard_remainder=remainder)
+                               world_size=world, frame_shards=2 if remainder else 1, shard_remainder=remainder)
             loop.prepare(d["latents"], d["pose_fea"], nocfg["audio"], nocfg["masks"][0], nocfg["masks"][1], nocfg["masks"][2],
                          nocfg["ehs"])
-            if remainder:
+            if remainder and world == 2:
                 assert sorted(sh for _, _, sh in loop.units) == [False, True], loop.units
             if dtype == torch.bfloat16:
                 loop.capture_graph()

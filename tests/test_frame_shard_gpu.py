@@ -264,13 +264,15 @@ def test_tiny_unet_frame_sharded_matches_unsharded(dev, compute_dtype, k):
     torch.cuda.empty_cache()
 
 
-def test_two_gpu_denoise_step_frame_sharded():
-    """One process per GPU, CUDA IPC + NVLink peer stores: tests/multigpu_frame_shard.py under torchrun."""
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs (run: gpurun --gpus 2 -- python -m pytest tests/test_frame_shard_gpu.py -m gpu)")
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_multi_gpu_schedules_match_oracle(n):
+    """One process per GPU, CUDA IPC + NVLink peer stores: tests/multigpu_frame_shard.py under torchrun on n GPUs (every
+    schedule of DenoiseLoop at that world size vs the oracle loop).  Skipped when fewer GPUs are visible."""
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs (run: gpurun --gpus {n} -- python -m pytest tests/test_frame_shard_gpu.py -m gpu -k multi_gpu)")
     here = os.path.dirname(os.path.abspath(__file__))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(29600 + os.getpid() % 300), os.path.join(here, "multigpu_frame_shard.py")]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + (os.getpid() + n) % 300), os.path.join(here, "multigpu_frame_shard.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     print(r.stdout[-4000:], r.stderr[-4000:])
     assert r.returncode == 0

@@ -201,12 +201,17 @@ def test_gemm_geglu_fast_erf_accuracy(dev):
     bias = torch.zeros(8 * C, device=dev)
     gb = eng.geglu_block(8 * C)
     Wi, bi = geglu_interleave(W.to(torch.bfloat16), bias, gb)
-    out = eng.gemm(A, Wi.contiguous(), bias=bi.contiguous(), geglu_block=gb).float()
     g = A[:, 1].float()
     ref = F.gelu(g)[:, None].expand(M, 4 * C)
-    err = (out - ref).abs()
-    assert float((err / (ref.abs() + 1e-3)).max()) < 6e-3      # bf16 output rounding (2^-8) dominates
-    assert float(err.max()) < 2e-2
+    try:
+        for exact in (False, True):     # default: logistic-polynomial fit of Phi (<= 8.2e-4 relative); flag 6: erf form
+            eng.ctx.set_geglu_exact(exact)
+            out = eng.gemm(A, Wi.contiguous(), bias=bi.contiguous(), geglu_block=gb).float()
+            err = (out - ref).abs()
+            assert float((err / (ref.abs() + 1e-3)).max()) < 6e-3      # bf16 output rounding (2^-8) dominates
+            assert float(err.max()) < 2e-2
+    finally:
+        eng.ctx.set_geglu_exact(False)
 
 
 def test_gemm_strided_views_and_f32_vectors(dev):
@@ -230,7 +235,13 @@ CONV_CASES = [  # N, H, W, Cin, Cout, stride, upsample
     (2, 16, 16, 4, 64, 1, 0), (2, 16, 16, 64, 4, 1, 0), (3, 16, 16, 320, 320, 1, 0), (2, 8, 8, 1920, 640, 1, 0),
     # widths no run of 128 consecutive rows covers (config 5: 96 / 48 / 24 / 12 latents): patch tiles pw x ph x frames
     (2, 96, 96, 64, 64, 1, 0), (1, 48, 48, 128, 64, 1, 0), (3, 24, 24, 64, 128, 1, 0), (5, 12, 12, 128, 128, 1, 0),
-    (3, 6, 6, 256, 256, 1, 0), (2, 24, 48, 64, 64, 1, 0)]
+    (3, 6, 6, 256, 256, 1, 0), (2, 24, 48, 64, 64, 1, 0),
+    # Downsample3D / Upsample3D at the model's shapes and at the config-5 widths: implicit GEMM on the tensor-core tier
+    # (TMA traversal stride 2; four 2x2-tap sub-pixel convolutions), im2col / CUDA cores otherwise
+    (2, 64, 64, 320, 320, 2, 0), (3, 32, 32, 640, 640, 2, 0), (3, 16, 16, 1280, 1280, 2, 0), (2, 8, 8, 1280, 1280, 1, 1),
+    (1, 16, 16, 1280, 1280, 1, 1), (2, 32, 32, 640, 640, 1, 1), (1, 96, 96, 64, 64, 2, 0), (2, 48, 48, 64, 128, 2, 0),
+    (3, 24, 24, 64, 64, 2, 0), (2, 12, 12, 128, 64, 1, 1), (1, 24, 24, 64, 64, 1, 1), (5, 4, 4, 256, 128, 1, 1),
+    (3, 4, 4, 128, 128, 2, 0)]
 
 
 @pytest.mark.parametrize("dtype,tc", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)],
@@ -253,12 +264,169 @@ def test_conv3x3_fused_epilogue(dev, dtype, tc, case):
         ref = ref + rb.repeat_interleave(fpg, 0)[:, :, None, None]
         res = rnd(*ref.permute(0, 2, 3, 1).shape, dev=dev, dtype=dtype, seed=45)
         ref = ref.permute(0, 2, 3, 1) + res.float()
+        wsp = None
+        if up and eng.subpixel_upsample:
+            from mmgt_b200.packing import subpixel_pack
+            wsp = subpixel_pack(w, eng)
+        n_simt = eng.ctx.simt_launches()
         out = eng.conv3x3(x, w.permute(0, 2, 3, 1).contiguous(), bias=bias, rowbias=rb, frames_per_group=fpg, residual=res,
-                          stride=stride, upsample2x=bool(up))
+                          stride=stride, upsample2x=bool(up), w_subpixel=wsp)
         assert out.shape == ref.shape
         assert rel_l2(out.float(), ref) < (1e-5 if dtype == torch.float32 else 8e-3)
+        if tc and Cin % 64 == 0 and Cout % 32 == 0:
+            assert eng.ctx.simt_launches() == n_simt, "a tensor-core shape fell back to the CUDA-core kernel"
+            if stride == 2 or up:      # implicit GEMM vs the staged im2col form of the same operator
+                eng.ctx.set_conv_implicit_all(False)
+                staged = eng.conv3x3(x, w.permute(0, 2, 3, 1).contiguous(), bias=bias, rowbias=rb, frames_per_group=fpg,
+                                     residual=res, stride=stride, upsample2x=bool(up))
+                eng.ctx.set_conv_implicit_all(True)
+                assert rel_l2(out.float(), staged.float()) < 6e-3
     finally:
         eng.ctx.set_tensor_cores(True)
+        eng.ctx.set_conv_implicit_all(True)
+
+
+@pytest.mark.parametrize("dtype,tc", [(torch.float32, False), (torch.bfloat16, True)], ids=["f32", "bf16tc"])
+@pytest.mark.parametrize("act", [1, 2])
+def test_conv_and_gemm_activation_epilogue_and_rowbias_slices(dev, dtype, tc, act):
+    """SiLU / ReLU epilogue (pose_guider.py:47-57, audio_proj.py:96) and row-bias taken as a column slice of a wider
+    matrix (one time-embedding projection for all resnets)."""
+    eng = eng_for(dev, dtype)
+    eng.ctx.set_tensor_cores(tc)
+    fn = F.silu if act == 1 else F.relu
+    tol = 1e-5 if dtype == torch.float32 else 8e-3
+    try:
+        N, H, W, Cin, Cout = 4, 16, 16, 64, 128
+        x = rnd(N, H, W, Cin, dev=dev, dtype=dtype, seed=1)
+        w = rnd(Cout, Cin, 3, 3, dev=dev, dtype=dtype, seed=2, scale=(9 * Cin) ** -0.5)
+        bias = rnd(Cout, dev=dev, seed=3)
+        wide = rnd(2, 3 * Cout + 64, dev=dev, seed=4)                # (B, total) float32: this conv owns columns [64, 64 + Cout)
+        rb = wide[:, 64:64 + Cout]
+        res = rnd(N, H, W, Cout, dev=dev, dtype=dtype, seed=5)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1) + rb.repeat_interleave(2, 0)[:, :, None, None]
+        ref = fn(ref).permute(0, 2, 3, 1) + res.float()
+        out = eng.conv3x3(x, w.permute(0, 2, 3, 1).contiguous(), bias=bias, rowbias=rb, frames_per_group=2, residual=res, act=act)
+        assert rel_l2(out.float(), ref) < tol
+        M, Nn, K = 1000, 256, 192
+        A = rnd(M, K, dev=dev, dtype=dtype, seed=6)
+        Wg = rnd(Nn, K, dev=dev, dtype=dtype, seed=7, scale=K ** -0.5)
+        bg = rnd(Nn, dev=dev, seed=8)
+        wide2 = rnd(5, Nn + 32, dev=dev, seed=9)
+        rb2 = wide2[:, 32:]
+        r2 = rnd(M, Nn, dev=dev, dtype=dtype, seed=10)
+        grp = (torch.arange(M, device=dev) // 100) % 5
+        refg = fn(A.float() @ Wg.float().t() + bg + rb2[grp]) + r2.float()
+        outg = eng.gemm(A, Wg, bias=bg, rowbias=rb2, rows_per_group=100, rowbias_mod=5, residual=r2, act=act)
+        assert rel_l2(outg.float(), refg) < tol
+    finally:
+        eng.ctx.set_tensor_cores(True)
+
+
+@pytest.mark.parametrize("dtype,tc", [(torch.float32, False), (torch.bfloat16, True)], ids=["f32", "bf16tc"])
+@pytest.mark.parametrize("C,N", [(320, 960), (640, 1920), (1280, 3840), (64, 192), (320, 2560)])
+def test_layernorm_folded_into_gemm(dev, dtype, tc, C, N):
+    """row_stats + GEMM epilogue (rowstats / colsum, packing.ln_fold) == LayerNorm -> Linear, also with the motion module's
+    positional table as a per-frame row bias and through the GEGLU epilogue (attention.py:331-362, motion_module.py:365)."""
+    from mmgt_b200.packing import geglu_interleave, ln_fold
+    eng = eng_for(dev, dtype)
+    eng.ctx.set_tensor_cores(tc)
+    try:
+        Fr, T = 3, 211
+        M = 2 * Fr * T
+        x = rnd(M, C, dev=dev, dtype=dtype, seed=7) * 2 + 0.7                  # non-zero row means
+        g, b = rnd(C, dev=dev, seed=8) * 0.2 + 1, rnd(C, dev=dev, seed=9) * 0.2
+        W = rnd(N, C, dev=dev, seed=10, scale=C ** -0.5)
+        bias = rnd(N, dev=dev, seed=11)
+        ln = F.layer_norm(x.float(), (C,), g, b, 1e-5)
+        st = eng.row_stats(x, 1e-5)
+        assert rel_l2(st[:, 0], x.float().mean(1)) < 1e-5 and rel_l2(st[:, 1], torch.rsqrt(x.float().var(1, unbiased=False) + 1e-5)) < 1e-4
+        wp, colsum, bp = ln_fold(W, bias, g, b, eng)
+        tol = 2e-5 if dtype == torch.float32 else 8e-3
+        out = eng.gemm(x, wp, bias=bp, rowstats=st, colsum=colsum)
+        ref = ln @ W.to(dtype).float().t() + bias
+        assert rel_l2(out.float(), ref) < tol
+        # + positional table through the projection, added per frame (rows ordered (b, f, t))
+        pe = rnd(32, C, dev=dev, seed=12)
+        tab = (pe.double() @ W.double().t()).float().contiguous()
+        frame = (torch.arange(M, device=dev) // T) % Fr
+        out = eng.gemm(x, wp, bias=bp, rowstats=st, colsum=colsum, rowbias=tab[:Fr], rows_per_group=T, rowbias_mod=Fr)
+        assert rel_l2(out.float(), (ln + pe[frame]) @ W.to(dtype).float().t() + bias) < tol
+        if N % 32 == 0:
+            gb = eng.geglu_block(N)
+            Wi, bi = geglu_interleave(W, bias, gb)
+            wpi, csi, bpi = ln_fold(Wi.contiguous(), bi.contiguous(), g, b, eng)
+            outg = eng.gemm(x, wpi, bias=bpi, geglu_block=gb, rowstats=st, colsum=csi)
+            full = ln @ W.to(dtype).float().t() + bias
+            refg = full[:, : N // 2] * F.gelu(full[:, N // 2:])
+            assert rel_l2(outg.float(), refg) < (5e-5 if dtype == torch.float32 else 1e-2)
+    finally:
+        eng.ctx.set_tensor_cores(True)
+
+
+def test_strict_tensor_core_mode_and_simt_counter(dev):
+    """A bf16 shape no tcgen05 kernel covers runs on CUDA cores and is COUNTED; in strict mode it is an error."""
+    from mmgt_b200._lib import MmgtError
+    eng = eng_for(dev, torch.bfloat16)
+    A = rnd(300, 72, dev=dev, dtype=torch.bfloat16, seed=1)
+    W = rnd(100, 72, dev=dev, dtype=torch.bfloat16, seed=2)            # N = 100: no tensor-core tile width divides it
+    n0 = eng.ctx.simt_launches()
+    out = eng.gemm(A, W)
+    assert eng.ctx.simt_launches() == n0 + 1
+    assert rel_l2(out.float(), A.float() @ W.float().t()) < 8e-3
+    ok = eng.gemm(rnd(300, 64, dev=dev, dtype=torch.bfloat16, seed=3), rnd(128, 64, dev=dev, dtype=torch.bfloat16, seed=4))
+    assert eng.ctx.simt_launches() == n0 + 1 and ok.shape == (300, 128)
+    eng.ctx.set_strict_tensor_cores(True)
+    try:
+        with pytest.raises(MmgtError, match="strict"):
+            eng.gemm(A, W)
+        x = rnd(2, 8, 8, 4, dev=dev, dtype=torch.bfloat16, seed=5)     # Cin = 4: not a tensor-core convolution
+        with pytest.raises(MmgtError, match="strict"):
+            eng.conv3x3(x, rnd(64, 3, 3, 4, dev=dev, dtype=torch.bfloat16, seed=6))
+        q = rnd(2, 16, 64, dev=dev, dtype=torch.bfloat16, seed=7)      # Lq = 16 < 64: CUDA-core attention
+        with pytest.raises(MmgtError, match="strict"):
+            eng.attention(q, q, q, 8)
+        v = rnd(2, 1280, dev=dev, seed=8)                              # batch-sized float32 vectors are CUDA-core by design
+        assert eng.gemm(v, rnd(320, 1280, dev=dev, seed=9), dtype=torch.float32).shape == (2, 320)
+    finally:
+        eng.ctx.set_strict_tensor_cores(False)
+
+
+def test_conv_in_padded_to_tensor_core_width(dev):
+    """InflatedConv3d(4 -> C): input channels zero-padded to 64 so conv_in runs as a tensor-core implicit GEMM."""
+    from mmgt_b200.resnet import InflatedConv3d
+    eng = eng_for(dev, torch.bfloat16)
+    conv = InflatedConv3d(4, 320, kernel_size=3, padding=(1, 1)).to(dev)
+    x = rnd(6, 32, 32, 4, dev=dev, dtype=torch.bfloat16, seed=1)
+    pose = rnd(6, 32, 32, 320, dev=dev, dtype=torch.bfloat16, seed=2)
+    n0 = eng.ctx.simt_launches()
+    out = conv.run(eng, x, residual=pose)
+    assert eng.ctx.simt_launches() == n0
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), conv.weight.to(torch.bfloat16).float(), conv.bias, padding=1)
+    assert rel_l2(out.float(), ref.permute(0, 2, 3, 1) + pose.float()) < 8e-3
+
+
+@pytest.mark.parametrize("shape", [(24, 4096, 320, 0), (24, 1024, 640, 0), (24, 256, 1280, 1280), (24, 64, 1280, 0),
+                                   (3, 4096, 640, 320), (5, 9216, 320, 0)])
+def test_groupnorm_split_kernels_match_fused_kernel(dev, shape):
+    """The default two-kernel GroupNorm (statistics, normalise) against the single spin-barrier kernel and torch, at the
+    model's shapes (config 2 levels 0-3, a skip concat, a 96x96 config-5 frame)."""
+    N, T, C1, C2 = shape
+    eng = eng_for(dev, torch.bfloat16)
+    x1 = rnd(N, T, C1, dev=dev, dtype=torch.bfloat16, seed=1) * 1.5 + 0.3
+    x2 = rnd(N, T, C2, dev=dev, dtype=torch.bfloat16, seed=2) if C2 else None
+    C = C1 + C2
+    g, b = rnd(C, dev=dev, seed=3) * 0.1 + 1, rnd(C, dev=dev, seed=4) * 0.1
+    xf = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], dim=-1)
+    ref = F.silu(F.group_norm(xf.transpose(1, 2), 32, g, b, 1e-5).transpose(1, 2))
+    outs = []
+    try:
+        for split in (True, False):
+            eng.ctx.set_groupnorm_split(split)
+            outs.append(eng.groupnorm(x1, x2, g, b, 32, 1e-5, True))
+    finally:
+        eng.ctx.set_groupnorm_split(True)
+    assert rel_l2(outs[0].float(), ref) < 5e-3 and rel_l2(outs[1].float(), ref) < 5e-3
+    assert rel_l2(outs[0].float(), outs[1].float()) < 3e-3
 
 
 def _attn_ref(q, k, v, heads):
