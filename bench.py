@@ -219,7 +219,7 @@ def run_ours(args):
     if args.pdl is not None:
         eng.ctx.set_pdl(bool(args.pdl))
     for name, setter in (("gn_split", eng.ctx.set_groupnorm_split), ("conv_implicit", eng.ctx.set_conv_implicit_all),
-                         ("geglu_exact", eng.ctx.set_geglu_exact)):
+                         ("geglu_exact", eng.ctx.set_geglu_exact), ("attn_v2", eng.ctx.set_attention_v2)):
         v = getattr(args, name)
         if v is not None:
             setter(bool(v))
@@ -561,6 +561,7 @@ def main():
     ap.add_argument("--gn-split", type=int, default=None, help="A/B: 1 / 0 two-kernel / fused spin-barrier GroupNorm")
     ap.add_argument("--conv-implicit", type=int, default=None, help="A/B: 1 / 0 implicit-GEMM / im2col stride-2 + upsample convs")
     ap.add_argument("--geglu-exact", type=int, default=None, help="A/B: 1 = erf GELU in the GEGLU epilogue")
+    ap.add_argument("--attn-v2", type=int, default=None, help="A/B: 1 / 0 three-S-buffer / round-1 attention kernel (head dim <= 64)")
     ap.add_argument("--fuse-ln", type=int, default=None, help="A/B: 1 / 0 LayerNorm in the GEMM epilogue / as its own pass")
     ap.add_argument("--no-tc", action="store_true", help="debug: CUDA-core kernels only")
     ap.add_argument("--no-graph", action="store_true", help="debug: eager launches instead of one CUDA graph per step")

@@ -63,7 +63,9 @@ MMGT_API const char* mmgt_last_error(void);
  * flag 7: GroupNorm as two kernels, statistics then normalise (default 1); 0 = the single kernel with a per-frame
  *         arrival barrier (grid limited to co-resident CTAs).  A/B switch.
  * flag 8: stride-2 and upsampling 3x3 convolutions as implicit GEMMs (TMA traversal stride 2; four sub-pixel 2x2-tap
- *         convolutions) (default 1); 0 = stage an im2col matrix and run the plain GEMM.  A/B switch. */
+ *         convolutions) (default 1); 0 = stage an im2col matrix and run the plain GEMM.  A/B switch.
+ * flag 9: head dim <= 64 attention on the kernel with three rotating S buffers and P aliased over S (default 1);
+ *         0 = the two-buffer kernel of round 1.  A/B switch. */
 MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);
 
 /* Layout ------------------------------------------------------------------------------------- */

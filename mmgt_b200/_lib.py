@@ -181,5 +181,8 @@ class Context:
     def set_groupnorm_split(self, on: bool) -> bool:
         return bool(self.lib.mmgt_ctx_flag(self.handle, 7, 1 if on else 0))
 
+    def set_attention_v2(self, on: bool) -> bool:
+        return bool(self.lib.mmgt_ctx_flag(self.handle, 9, 1 if on else 0))
+
     def set_conv_implicit_all(self, on: bool) -> bool:
         return bool(self.lib.mmgt_ctx_flag(self.handle, 8, 1 if on else 0))

@@ -520,6 +520,317 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------- head dim <= 64, version 2
+// Same contract as attention_tc_kernel<1, 128>, restructured after the ncu source-level profile of that kernel at the
+// config-2 level-0 shape (profiles/r2_attention_v2.md): 23 % of all warp samples sat in the softmax groups' wait for
+// S = Q K^T.  With one S buffer per group QK(j+2) could only be issued once the group had pulled S(j) into registers
+// (three quarters into its tile), leaving ~1/4 tile of slack against the ~450-clock mbarrier -> MMA -> commit -> wake-up
+// latency.  Here S lives in THREE rotating 128-column buffers and P (bf16, 64 columns) is written back over the S buffer
+// it was computed from (the TMEM budget is exactly 3 x 128 + 2 x 64 = 512 columns): QK(j+3) is issued as soon as
+// PV(j) has retired, i.e. a HALF tile period before its softmax group asks for it.
+// The running-max bookkeeping is also simpler (smaller code: instruction-fetch stalls were 7 % of the samples): chunks
+// are scored against the reference maximum m_ref; when a chunk exceeds it by more than 2^8 (always on the first tile,
+// rarely later) the thread takes the exact row maximum of the tile from a second pass over S -- still in TMEM, because
+// the buffer is only released by writing P -- rescales l and the pending factor for O, and redoes the tile once.
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attention_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
+                      const __grid_constant__ CUtensorMap tmV2, const AttnArgs args) {
+  static_assert(BN == 128, "three 128-column S buffers + two 64-column O accumulators fill the 512 TMEM columns");
+  constexpr int DPAD = 64, KS = 4, VS = 3, NB = 3;
+  constexpr int Q_BYTES = BQ * DPAD * 2;
+  constexpr int KV_BYTES = BN * DPAD * 2;
+  constexpr int TM_O = NB * BN;                   // O accumulators at 384 / 448
+  constexpr uint32_t IDESC_QK = idesc_bf16(BN, false);
+  const int qk_steps = (args.d + 15) >> 4;
+  const uint32_t IDESC_PV = idesc_bf16(qk_steps << 4, true);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;
+  uint8_t* sV = sK + KS * KV_BYTES;
+  float* stats = reinterpret_cast<float*>(sV + VS * KV_BYTES);        // [128][2]: (m_ref, l) of group 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 2 * BQ);
+  uint64_t* q_full = bars;                     // 1
+  uint64_t* k_full = bars + 1;                 // KS
+  uint64_t* k_empty = k_full + KS;
+  uint64_t* v_full = k_empty + KS;             // VS
+  uint64_t* v_empty = v_full + VS;
+  uint64_t* s_full = v_empty + VS;             // NB: S(j) complete in buffer j % NB
+  uint64_t* p_full = s_full + NB;              // NB: P(j) written over it (4 warps arrive)
+  uint64_t* o_ready = p_full + NB;             // 2:  PV of the group's latest tile retired (O_g stable, buffer reusable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int b = 0; b < NB; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); }
+    mbar_init(&o_ready[0], 1); mbar_init(&o_ready[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue();
+
+  int seg2 = -1;
+  if (args.has_seg2) seg2 = args.seg2_index ? args.seg2_index[n] : 0;
+  const int tiles1 = (args.Lk + BN - 1) / BN;
+  const int tiles2 = seg2 >= 0 ? (args.Lk2 + BN - 1) / BN : 0;
+  const int num_tiles = tiles1 + tiles2;
+
+  if (threadIdx.x == 0) {
+    // ===================== TMA producer =====================
+    mbar_expect_tx(q_full, Q_BYTES);
+    tma_load_3d(sQ, &tmQ, q_full, 0, h, n * args.Lq + q0);
+    auto tile_row = [&](int j) { return j >= tiles1 ? seg2 * args.Lk2 + (j - tiles1) * BN : n * args.Lk + j * BN; };
+    auto load_k = [&](int j) {
+      const int st = j % KS;
+      mbar_wait(&k_empty[st], ((j / KS) & 1) ^ 1);
+      mbar_expect_tx(&k_full[st], KV_BYTES);
+      tma_load_3d(sK + st * KV_BYTES, j >= tiles1 ? &tmK2 : &tmK, &k_full[st], 0, h, tile_row(j));
+    };
+    auto load_v = [&](int j) {
+      const int st = j % VS;
+      mbar_wait(&v_empty[st], ((j / VS) & 1) ^ 1);
+      mbar_expect_tx(&v_full[st], KV_BYTES);
+      tma_load_3d(sV + st * KV_BYTES, j >= tiles1 ? &tmV2 : &tmV, &v_full[st], 0, h, tile_row(j));
+    };
+    // The MMA warp consumes K(0..2), then per tile j: V(j), K(j+3).  K(i+4) can be requested once QK(i) retired (early),
+    // V(i+3) once PV(i) did.
+    for (int j = 0; j < KS && j < num_tiles; ++j) load_k(j);
+    for (int j = 0; j < VS && j < num_tiles; ++j) load_v(j);
+    for (int i = 0; i < num_tiles; ++i) {
+      if (i + KS < num_tiles) load_k(i + KS);
+      if (i + VS < num_tiles) load_v(i + VS);
+    }
+  } else if (threadIdx.x == 32) {
+    // ===================== MMA issuer =====================
+    auto issue_qk = [&](int j) {
+      const int st = j % KS, b = j % NB;
+      mbar_wait(&k_full[st], (j / KS) & 1);
+      tc_fence_after();
+      const uint32_t tS = tmem_base + b * BN;
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + st * KV_BYTES);
+#pragma unroll
+      for (int k = 0; k < DPAD / 16; ++k)
+        if (k < qk_steps) umma(tS, desc_kmajor(aQ + k * 32), desc_kmajor(aK + k * 32), IDESC_QK, k != 0);
+      umma_commit(&k_empty[st]);
+      umma_commit(&s_full[b]);
+    };
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < NB && j < num_tiles; ++j) issue_qk(j);
+    for (int j = 0; j < num_tiles; ++j) {
+      const int st = j % VS, b = j % NB, g = j & 1;
+      mbar_wait(&v_full[st], (j / VS) & 1);
+      mbar_wait(&p_full[b], (j / NB) & 1);
+      tc_fence_after();
+      const uint32_t aV = smem_u32(sV + st * KV_BYTES);
+      const uint32_t tOg = tmem_base + TM_O + g * DPAD, tP = tmem_base + b * BN;
+#pragma unroll
+      for (int k = 0; k < BN / 16; ++k)   // A = P from TMEM: 16 keys = 8 packed columns per step; B = V, MN-major
+        umma_ts(tOg, tP + k * 8, desc_mnmajor(aV + k * 2048, BN * 128), IDESC_PV, ((j >> 1) | k) != 0);
+      umma_commit(&v_empty[st]);
+      umma_commit(&o_ready[g]);
+      if (j + NB < num_tiles) {
+        // QK(j + 3) overwrites the buffer PV(j) reads P from: issue it once PV(j) has retired (half a tile period before
+        // its softmax group needs it)
+        mbar_wait(&o_ready[g], (j >> 1) & 1);
+        issue_qk(j + NB);
+      }
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax groups / merge / epilogue =====================
+    const int g = (warp - 2) >> 2;                   // softmax group: tiles j = g, g+2, ...
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;            // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
+    const float c = args.scale_log2e;
+    float m_ref = -INFINITY;   // reference maximum the stored O_g / l are relative to (raw score units)
+    float l_run = 0.f;
+    const uint32_t tO = tmem_base + TM_O + g * DPAD + lane_addr;
+    int it = 0;
+
+    for (int j = g; j < num_tiles; j += 2, ++it) {
+      const bool second = j >= tiles1;
+      const int seg_len = second ? args.Lk2 : args.Lk;
+      const int k0 = (second ? (j - tiles1) : j) * BN;
+      const int valid = min(BN, seg_len - k0);       // keys of this tile that exist
+      const int b = j % NB;
+      const uint32_t tS = tmem_base + b * BN + lane_addr;
+      mbar_wait(&s_full[b], (j / NB) & 1);
+      tc_fence_after();
+      uint32_t pk[BN / 2];
+      float alpha_tile = 1.f;
+      float lsum[4];
+      bool exceeded = false;
+      auto process = [&]() {
+        lsum[0] = lsum[1] = lsum[2] = lsum[3] = 0.f;
+        const float mc = m_ref * c;
+        uint32_t sa[32], sb[32];
+        auto chunk = [&](uint32_t (&sc)[32], const int ci) {
+          if (valid < BN) {   // partial last tile of a segment: mask the keys that do not exist (warp-uniform branch)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (ci * 32 + i >= valid) sc[i] = 0xff800000u;   // -inf
+          }
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(sc[i + e]));
+          }
+          const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+          exceeded = exceeded || ((mx - m_ref) * c > RESCALE_THRESHOLD);   // true for the first tile (m_ref = -inf)
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sc[i]), c, -mc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sc[i + 1]), c, -mc));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(sc[i + 2]), c, -mc));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(sc[i + 3]), c, -mc));
+            pk[ci * 16 + i / 2] = pack_bf16(p0, p1);
+            pk[ci * 16 + i / 2 + 1] = pack_bf16(p2, p3);
+            lsum[0] += p0; lsum[1] += p1; lsum[2] += p2; lsum[3] += p3;
+          }
+        };
+        tmem_ld32(tS, sa);
+        tmem_ld_wait();
+        pin32(sa);
+#pragma unroll
+        for (int ci = 0; ci < BN / 32; ci += 2) {
+          tmem_ld32(tS + (ci + 1) * 32, sb);                        // in flight during chunk ci
+          chunk(sa, ci);
+          tmem_ld_wait();
+          pin32(sb);
+          if (ci + 2 < BN / 32) tmem_ld32(tS + (ci + 2) * 32, sa);  // in flight during chunk ci + 1
+          chunk(sb, ci + 1);
+          if (ci + 2 < BN / 32) {
+            tmem_ld_wait();
+            pin32(sa);
+          }
+        }
+      };
+      process();
+      if (__any_sync(0xffffffffu, exceeded)) {
+        // Rare after the first tile.  Exact row maximum of this tile from a second pass over S (still in TMEM), then the
+        // tile is redone against it; what the previous tiles accumulated (l, O) is rescaled by 2^((m_old - m_new) c).
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int ci = 0; ci < BN / 32; ++ci) {
+          uint32_t sa[32];
+          tmem_ld32(tS + ci * 32, sa);
+          tmem_ld_wait();
+          pin32(sa);
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (ci * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(sa[i]));
+        }
+        if ((mx - m_ref) * c > RESCALE_THRESHOLD) {      // (lanes whose row did not move keep their reference)
+          const float a = ex2_approx((m_ref - mx) * c);  // 0 the first time (m_ref = -inf)
+          m_ref = mx;
+          alpha_tile *= a;
+          l_run *= a;
+        }
+        process();                                       // every lane redoes the tile (warp-uniform TMEM loads)
+      }
+      l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+
+      if (it > 0) {
+        mbar_wait(&o_ready[g], (it - 1) & 1);   // this group's previous PV retired: O_g stable
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha_tile != 1.f)) {
+#pragma unroll
+          for (int cc = 0; cc < DPAD / 32; ++cc) {
+            uint32_t o[32];
+            tmem_ld32(tO + cc * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha_tile);
+            tmem_st32(tO + cc * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // P over the S buffer it came from: lane = query row, column = key pair
+#pragma unroll
+      for (int i = 0; i < BN / 64; ++i) tmem_st32(tS + i * 32, pk + i * 32);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+    }
+
+    // ---- merge the two groups and store O / l (only the first d columns are real)
+    if (it > 0) {
+      mbar_wait(&o_ready[g], (it - 1) & 1);
+      tc_fence_after();
+    }
+    if (g == 1) {
+      stats[2 * row] = m_ref;
+      stats[2 * row + 1] = l_run;
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 softmax warps
+    tc_fence_after();
+    if (g == 0) {
+      const float m1 = stats[2 * row], l1 = stats[2 * row + 1];
+      const bool has1 = num_tiles > 1;                 // group 1 processed at least one tile (uniform)
+      const float m = has1 ? fmaxf(m_ref, m1) : m_ref;
+      const float a0 = ex2_approx((m_ref - m) * c);
+      const float a1 = has1 ? ex2_approx((m1 - m) * c) : 0.f;
+      const float inv = 1.f / (l_run * a0 + (has1 ? l1 * a1 : 0.f));
+      const float w0 = a0 * inv, w1 = a1 * inv;
+      const int q = q0 + row;
+      bf16* orow = args.out + ((int64_t)n * args.Lq + q) * args.ldo + h * args.d;
+      const uint32_t tO0 = tmem_base + TM_O + lane_addr, tO1 = tO0 + DPAD;
+#pragma unroll
+      for (int cc = 0; cc < DPAD / 32; ++cc) {
+        if (cc * 32 < args.d) {
+          uint32_t o[32], o1[32];
+          tmem_ld32(tO0 + cc * 32, o);
+          if (has1) tmem_ld32(tO1 + cc * 32, o1);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(o[i]) * w0 + (has1 ? __uint_as_float(o1[i]) * w1 : 0.f);
+          if (q < args.Lq) {
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) {
+              const int col = cc * 32 + gg * 8;
+              if (col < args.d) {
+                uint4 val;
+                val.x = pack_bf16(f[gg * 8 + 0], f[gg * 8 + 1]);
+                val.y = pack_bf16(f[gg * 8 + 2], f[gg * 8 + 3]);
+                val.z = pack_bf16(f[gg * 8 + 4], f[gg * 8 + 5]);
+                val.w = pack_bf16(f[gg * 8 + 6], f[gg * 8 + 7]);
+                *reinterpret_cast<uint4*>(orow + col) = val;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -565,6 +876,16 @@ int launch_attn(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaS
   return 0;
 }
 
+int launch_attn64(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaStream_t st) {
+  constexpr int smem = BQ * 64 * 2 + (4 + 3) * 128 * 64 * 2 + BQ * 8 + 1024 + 256;
+  MMGT_CUDA_OK(mmgt_smem_optin(ctx, attention_tc64_kernel<128>, smem));
+  dim3 grid((a.Lq + BQ - 1) / BQ, a.heads, a.N);
+  MMGT_CUDA_OK(mmgt_launch(ctx, attention_tc64_kernel<128>, grid, dim3(NUM_THREADS), smem, st, maps[0], maps[1], maps[2], maps[3],
+                           maps[4], a));
+  MMGT_LAUNCH_OK(ctx);
+  return 0;
+}
+
 }  // namespace
 
 bool mmgt_attention_tc_supported(const mmgt_ctx* ctx, const mmgt_attention_params* p) {
@@ -597,7 +918,7 @@ int mmgt_attention_tc(mmgt_ctx* ctx, const mmgt_attention_params* p, cudaStream_
   a.seg2_index = p->seg2_index; a.has_seg2 = p->k2 != nullptr;
   a.out = (bf16*)p->out; a.ldo = p->ldo;
   a.scale_log2e = p->scale * 1.4426950408889634f;
-  if (dch == 1) return launch_attn<1, 128>(ctx, maps, a, st);
+  if (dch == 1) return ctx->attn_v2 ? launch_attn64(ctx, maps, a, st) : launch_attn<1, 128>(ctx, maps, a, st);
   if (dch == 2) return launch_attn<2, 128>(ctx, maps, a, st);
   return launch_attn<3, 64>(ctx, maps, a, st);
 }

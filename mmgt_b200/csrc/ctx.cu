@@ -37,6 +37,7 @@ extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
   c->geglu_exact = 0;
   c->gn_split = 1;
   c->conv_implicit_all = 1;
+  c->attn_v2 = 1;
   *out = c;
   return 0;
 }
@@ -66,6 +67,10 @@ extern "C" int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value) {
     return ctx->strict_tc;
   }
   if (flag == 5) return ctx->simt_launches;
+  if (flag == 9) {
+    if (value >= 0) ctx->attn_v2 = value ? 1 : 0;
+    return ctx->attn_v2;
+  }
   if (flag == 8) {
     if (value >= 0) ctx->conv_implicit_all = value ? 1 : 0;
     return ctx->conv_implicit_all;

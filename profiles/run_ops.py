@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 from mmgt_b200.kernels import get_engine  # noqa: E402
-from mmgt_b200.packing import geglu_interleave  # noqa: E402
+from mmgt_b200.packing import geglu_interleave, ln_fold, subpixel_pack  # noqa: E402
 
 
 def make_ops(eng, dev):
@@ -99,6 +99,28 @@ def make_ops(eng, dev):
     wc2 = rnd(1280, 3, 3, 1280, scale=0.02)
     ops["conv3x3_1280_1280"] = (lambda: eng.conv3x3(x4b, wc2, bias=b3, residual=x4b), 2.0 * M2 * 9 * 1280 * 1280,
                                 (3.0 * M2 * 1280 + 9 * 1280 * 1280) * 2)
+    # ---- round 2: LayerNorm folded into the consuming GEMM (row statistics + epilogue), strided / upsampling implicit convs
+    ops["row_stats_320"] = (lambda: eng.row_stats(a320, 1e-5), 0.0, 1.0 * M * 320 * 2)
+    wq_f = torch.randn(960, 320, generator=g) * 0.05
+    wq_ln, cs_ln, b_ln = ln_fold(wq_f, None, gam, bet, eng)
+    st320 = eng.row_stats(a320, 1e-5)
+    ops["gemm_960x320_lnfused"] = (lambda: eng.gemm(a320, wq_ln, bias=b_ln, rowstats=st320, colsum=cs_ln),
+                                   2.0 * M * 960 * 320, (M * 320 + M * 960) * 2.0)
+    w1_ln, cs1_ln, b1_ln = ln_fold(w1i.float(), b1i, gam, bet, eng)
+    ops["gemm_geglu_2560x320_lnfused"] = (lambda: eng.gemm(a320, w1_ln, bias=b1_ln, geglu_block=gb, rowstats=st320, colsum=cs1_ln),
+                                          2.0 * M * 2560 * 320, (M * 320 + M * 1280) * 2.0)
+    ops["conv3x3_320_320_stride2"] = (lambda: eng.conv3x3(x4, wc, bias=b, stride=2), 2.0 * (M // 4) * 9 * 320 * 320,
+                                      (M * 320 + (M // 4) * 320) * 2.0)
+    x32 = rnd(N, 32, 32, 640)
+    wc640 = torch.randn(640, 640, 3, 3, generator=g) * 0.02
+    wc640_k = wc640.permute(0, 2, 3, 1).to(dev, bf).contiguous()
+    wc640_sp = subpixel_pack(wc640, eng)
+    b640 = rnd(640, dtype=torch.float32)
+    ops["conv3x3_640_640_upsample2x"] = (lambda: eng.conv3x3(x32, wc640_k, bias=b640, upsample2x=True, w_subpixel=wc640_sp),
+                                         2.0 * M * 9 * 640 * 640, (N * 1024 * 640 + M * 640) * 2.0)
+    x4c = rnd(N, 64, 64, 640)
+    g640, be640 = rnd(640, dtype=torch.float32), rnd(640, dtype=torch.float32)
+    ops["groupnorm_640_silu_64x64"] = (lambda: eng.groupnorm(x4c, None, g640, be640, 32, 1e-5, True), 0.0, 2.0 * M * 640 * 2)
     # ---- temporal attention
     tq = rnd(M, 960)
     ops["temporal_attn_d40"] = (lambda: eng.temporal_attention(tq, 2, 12, T0, 8), 4.0 * 2 * T0 * 8 * 144 * 40,
@@ -111,10 +133,18 @@ def main():
     ap.add_argument("ops", nargs="*")
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--attn-v1", action="store_true", help="A/B: the round-1 two-buffer attention kernel for head dim <= 64")
+    ap.add_argument("--gn-fused", action="store_true", help="A/B: the round-1 single-kernel GroupNorm (spin barrier)")
+    ap.add_argument("--conv-im2col", action="store_true", help="A/B: stride-2 / upsampling convs through a staged im2col matrix")
+    ap.add_argument("--geglu-exact", action="store_true", help="A/B: erf GELU in the GEGLU epilogue")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     eng = get_engine(dev, torch.bfloat16)
+    eng.ctx.set_attention_v2(not args.attn_v1)
+    eng.ctx.set_groupnorm_split(not args.gn_fused)
+    eng.ctx.set_conv_implicit_all(not args.conv_im2col)
+    eng.ctx.set_geglu_exact(args.geglu_exact)
     ops = make_ops(eng, dev)
     names = args.ops or list(ops)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)

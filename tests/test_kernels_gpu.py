@@ -461,6 +461,11 @@ def test_attention_two_segments(dev, dtype, tc, N, Lq, Lk, Lk2, heads, d):
             k2, v2 = bank[:, :, :C], bank[:, :, C:]
             idx = torch.tensor([(-1 if i % 3 == 0 else i % 2) for i in range(N)], dtype=torch.int32, device=dev)
             out = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
+            if tc and d <= 64:      # the round-1 two-buffer kernel (flag 9 off) must agree with the default one
+                eng.ctx.set_attention_v2(False)
+                old = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
+                eng.ctx.set_attention_v2(True)
+                assert rel_l2(out.float(), old.float()) < 4e-3
             refs = []
             for n in range(N):
                 kk, vv = k[n:n + 1], v[n:n + 1]
@@ -475,6 +480,33 @@ def test_attention_two_segments(dev, dtype, tc, N, Lq, Lk, Lk2, heads, d):
         assert rel_l2(out.float(), ref) < (2e-5 if dtype == torch.float32 else 8e-3)
     finally:
         eng.ctx.set_tensor_cores(True)
+        eng.ctx.set_attention_v2(True)
+
+
+def test_attention_running_max_jumps_late(dev):
+    """Scores that grow along the key axis (every tile's maximum exceeds the previous reference by far more than the lazy
+    rescale threshold) and a huge outlier in the LAST key tile: exercises the redo-the-tile path and the O rescale of both
+    head-dim <= 64 kernels, plus a partial last tile in each segment."""
+    eng = eng_for(dev, torch.bfloat16)
+    N, Lq, Lk, Lk2, heads, d = 2, 192, 700, 333, 2, 40
+    C = heads * d
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(N, Lq, C, generator=g)
+    k = torch.randn(N, Lk, C, generator=g) * torch.linspace(0.2, 6.0, Lk)[None, :, None]
+    v = torch.randn(N, Lk, C, generator=g)
+    k2 = torch.randn(1, Lk2, C, generator=g) * 0.3
+    k2[:, -5] = 9.0 * q[0, 7].sign()                   # one key of the last (partial) tile dominates for some rows
+    v2 = torch.randn(1, Lk2, C, generator=g)
+    q, k, v, k2, v2 = (t.to(device=dev, dtype=torch.bfloat16) for t in (q, k, v, k2, v2))
+    ref = _attn_ref(q, torch.cat([k, k2.expand(N, -1, -1)], 1), torch.cat([v, v2.expand(N, -1, -1)], 1), heads)
+    try:
+        for v2_kernel in (True, False):
+            eng.ctx.set_attention_v2(v2_kernel)
+            out = eng.attention(q, k, v, heads, k2=k2, v2=v2)
+            assert torch.isfinite(out).all()
+            assert rel_l2(out.float(), ref) < 1e-2, v2_kernel
+    finally:
+        eng.ctx.set_attention_v2(True)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
