@@ -244,7 +244,7 @@ def run_ours(args):
     t_first0 = time.perf_counter()
     for attempt in range(2):
         try:
-            first = call_pipeline(host, 2 if args.ncu_step else N_STEPS)   # (a profiling run only needs the captured loop)
+            first = call_pipeline(host, 2 if (args.ncu_step or args.quick) else N_STEPS)   # (profiling / A-B runs only need the captured loop)
             break
         except RuntimeError as e:
             if attempt == 0 and args.frame_shards == 0 and "peer memory" in str(e):   # raised on every rank together
@@ -261,7 +261,13 @@ def run_ours(args):
         f"({loop.graph_launches} kernel launches per DDIM step in the graph)")
 
     # ---- device-resident timing: W warm-up + K timed steps, CUDA events, max over ranks
+    from mmgt_b200.mutual_self_attention import ReferenceAttentionControl
+    reader = ReferenceAttentionControl(unet, do_classifier_free_guidance=True, mode="read", fusion_blocks="full")
+
+    def attach_banks(h):     # (the pipeline call clears the reference banks when it returns, like the reference)
+        reader.set_banks([b.to(dev) for b in h["banks"]])
     d = to_device(host, dev)
+    attach_banks(host)
     loop.reload(d["latents"], d["pose"], d["audio"], d["full"], d["face"], d["lip"], d["ehs"])
     for i in range(args.warmup):
         loop.step(i % len(loop.timesteps))
@@ -294,6 +300,16 @@ def run_ours(args):
     ms_per_step = float(ms) / args.steps
     n_videos = world if replicas else 1
     value = n_videos * L / (N_STEPS * ms_per_step / 1e3)
+    if args.quick:      # A/B aid: the device-resident step time only (no e2e / parity / roofline / CPU legs)
+        if rank == 0:
+            print(json.dumps(dict(quick=True, ms_per_step=ms_per_step, value=value, n_gpus=world, config=args.config,
+                                  flags=dict(gn_split=args.gn_split, conv_implicit=args.conv_implicit, geglu_exact=args.geglu_exact,
+                                             fuse_ln=args.fuse_ln, attn_v2=args.attn_v2), simt_launches=eng.ctx.simt_launches() - s0,
+                                  gpu_launches=launches, clocks=clocks)), flush=True)
+        pipe.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- parity of the multi-GPU schedule, asserted in the run itself: two DDIM steps from the same latents through the
     #      distributed loop (every rank ends with the same latents after the all-reduce) and, on rank 0, through a local
@@ -362,6 +378,8 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launch stream over one more step
     roof = None
+    attach_banks(host2)
+    loop.reload(d["latents"], d["pose"], d["audio"], d["full"], d["face"], d["lip"], d["ehs"])
     # every rank runs this extra eager step (it contains the per-step all-reduce); only rank 0 instruments it
     eng.prof = {} if rank == 0 else None
     graph, loop._graph = loop._graph, None        # per-launch events need eager launches
@@ -556,6 +574,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
                     help="BASELINE.json config (1-based): 2 = headline (3 = the same at N > 1), 4 = one independent audio2vid "
                          "clip per GPU, 5 = 768x768 / 160 frames")
+    ap.add_argument("--quick", action="store_true", help="A/B aid: print only the device-resident step time")
     ap.add_argument("--strict", action="store_true",
                     help="strict tensor-core mode: a bf16 operator without a tcgen05 kernel is an error, not a CUDA-core fallback")
     ap.add_argument("--gn-split", type=int, default=None, help="A/B: 1 / 0 two-kernel / fused spin-barrier GroupNorm")

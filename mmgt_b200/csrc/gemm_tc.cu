@@ -500,11 +500,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 g[e] = __float_as_uint(ln_rstd * fmaf(-ln_mean, sg[e], __uint_as_float(g[e])));
               }
             }
+            if (args.bias) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              float val = __uint_as_float(r[e]), gate = __uint_as_float(g[e]);
-              if (args.bias) { val += bv[e]; gate += bg[e]; }
-              v[e] = val * (args.act == 3 ? gelu_erf_fast(gate) : gelu_logistic(gate));
+              for (int e = 0; e < 16; ++e) {
+                r[e] = __float_as_uint(__uint_as_float(r[e]) + bv[e]);
+                g[e] = __float_as_uint(__uint_as_float(g[e]) + bg[e]);
+              }
+            }
+            if (args.act == 3) {          // A/B switch: one branch per chunk, not a select per element
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) * gelu_erf_fast(__uint_as_float(g[e]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) * gelu_logistic(__uint_as_float(g[e]));
             }
           } else {
             float bv[16];

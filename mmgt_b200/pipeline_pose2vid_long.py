@@ -328,6 +328,8 @@ class Pose2VideoPipeline:
         self.frame_shards = 1                                           # k ranks split the frames of a window
         self.shard_remainder = False                                    # only the forwards left over by the whole deal
         self.use_cuda_graph = True
+        self.decode_chunk_size = 8                                      # frames per vae.decode call (the reference: 1)
+        self.shard_decode = True                                        # multi-GPU: every rank decodes a slice of the frames
         self._loops = {}                                                # video shape -> captured DenoiseLoop
 
     def to(self, *a, **k):
@@ -372,14 +374,33 @@ class Pose2VideoPipeline:
             latents = latents.to(device)
         return latents * 1.0   # init_noise_sigma == 1 for DDIM
 
-    def decode_latents(self, latents):
-        """Frame-by-frame VAE decode, as pipeline_pose2vid_long.py:112-125 (PyTorch; out of the timed path)."""
-        video_length = latents.shape[2]
-        latents = 1 / 0.18215 * latents
-        frames = []
-        for f in range(video_length):
-            frames.append(self.vae.decode(latents[:, :, f].to(self.vae.dtype)).sample)
-        video = torch.stack(frames, dim=2)
+    def decode_latents(self, latents, decode_chunk_size: Optional[int] = None):
+        """VAE decode of the L frames (pipeline_pose2vid_long.py:112-125: the reference decodes ONE frame per ``vae.decode``
+        call, 80 sequential 512x512 decodes).  The VAE is per-frame, so frames are decoded ``decode_chunk_size`` at a
+        time (default ``self.decode_chunk_size``) and, with more than one rank (``self.shard_decode``), every rank decodes a
+        contiguous slice of the frames and the slices are all-gathered -- same values, 1 / (chunk x ranks) of the
+        sequential latency.  The VAE itself stays the caller's PyTorch module (north_star: out of the hot path).
+        -> numpy (1, 3, L, H, W) float32 in [0, 1]."""
+        chunk = int(decode_chunk_size or self.decode_chunk_size)
+        L = latents.shape[2]
+        lat = (1 / 0.18215 * latents)[0].permute(1, 0, 2, 3)                               # (L, 4, h, w) = "(b f) c h w"
+        lo, hi = 0, L
+        sharded = self.shard_decode and self.world_size > 1
+        if sharded:
+            per = (L + self.world_size - 1) // self.world_size
+            lo, hi = min(L, self.rank * per), min(L, (self.rank + 1) * per)
+        frames = [self.vae.decode(lat[i:min(hi, i + chunk)].to(self.vae.dtype)).sample for i in range(lo, hi, chunk)]
+        video = torch.cat(frames) if frames else lat.new_zeros((0, 3, lat.shape[2] * self.vae_scale_factor,
+                                                                  lat.shape[3] * self.vae_scale_factor))
+        if sharded:
+            import torch.distributed as dist
+            per = (L + self.world_size - 1) // self.world_size
+            pad = torch.zeros((per,) + tuple(video.shape[1:]), device=video.device, dtype=video.dtype)
+            pad[: video.shape[0]] = video
+            parts = [torch.empty_like(pad) for _ in range(self.world_size)]
+            dist.all_gather(parts, pad, group=self.process_group)
+            video = torch.cat(parts)[:L]
+        video = video.permute(1, 0, 2, 3).unsqueeze(0)                                       # (1, 3, L, H, W)
         return ((video / 2 + 0.5).clamp(0, 1)).cpu().float().numpy()
 
     def interpolate_latents(self, latents: torch.Tensor, interpolation_factor: int, device=None):

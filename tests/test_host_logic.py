@@ -420,3 +420,61 @@ def test_engine_wrappers_with_a_mocked_library():
         g = eng.lib.mmgt_gemm.call_args[0][1]._obj
         assert y.shape == (10, 32) and (g.M, g.N, g.K, g.lda, g.ldw, g.ldd, g.geglu_block) == (10, 64, 32, 32, 32, 32, 16)
         assert not g.exchange
+
+
+def test_mask_frontend_matches_the_scripts_recipe():
+    """mmgt_b200.mask_frontend (f3): blur_mask + pyramid + the two full-mask recipes against the scripts' own code path --
+    cv2 blur (scripts/pose2vid.py:94-114), torchvision Resize + ToTensor per level (image_processor.py:75-102,311-333),
+    ``1 + lips`` (scripts/audio2vid.py:470-476) and the per-level ``clamp(1 - face + lips + hands)`` that the broken loop at
+    scripts/pose2vid.py:262-271 means.  The pyramid here is the oracle's (numpy); the CUDA one is checked bit-exactly
+    against it in tests/test_kernels_gpu.py::test_mask_pyramid_bit_exact."""
+    import cv2
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    from mmgt_b200 import mask_frontend as mf
+    from oracle.mask_pyramid import mask_pyramid_u8
+
+    class OraclePyramid:
+        def __init__(self, image_size):
+            self.image_size = image_size
+
+        def levels(self, images):
+            u8 = np.stack([np.asarray(m, dtype=np.uint8) for m in images])
+            return [torch.from_numpy(l.astype(np.float32) / 255.0).reshape(len(images), -1)
+                    for l in mask_pyramid_u8(u8, self.image_size)]
+    rng = np.random.default_rng(0)
+    L = 5
+
+    def frames():
+        out = []
+        for _ in range(L):
+            img = np.zeros((96, 128, 3), dtype=np.uint8)
+            y, x = rng.integers(5, 60, 2)
+            img[y:y + 30, x:x + 40] = 255
+            out.append(Image.fromarray(img))
+        return out
+    face_f, lips_f, hands_f = frames(), frames(), frames()
+    for size in (512, 768):
+        full_a, face, lips = mf.motion_masks(face_f, lips_f, None, image_size=size, recipe="audio2vid", pyramid=OraclePyramid(size))
+        full_p, _, _ = mf.motion_masks(face_f, lips_f, hands_f, image_size=size, recipe="pose2vid", pyramid=OraclePyramid(size))
+        # the scripts' path: cv2 front-end, then torchvision per level
+        def script_levels(fr, k):
+            pil = []
+            for img in fr:
+                a = cv2.normalize(cv2.GaussianBlur(cv2.resize(np.array(img), (64, 64)), k, 0), None, 0, 255, cv2.NORM_MINMAX)
+                pil.append(Image.fromarray(a.astype(np.uint8)).convert("L"))
+            lv = []
+            for kk in range(4):
+                s = size // (8 << kk)
+                t = transforms.Compose([transforms.Resize((s, s)), transforms.ToTensor()])
+                lv.append(torch.stack([t(p) for p in pil]).view(L, 1, -1).squeeze(1))
+            return lv
+        ref_face, ref_lips, ref_hands = script_levels(face_f, (31, 31)), script_levels(lips_f, (21, 21)), script_levels(hands_f, (21, 21))
+        for k in range(4):
+            assert face[k].shape == (L, (size // (8 << k)) ** 2)
+            assert torch.equal(face[k], ref_face[k]) and torch.equal(lips[k], ref_lips[k])          # bit-exact
+            assert torch.equal(full_a[k], 1.0 + ref_lips[k])
+            assert torch.equal(full_p[k], torch.clamp(1.0 - ref_face[k] + ref_lips[k] + ref_hands[k], 0.0, 1.0))
+    with pytest.raises(ValueError):
+        mf.full_mask_levels(face, lips, None, "nope")

@@ -409,3 +409,80 @@ def test_multi_rank_schedules_sum_to_the_single_rank_step(monkeypatch, world, k,
     assert rel_l2(total, single.noise_acc) < 1e-5
     if L == 80:
         assert max(work) == min(work) == 20.0 / world       # balanced: 5 (4 ranks) / 2.5 (8 ranks) forwards of work per rank
+
+
+def _conditioning_modules():
+    import json
+    from mmgt_b200.audio_proj import AudioProjModel
+    from mmgt_b200.pose_guider import PoseGuider
+    from oracle.make_golden_f1 import AUDIO_CFG, POSE_CFG, zero_init_visible
+    from oracle.weights import make_state_dict
+    with open(os.path.join(GOLD, "conditioning_spec.json")) as f:
+        spec = json.load(f)
+    pg, ap = PoseGuider(**POSE_CFG), AudioProjModel(**AUDIO_CFG)
+    assert [(k, list(v.shape)) for k, v in pg.state_dict().items()] == [(k, s) for k, s in spec["pose_guider"]]
+    assert [(k, list(v.shape)) for k, v in ap.state_dict().items()] == [(k, s) for k, s in spec["audio_proj"]]
+    assert float(pg.conv_out.weight.abs().max()) == 0.0                      # zero_module, pose_guider.py:38-45
+    pg.load_state_dict(zero_init_visible(make_state_dict([(k, tuple(s)) for k, s in spec["pose_guider"]], seed=3), "conv_out",
+                                         seed=31), strict=True)
+    ap.load_state_dict(make_state_dict([(k, tuple(s)) for k, s in spec["audio_proj"]], seed=4), strict=True)
+    return pg, ap
+
+
+def test_pose_guider_and_audio_proj_host_mirror_on_cpu():
+    """f1: PoseGuider / AudioProjModel (reference constructors and state-dict keys) on the fake engine vs the outputs of the
+    reference's own classes (tests/golden/conditioning.npz)."""
+    from oracle.make_golden_f1 import audio_input, pose_input
+    g = np.load(os.path.join(GOLD, "conditioning.npz"))
+    pg, ap = _conditioning_modules()
+    eng = FakeEngine()
+    pg._engine = ap._engine = lambda x: eng
+    assert rel_l2(pg(pose_input()), torch.from_numpy(g["pose_out"])) < 1e-6
+    assert rel_l2(ap(audio_input()), torch.from_numpy(g["audio_out"])) < 1e-6
+
+
+def _decode_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from mmgt_b200.pipeline_pose2vid_long import Pose2VideoPipeline
+    from vae_stub import VaeStub
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    vae = VaeStub()
+    pipe = Pose2VideoPipeline(vae, None, None, None, None, None)
+    pipe.rank, pipe.world_size = rank, world
+    lat = torch.randn(1, 4, 7, 4, 4, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        out = pipe.decode_latents(lat, decode_chunk_size=2)
+    q.put((rank, out, list(vae.decode_calls)))
+    dist.destroy_process_group()
+
+
+def test_decode_latents_chunked_and_frame_sharded_matches_the_sequential_reference_recipe():
+    """f2: decode_latents in chunks and as frame slices over 2 ranks (gloo) == the reference's one-frame-at-a-time loop
+    (pipeline_pose2vid_long.py:112-125)."""
+    import torch.multiprocessing as mp
+    from mmgt_b200.pipeline_pose2vid_long import Pose2VideoPipeline
+    from vae_stub import VaeStub
+    vae = VaeStub()
+    pipe = Pose2VideoPipeline(vae, None, None, None, None, None)
+    assert pipe.vae_scale_factor == 8
+    lat = torch.randn(1, 4, 7, 4, 4, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = torch.cat([vae.decode(1 / 0.18215 * lat[:, :, f]).sample for f in range(7)])     # the reference's loop
+        ref = ((ref.permute(1, 0, 2, 3).unsqueeze(0) / 2 + 0.5).clamp(0, 1)).numpy()
+        vae.decode_calls.clear()
+        out = pipe.decode_latents(lat, decode_chunk_size=3)
+    assert out.shape == (1, 3, 7, 32, 32) and vae.decode_calls == [3, 3, 1]
+    assert np.abs(out - ref).max() < 1e-5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_decode_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][2] == [2, 2] and res[1][2] == [2, 1]                      # 4 + 3 frames, two per call
+    for _, o, _ in res:
+        assert np.abs(o - ref).max() < 1e-5
