@@ -289,7 +289,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        loop.step((args.warmup + i) % N_STEPS)
+        loop.step((args.warmup + i) % len(loop.timesteps))
     e1.record()
     barrier()
     clocks = sampler.stop()

@@ -206,7 +206,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_empty = p_full + 2;              // 2  ("PV of this group's tile retired": P buffer free, O_g stable)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
   const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
 
   if (threadIdx.x == 0) {
@@ -234,7 +234,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int tiles2 = seg2 >= 0 ? (args.Lk2 + BN - 1) / BN : 0;
   const int num_tiles = tiles1 + tiles2;
 
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one_sync()) {
     // ===================== TMA producer =====================
     mbar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
@@ -271,7 +271,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (i + VS < num_tiles) load_v(i + VS);
       if (i + 2 + KS < num_tiles) load_k(i + 2 + KS);
     }
-  } else if (threadIdx.x == 32) {
+  } else if (warp == 1 && elect_one_sync()) {
     // ===================== MMA issuer =====================
     // Issue order: QK(0), QK(1), then per tile j: QK(j+2), PV(j).  QK(j+2) only needs group (j & 1) to have pulled
     // S(j) out of TMEM (signalled three quarters into its softmax of tile j), so S(j+2) is ready when the group
@@ -281,12 +281,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int st = j % KS, g = j & 1;
       tc_fence_after();
       const uint32_t tS = tmem_base + TM_S + g * BN;
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + st * KV_BYTES);
+      // descriptors differ only in the (address >> 4) field: build one per operand and step it
+      const uint64_t dQ = desc_kmajor(smem_u32(sQ)), dK = desc_kmajor(smem_u32(sK + st * KV_BYTES));
 #pragma unroll
       for (int k = 0; k < DPAD / 16; ++k) {
         if (k < qk_steps) {
           const uint32_t offq = (k / 4) * (BQ * 128) + (k % 4) * 32, offk = (k / 4) * KV_CHUNK + (k % 4) * 32;
-          umma(tS, desc_kmajor(aQ + offq), desc_kmajor(aK + offk), IDESC_QK, k != 0);
+          umma(tS, dQ + (offq >> 4), dK + (offk >> 4), IDESC_QK, k != 0);
         }
       }
       umma_commit(&k_empty[st]);
@@ -295,20 +296,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     auto issue_pv = [&](int j) {
       const int st = j % VS, g = j & 1;
       tc_fence_after();
-      const uint32_t aV = smem_u32(sV + st * KV_BYTES);
+      const uint64_t dV = desc_mnmajor(smem_u32(sV + st * KV_BYTES), KV_CHUNK);
       const uint32_t tOg = tmem_base + TM_O + g * DPAD;
       if constexpr (P_TMEM) {
         const uint32_t tPg = tmem_base + TM_P + g * (BN / 2);
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k)   // A = P from TMEM: 16 keys = 8 packed columns per step; B = V, MN-major
-          umma_ts(tOg, tPg + k * 8, desc_mnmajor(aV + k * 2048, KV_CHUNK), IDESC_PV, ((j >> 1) | k) != 0);
+          umma_ts(tOg, tPg + k * 8, dV + k * (2048 >> 4), IDESC_PV, ((j >> 1) | k) != 0);
       } else {
-        const uint32_t aP = smem_u32(sP + g * P_BYTES);
+        const uint64_t dP = desc_kmajor(smem_u32(sP + g * P_BYTES));
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) {
           // A = P: K-major, 64-key chunks of (128 rows x 128 B); B = V: MN-major, 16 keys = 2 x 1024 B per step
           const uint32_t offp = (k / 4) * (BQ * 128) + (k % 4) * 32;
-          umma(tOg, desc_kmajor(aP + offp), desc_mnmajor(aV + k * 2048, KV_CHUNK), IDESC_PV, ((j >> 1) | k) != 0);
+          umma(tOg, dP + (offp >> 4), dV + k * (2048 >> 4), IDESC_PV, ((j >> 1) | k) != 0);
         }
       }
       umma_commit(&v_empty[st]);
@@ -563,7 +564,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* o_ready = p_full + NB;             // 2:  PV of the group's latest tile retired (O_g stable, buffer reusable)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
   const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
 
   if (threadIdx.x == 0) {
@@ -590,7 +591,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int tiles2 = seg2 >= 0 ? (args.Lk2 + BN - 1) / BN : 0;
   const int num_tiles = tiles1 + tiles2;
 
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one_sync()) {
     // ===================== TMA producer =====================
     mbar_expect_tx(q_full, Q_BYTES);
     tma_load_3d(sQ, &tmQ, q_full, 0, h, n * args.Lq + q0);
@@ -615,17 +616,17 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (i + KS < num_tiles) load_k(i + KS);
       if (i + VS < num_tiles) load_v(i + VS);
     }
-  } else if (threadIdx.x == 32) {
+  } else if (warp == 1 && elect_one_sync()) {
     // ===================== MMA issuer =====================
     auto issue_qk = [&](int j) {
       const int st = j % KS, b = j % NB;
       mbar_wait(&k_full[st], (j / KS) & 1);
       tc_fence_after();
       const uint32_t tS = tmem_base + b * BN;
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + st * KV_BYTES);
+      const uint64_t dQ = desc_kmajor(smem_u32(sQ)), dK = desc_kmajor(smem_u32(sK + st * KV_BYTES));
 #pragma unroll
       for (int k = 0; k < DPAD / 16; ++k)
-        if (k < qk_steps) umma(tS, desc_kmajor(aQ + k * 32), desc_kmajor(aK + k * 32), IDESC_QK, k != 0);
+        if (k < qk_steps) umma(tS, dQ + 2 * k, dK + 2 * k, IDESC_QK, k != 0);
       umma_commit(&k_empty[st]);
       umma_commit(&s_full[b]);
     };
@@ -636,11 +637,11 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_wait(&v_full[st], (j / VS) & 1);
       mbar_wait(&p_full[b], (j / NB) & 1);
       tc_fence_after();
-      const uint32_t aV = smem_u32(sV + st * KV_BYTES);
+      const uint64_t dV = desc_mnmajor(smem_u32(sV + st * KV_BYTES), BN * 128);
       const uint32_t tOg = tmem_base + TM_O + g * DPAD, tP = tmem_base + b * BN;
 #pragma unroll
       for (int k = 0; k < BN / 16; ++k)   // A = P from TMEM: 16 keys = 8 packed columns per step; B = V, MN-major
-        umma_ts(tOg, tP + k * 8, desc_mnmajor(aV + k * 2048, BN * 128), IDESC_PV, ((j >> 1) | k) != 0);
+        umma_ts(tOg, tP + k * 8, dV + k * (2048 >> 4), IDESC_PV, ((j >> 1) | k) != 0);
       umma_commit(&v_empty[st]);
       umma_commit(&o_ready[g]);
       if (j + NB < num_tiles) {

@@ -94,6 +94,25 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// One lane of a converged warp.  The TMA-producer and MMA-issuer roles run under `warp == k && elect_one_sync()` with a
+// warp-uniform `warp`: ptxas then KNOWS a single lane is active and feeds tcgen05.mma / cp.async.bulk their uniform-register
+// operands directly.  Under `threadIdx.x == 32` it wrapped every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+// "waterfall" loop with the descriptor arithmetic serialised in front of it (~17 dependent instructions, 70-100 clocks per
+// MMA): the issuing thread, not the tensor pipe, paced the attention kernel (11 MMAs per 128 x 128 tile) and the narrow-tile
+// GEMMs (profiles/r2_mma_issue.md).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ int uniform_warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t mmgt_launch(const mmgt_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                cudaStream_t st, Args&&... args) {

@@ -23,6 +23,7 @@ constexpr int BK = 64;             // 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 320;            // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int EPI_VEC_BYTES = 2 * 3 * 256 * 4;   // [accumulator stage][bias | colsum | row bias][256 columns] floats
 
 __host__ __device__ constexpr int acc_stride(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
 __host__ __device__ constexpr int num_stages(int bn) { return bn >= 256 ? 4 : bn >= 128 ? 6 : 8; }
@@ -43,6 +44,8 @@ struct TcArgs {
   const float* rowstats;    // fused LayerNorm: (M, 2) [mean, rstd]; D = rstd * (acc - mean * colsum[n]) + bias[n]
   const float* colsum;
   int act;                  // 0 none, 1 SiLU, 2 ReLU
+  int rb_tile_rows;         // > 0: every M tile lies inside ONE row-bias group of this many TILE-SPACE rows (a multiple of
+                            // 128), so the tile's row-bias vector is staged in shared memory with bias / colsum
   // conv geometry (CONV only).  H, W span the TILE space: the output image for conv_mode 0 (3x3, stride 1: same as the
   // input) and 1 (stride 2: A boxes are fetched with a TMA traversal stride of 2 from coordinate 2*o + tap - 1); the
   // INPUT image for conv_mode 2 (nearest x2 upsample + 3x3 = four 2x2-tap convolutions on the low-resolution input with
@@ -198,6 +201,13 @@ __device__ __forceinline__ void st_row32(bf16* p, const float (&v)[16], bool wid
   }
 }
 
+__device__ __forceinline__ void lds16_f32(const float* src, float (&v)[16]) {    // shared memory, warp-uniform address (broadcast)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 f = reinterpret_cast<const float4*>(src)[i];
+    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+  }
+}
 __device__ __forceinline__ void load16_f32(const float* src, float (&v)[16]) {   // 64-byte aligned, warp-uniform address
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -278,8 +288,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* b_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  // Per-column epilogue vectors of the current tile (bias, LayerNorm column sums, row bias), one set per accumulator
+  // stage: loaded by the epilogue warps BEFORE they wait for the accumulator, read back as shared-memory broadcasts.
+  // (Read with __ldg inside the chunk loop they were the top stall of the small-K GEMMs: every 16-column chunk waited a
+  // full L2 round trip for 64 bytes -- profiles/r2_gemm_epilogue.md.)
+  float* s_vec = reinterpret_cast<float*>(full_bar) + 64;       // 256 bytes after the barriers; [2][3][256] floats
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -315,7 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     return tile < num_tiles;
   };
 
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one_sync()) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
@@ -361,7 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (threadIdx.x == 32) {
+  } else if (warp == 1 && elect_one_sync()) {
     // ===================== MMA issuer =====================
     int stage = 0;
     uint32_t phase = 0;
@@ -444,11 +459,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = 0; i < CH0; ++i)
         if (i < c_count) resv[i] = ld_row32(rp + 16 * i, wide);
     }
+    const int et = (int)threadIdx.x - 64;          // epilogue thread 0..255
     for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m = row_of(m_blk);
       const bool m_ok = m < args.M;
+      float* sv = s_vec + acc * 768;
+      const bool rb_staged = args.rowbias != nullptr && args.rb_tile_rows > 0;
+      if (et < BN / 4) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(sv)[et] = args.bias ? __ldg(reinterpret_cast<const float4*>(args.bias + n_blk * BN) + et) : z;
+        if (args.rowstats)
+          reinterpret_cast<float4*>(sv + 256)[et] = __ldg(reinterpret_cast<const float4*>(args.colsum + n_blk * BN) + et);
+        if (rb_staged && et < OUT_COLS / 4) {
+          int tile_row0 = m_blk * BM;
+          if (CONV && args.conv_mode == 2) tile_row0 = (m_blk >> 2) * BM;
+          int grp = tile_row0 / args.rb_tile_rows;
+          if (args.rowbias_mod > 0) grp %= args.rowbias_mod;
+          reinterpret_cast<float4*>(sv + 512)[et] =
+              __ldg(reinterpret_cast<const float4*>(args.rowbias + (int64_t)grp * args.ld_rowbias + n_blk * OUT_COLS) + et);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps: vectors of this tile are in place
       const int n_out0 = n_blk * OUT_COLS;
       const bool has_res = args.residual != nullptr && m_ok;
       const bf16* res_next = nullptr;
@@ -461,15 +494,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (args.ex.direction != 0 && m_ok) drow = exchange_row_ptr<bf16>(args.ex, m);
       const float rs = (args.rowscale && m_ok ? args.rowscale[m] : 1.f) * args.alpha;
       const float* rb = nullptr;
-      if (args.rowbias && m_ok) {
+      if (args.rowbias && m_ok && !rb_staged) {
         int grp = m / args.rows_per_group;
         if (args.rowbias_mod > 0) grp %= args.rowbias_mod;
         rb = args.rowbias + (int64_t)grp * args.ld_rowbias;
       }
-      float ln_mean = 0.f, ln_rstd = 1.f;
+      float ln_nmr = 0.f, ln_rstd = 1.f;      // (-rstd * mean, rstd) of this thread's row
       if (args.rowstats && m_ok) {
         const float2 st = __ldg(reinterpret_cast<const float2*>(args.rowstats) + m);
-        ln_mean = st.x; ln_rstd = st.y;
+        ln_rstd = st.y; ln_nmr = -st.x * st.y;
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
@@ -485,22 +518,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t g[16];
             tmem_ld_x16(taddr + 2 * c + 16, g);
             float bv[16], bg[16];
-            if (args.bias) {
-              load16_f32(args.bias + n_blk * BN + 2 * c, bv);
-              load16_f32(args.bias + n_blk * BN + 2 * c + 16, bg);
-            }
+            lds16_f32(sv + 2 * c, bv);
+            lds16_f32(sv + 2 * c + 16, bg);
             tmem_ld_wait();
-            if (args.rowstats) {          // fused LayerNorm (warp-uniform branch)
-              float sv[16], sg[16];
-              load16_f32(args.colsum + n_blk * BN + 2 * c, sv);
-              load16_f32(args.colsum + n_blk * BN + 2 * c + 16, sg);
+            if (args.rowstats) {          // fused LayerNorm (warp-uniform branch): rstd * acc + (-rstd * mean) * colsum + bias
+              float cv[16], cg[16];
+              lds16_f32(sv + 256 + 2 * c, cv);
+              lds16_f32(sv + 256 + 2 * c + 16, cg);
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-                r[e] = __float_as_uint(ln_rstd * fmaf(-ln_mean, sv[e], __uint_as_float(r[e])));
-                g[e] = __float_as_uint(ln_rstd * fmaf(-ln_mean, sg[e], __uint_as_float(g[e])));
+                r[e] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(r[e]), fmaf(ln_nmr, cv[e], bv[e])));
+                g[e] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(g[e]), fmaf(ln_nmr, cg[e], bg[e])));
               }
-            }
-            if (args.bias) {
+            } else {
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
                 r[e] = __float_as_uint(__uint_as_float(r[e]) + bv[e]);
@@ -516,24 +546,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else {
             float bv[16];
-            if (args.bias) load16_f32(args.bias + n_out0 + c, bv);
+            lds16_f32(sv + c, bv);
             tmem_ld_wait();
             if (args.rowstats) {
-              float sv[16];
-              load16_f32(args.colsum + n_out0 + c, sv);
+              float cv[16];
+              lds16_f32(sv + 256 + c, cv);
 #pragma unroll
-              for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(ln_rstd * fmaf(-ln_mean, sv[e], __uint_as_float(r[e])));
-            }
+              for (int e = 0; e < 16; ++e) v[e] = fmaf(ln_rstd, __uint_as_float(r[e]), fmaf(ln_nmr, cv[e], bv[e]));
+            } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              v[e] = __uint_as_float(r[e]);
-              if (args.bias) v[e] += bv[e];
+              for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + bv[e];
             }
           }
           if (m_ok) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] *= rs;
-            if (rb) {
+            if (rb_staged) {
+              float rv[16];
+              lds16_f32(sv + 512 + c, rv);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] += rv[e];
+            } else if (rb) {
               float rv[16];
               load16_f32(rb + n_out0 + c, rv);
 #pragma unroll
@@ -633,7 +666,7 @@ int pick_bn_for(int N, int M, int num_sms) {
 template <int BN, bool CONV, bool GEGLU>
 int launch_tc(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
   constexpr int STAGES = num_stages(BN);
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + EPI_VEC_BYTES;
   MMGT_CUDA_OK(mmgt_smem_optin(ctx, gemm_tc_kernel<BN, CONV, GEGLU, false>, smem));
   const int tiles = a.num_m_tiles * a.num_n_tiles;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
@@ -663,7 +696,7 @@ int dispatch_tc(mmgt_ctx* ctx, int bn, bool geglu, const CUtensorMap& tmA, const
 
 // ---- weight-stationary plan (BRES kernels)
 constexpr int SMEM_OPTIN = 232448;          // 227 KB per CTA on sm_100
-constexpr int BRES_OVERHEAD = 1024 + 256;   // alignment slack + barriers
+constexpr int BRES_OVERHEAD = 1024 + 256 + EPI_VEC_BYTES;   // alignment slack + barriers + epilogue vectors
 
 struct BresPlan { int bn, stages, grid; };
 
@@ -775,6 +808,7 @@ int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
   a.ld_rowbias = p->ld_rowbias ? p->ld_rowbias : a.N_out; a.rowbias_mod = p->rowbias_mod;
   a.rowstats = p->rowstats; a.colsum = p->colsum;
   a.act = p->geglu_block ? (ctx->geglu_exact ? 3 : 0) : p->act;
+  a.rb_tile_rows = (p->rowbias && a.rows_per_group % BM == 0) ? a.rows_per_group : 0;
   a.wide_io = aligned32(p->D) && p->ldd % 16 == 0 && (!p->residual || (aligned32(p->residual) && p->ldr % 16 == 0));
   if (p->exchange) {
     int rc = mmgt_row_exchange_check(p->exchange, p->M, "gemm");
@@ -901,6 +935,10 @@ int mmgt_conv3x3_tc(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, cudaStream_t st
   a.ld_rowbias = p->ld_rowbias ? p->ld_rowbias : p->Cout;
   a.act = p->act;
   a.alpha = 1.f;
+  {   // row-bias group in TILE-SPACE rows (mode 2 tiles walk the input image)
+    const int tile_rows_per_group = p->frames_per_group * Ht * Wt;
+    a.rb_tile_rows = (p->rowbias && !patch && tile_rows_per_group % BM == 0) ? tile_rows_per_group : 0;
+  }
   a.H = Ht; a.W = Wt;
   return dispatch_tc<true>(ctx, bn, false, tmA, tmB, a, st);
 }

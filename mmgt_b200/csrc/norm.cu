@@ -160,15 +160,20 @@ gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restric
     // ---------------- phase 3: normalise
     float* scale = sm;
     float* shift = sm + C;
-    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
-      const int g = c / cpg;
+    float* gstat = sm + 2 * C;      // (mean, rstd) per group: the double-precision part once per group, not per channel
+    for (int g = threadIdx.x; g < groups; g += GN_THREADS) {
       const double mean = __ldcg(&stats[((size_t)n * groups + g) * 2]) / cnt;
       double var = __ldcg(&stats[((size_t)n * groups + g) * 2 + 1]) / cnt - mean * mean;
       if (var < 0) var = 0;
-      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-      const float sc = rstd * gamma[c];
+      gstat[2 * g] = (float)mean;
+      gstat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+      const int g = c / cpg;
+      const float sc = gstat[2 * g + 1] * gamma[c];
       scale[c] = sc;
-      shift[c] = beta[c] - (float)mean * sc;
+      shift[c] = beta[c] - gstat[2 * g] * sc;
     }
     __syncthreads();
     if (active) {
@@ -224,12 +229,12 @@ __device__ __forceinline__ float silu_fast(float v) {
 }
 
 template <typename T, int NV>
-__global__ void __launch_bounds__(GN_THREADS)
+__global__ void __launch_bounds__(GN_THREADS, 3)
 gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __restrict__ stats, int T_tok, int C1, int C2,
                 int groups, int tok_per_block) {
   constexpr int VEC = VecOf<T>::N;
   typedef typename VecOf<T>::type Raw;
-  constexpr int UNR = 8 / NV < 1 ? 1 : 8 / NV;
+  constexpr int UNR = 4 / NV < 1 ? 1 : 4 / NV;
   pdl_prologue();
   extern __shared__ float sm[];   // [2][rows_per_pass][C] per-thread partial sums
   const int C = C1 + C2, Cv = C / VEC, C1v = C1 / VEC, cpg = C / groups;
@@ -296,13 +301,13 @@ gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __re
 }
 
 template <typename T, int NV>
-__global__ void __launch_bounds__(GN_THREADS)
+__global__ void __launch_bounds__(GN_THREADS, 3)
 gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restrict__ y, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const double* __restrict__ stats, int T_tok, int C1, int C2, int groups,
                 float eps, int silu, int tok_per_block) {
   constexpr int VEC = VecOf<T>::N;
   typedef typename VecOf<T>::type Raw;
-  constexpr int UNR = 8 / NV < 1 ? 1 : 8 / NV;
+  constexpr int UNR = 4 / NV < 1 ? 1 : 4 / NV;
   pdl_prologue();
   extern __shared__ float sm[];   // scale[C], shift[C]
   const int C = C1 + C2, Cv = C / VEC, C1v = C1 / VEC, cpg = C / groups;
@@ -316,15 +321,20 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restric
   const double cnt = (double)T_tok * cpg;
   float* scale = sm;
   float* shift = sm + C;
-  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
-    const int g = c / cpg;
+  float* gstat = sm + 2 * C;        // (mean, rstd) per group: the double-precision part once per group, not per channel
+  for (int g = threadIdx.x; g < groups; g += GN_THREADS) {
     const double mean = stats[((size_t)n * groups + g) * 2] / cnt;
     double var = stats[((size_t)n * groups + g) * 2 + 1] / cnt - mean * mean;
     if (var < 0) var = 0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = rstd * gamma[c];
+    gstat[2 * g] = (float)mean;
+    gstat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    const int g = c / cpg;
+    const float sc = gstat[2 * g + 1] * gamma[c];
     scale[c] = sc;
-    shift[c] = beta[c] - (float)mean * sc;
+    shift[c] = beta[c] - gstat[2 * g] * sc;
   }
   __syncthreads();
   auto src = [&](size_t row, int cv) -> const Raw* {
@@ -637,15 +647,15 @@ extern "C" int mmgt_groupnorm(mmgt_ctx* ctx, const void* x1, const void* x2, voi
   const int nv = (Cv + GN_THREADS - 1) / GN_THREADS;
   const int lanes = std::min(Cv, GN_THREADS);
   const int rpp = GN_THREADS / lanes;
-  const size_t smem = sizeof(float) * 2 * C;
+  const size_t smem = sizeof(float) * (2 * C + 2 * groups);
   if (ctx->gn_split) {
     // statistics kernel + normalise kernel: grid (token chunks, frames), ~8 CTAs per SM worth of chunks
     const int want = std::max(1, (ctx->num_sms * 8 + N - 1) / N);
-    const int unr = std::max(1, 8 / nv);
+    const int unr = std::max(1, 4 / nv);
     int tok_per_block = std::max((T + want - 1) / want, rpp * unr);
     tok_per_block = (tok_per_block + rpp - 1) / rpp * rpp;
     const int chunks = (T + tok_per_block - 1) / tok_per_block;
-    const size_t smem_stats = sizeof(float) * 2 * (size_t)rpp * C;
+    const size_t smem_stats = std::max(sizeof(float) * 2 * (size_t)rpp * C, smem);
     MMGT_CHECK_ARG(chunks <= 65535 * 16, MMGT_E_INVALID, "groupnorm: too many token chunks");
     MMGT_CUDA_OK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * N * groups, st));
     dim3 grid(chunks, N);
