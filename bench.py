@@ -210,6 +210,7 @@ def run_ours(args):
     pipe.rank, pipe.world_size, pipe.process_group = loop_rank, loop_world, None
     pipe.frame_shards, pipe.shard_remainder = shards, remainder
     pipe.use_cuda_graph = not args.no_graph
+    pipe.deep_batch = args.deep_batch
     eng = unet._engine(dev)
     if args.no_tc:
         eng.ctx.set_tensor_cores(False)
@@ -304,7 +305,7 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps(dict(quick=True, ms_per_step=ms_per_step, value=value, n_gpus=world, config=args.config,
                                   flags=dict(gn_split=args.gn_split, conv_implicit=args.conv_implicit, geglu_exact=args.geglu_exact,
-                                             fuse_ln=args.fuse_ln, attn_v2=args.attn_v2), simt_launches=eng.ctx.simt_launches() - s0,
+                                             fuse_ln=args.fuse_ln, attn_v2=args.attn_v2, deep_batch=args.deep_batch), simt_launches=eng.ctx.simt_launches() - s0,
                                   gpu_launches=launches, clocks=clocks)), flush=True)
         pipe.close()
         if world > 1:
@@ -581,6 +582,8 @@ def main():
     ap.add_argument("--conv-implicit", type=int, default=None, help="A/B: 1 / 0 implicit-GEMM / im2col stride-2 + upsample convs")
     ap.add_argument("--geglu-exact", type=int, default=None, help="A/B: 1 = erf GELU in the GEGLU epilogue")
     ap.add_argument("--attn-v2", type=int, default=None, help="A/B: 1 / 0 three-S-buffer / round-1 attention kernel (head dim <= 64)")
+    ap.add_argument("--deep-batch", type=int, default=None,
+                    help="A/B: forwards whose 16x16 / 8x8 levels run as one batch (default: all of a rank's; 1 = unit by unit)")
     ap.add_argument("--fuse-ln", type=int, default=None, help="A/B: 1 / 0 LayerNorm in the GEMM epilogue / as its own pass")
     ap.add_argument("--no-tc", action="store_true", help="debug: CUDA-core kernels only")
     ap.add_argument("--no-graph", action="store_true", help="debug: eager launches instead of one CUDA graph per step")

@@ -57,6 +57,8 @@ class DenoiseLoop:
         self.graph_launches = 0
         self._made_group = False
         self._bank_ptrs = None
+        # units whose 16x16 / 8x8 levels run as ONE batch (UNet3DConditionModel.forward_tokens_group); 1 = unit by unit
+        self.deep_batch = 16
 
     # ------------------------------------------------------------------ one-off preparation per video
     def prepare(self, latents, pose_fea, audio, full_mask, face_mask, lip_mask, encoder_hidden_states):
@@ -176,15 +178,35 @@ class DenoiseLoop:
 
     # ------------------------------------------------------------------ the hot loop
     def _forward_units(self, lat_tok):
+        """This rank's (window, CFG-branch) forwards of one step.  Frame-sharded units run one by one (their motion modules
+        exchange rows with the peers); the others go through ``forward_tokens_group``: 64x64 / 32x32 levels unit by unit,
+        the 16x16 / 8x8 levels of ALL units as one batch (``deep_batch``)."""
         eng, u = self.eng, self.unet
+
+        def finish(e, out):
+            nbr, F_ = len(e["branches"]), e["frames"]
+            pred = eng.tokens_to_ncfhw(out, nbr, F_, torch.float32)
+            eng.window_accumulate(self.noise_acc, pred, e["idx"], e["branches"][0])
+        plain = []
         for e in self.prepared:
             x = eng.gather_rows(lat_tok, e["x_idx"])
             nbr, F_ = len(e["branches"]), e["frames"]
-            out = u.forward_tokens(eng, x, self.t_dev, e["ehs"], e["audio"], e["pose"], e["masks"][0], e["masks"][1],
-                                   e["masks"][2], self.motion_scale, nbr, F_, ref_index=e["ref"], shard=e["shard"],
-                                   time_proj=self._time_proj)
-            pred = eng.tokens_to_ncfhw(out, nbr, F_, torch.float32)
-            eng.window_accumulate(self.noise_acc, pred, e["idx"], e["branches"][0])
+            if e["shard"] is not None:
+                finish(e, u.forward_tokens(eng, x, self.t_dev, e["ehs"], e["audio"], e["pose"], e["masks"][0], e["masks"][1],
+                                           e["masks"][2], self.motion_scale, nbr, F_, ref_index=e["ref"], shard=e["shard"],
+                                           time_proj=self._time_proj))
+            else:
+                plain.append((e, dict(x=x, pose=e["pose"], ehs=e["ehs"], audio=e["audio"], full=e["masks"][0],
+                                      face=e["masks"][1], body=e["masks"][2], B=nbr, F=F_, ref=e["ref"])))
+        if not plain:
+            return
+        same_f = len({un["F"] for _, un in plain}) == 1
+        chunk = max(1, int(self.deep_batch)) if same_f else 1
+        for i in range(0, len(plain), chunk):
+            part = plain[i:i + chunk]
+            outs = u.forward_tokens_group(eng, [un for _, un in part], self.t_dev, self.motion_scale, time_proj=self._time_proj)
+            for (e, _), out in zip(part, outs):
+                finish(e, out)
 
     def _units_body(self):
         """Everything of a step that does not depend on host scalars: zero the accumulator, re-layout the latents,
@@ -328,6 +350,7 @@ class Pose2VideoPipeline:
         self.frame_shards = 1                                           # k ranks split the frames of a window
         self.shard_remainder = False                                    # only the forwards left over by the whole deal
         self.use_cuda_graph = True
+        self.deep_batch = None                                          # None = DenoiseLoop's default (all units of a rank)
         self.decode_chunk_size = 8                                      # frames per vae.decode call (the reference: 1)
         self.shard_decode = True                                        # multi-GPU: every rank decodes a slice of the frames
         self._loops = {}                                                # video shape -> captured DenoiseLoop
@@ -518,6 +541,8 @@ class Pose2VideoPipeline:
                 loop = DenoiseLoop(self.denoising_unet, sched, num_inference_steps, guidance_scale, context_frames,
                                    context_stride, context_overlap, context_schedule, motion_scale, self.rank, self.world_size,
                                    self.process_group, self.frame_shards, shard_remainder=self.shard_remainder)
+                if self.deep_batch is not None:
+                    loop.deep_batch = int(self.deep_batch)
                 loop.prepare(latents, pose_fea, audio, full, face, lip, ehs)
                 if self.use_cuda_graph and latents.is_cuda:
                     loop.capture_graph()

@@ -376,6 +376,91 @@ class UNet3DConditionModel(nn.Module):
         ``shard`` (frame_shard.FrameShardGroup): x / pose / audio / masks hold only this rank's F frames of a window
         whose k*F frames are spread over k ranks; the motion modules exchange rows with the peers.
         ``time_proj``: TimeProjections of this timestep computed by the caller (once per DDIM step)."""
+        si = self._step_inputs(eng, x, timestep, encoder_hidden_states, audio_embedding, full_mask, face_mask, body_mask,
+                               motion_scale, B, F, ref_index, shard, time_proj)
+        reaches = self._motion_scale_reaches_audio()
+        x, skips = self._run_down(eng, x, pose, si, reaches, 0, len(self.down_blocks))
+        x = self.mid_block.run(eng, x, si)
+        return self._run_up(eng, x, skips, si, 0, len(self.up_blocks), final=True)
+
+    def forward_tokens_group(self, eng: Engine, units, timestep, motion_scale, time_proj=None, deep_from: int = 2):
+        """Several independent forwards (context windows / CFG branches of one DDIM step) with the DEEP levels batched.
+        ``units``: list of dicts(x, pose, ehs, audio, full, face, body, B, F, ref) -- the arguments of ``forward_tokens``.
+        The first ``deep_from`` down blocks (and the matching last up blocks: 64x64 and 32x32 latents at 512x512) run unit
+        by unit, so their tensors stay L2-sized; down blocks ``deep_from``.., the mid block and the first up blocks run ONCE on
+        the frames of all units concatenated (16x16 and 8x8: a 12-frame window gives those GEMMs M = 6144 / 1536 rows, 48 / 12
+        tiles for 148 SMs; ten windows fill the machine and amortise ~1200 launches).  Every layer is per sample / per
+        frame / per (sample, pixel), so the result is the same as ``forward_tokens`` unit by unit.  -> list of outputs."""
+        if len(units) == 1 or deep_from <= 0 or deep_from >= len(self.down_blocks):
+            return [self.forward_tokens(eng, u["x"], timestep, u["ehs"], u["audio"], u["pose"], u["full"], u["face"], u["body"],
+                                        motion_scale, u["B"], u["F"], ref_index=u["ref"], time_proj=time_proj) for u in units]
+        F = units[0]["F"]
+        if any(u["F"] != F for u in units):
+            raise ValueError("forward_tokens_group: all units must have the same number of frames per sample")
+        reaches = self._motion_scale_reaches_audio()
+        n_up_deep = len(self.up_blocks) - deep_from
+        sis, tops, xs = [], [], []
+        for u in units:
+            si = self._step_inputs(eng, u["x"], timestep, u["ehs"], u["audio"], u["full"], u["face"], u["body"], motion_scale,
+                                   u["B"], u["F"], u["ref"], None, time_proj)
+            x, skips = self._run_down(eng, u["x"], u["pose"], si, reaches, 0, deep_from)
+            sis.append(si)
+            tops.append(skips)
+            xs.append(x)
+        # ---- deep levels: one batched pass over the frames of all units
+        Bt = sum(u["B"] for u in units)
+        have_audio = sis[0].audio_rows is not None
+        masks = None
+        if have_audio:
+            masks = [None if lvl < deep_from else tuple(torch.cat([si.masks[lvl][r] for si in sis]) for r in range(3))
+                     for lvl in range(len(sis[0].masks))]
+        tp0 = sis[0].temb_silu
+        tproj = type(tp0)(tp0.all_proj[:1].expand(Bt, -1).contiguous(), tp0.offsets)       # same timestep for every sample
+        seg2 = None
+        if sis[0].seg2_index is not None:
+            seg2 = torch.cat([si.seg2_index for si in sis])
+            seg2._n_seg2 = sum(getattr(si.seg2_index, "_n_seg2", si.seg2_index.numel()) for si in sis)   # bench FLOP accounting
+        si_deep = StepInputs(frames=F, temb_silu=tproj, clip=torch.cat([si.clip for si in sis]), seg2_index=seg2,
+                             audio_rows=torch.cat([si.audio_rows for si in sis]) if have_audio else None, masks=masks,
+                             scale=sis[0].scale, shard=None)
+        X = torch.cat(xs)
+        x, deep_skips = self._run_down(eng, X, None, si_deep, reaches, deep_from, len(self.down_blocks), skips=[X])
+        x = self.mid_block.run(eng, x, si_deep)
+        y = self._run_up(eng, x, deep_skips, si_deep, 0, n_up_deep, final=False)
+        assert len(deep_skips) == 0
+        # ---- back to the units
+        outs, n0 = [], 0
+        for u, si, skips in zip(units, sis, tops):
+            n = u["B"] * u["F"]
+            skips.pop()                      # the last top skip is the deep input itself (consumed inside the batch)
+            outs.append(self._run_up(eng, y[n0:n0 + n], skips, si, n_up_deep, len(self.up_blocks), final=True))
+            n0 += n
+        return outs
+
+    def _run_down(self, eng, x, pose, si, reaches, lo, hi, skips=None):
+        if lo == 0:
+            # pre-process: conv_in (+ pose features fused as the residual) (unet_3d.py:517-519)
+            x = self.conv_in.run(eng, x, residual=pose)
+            skips = [x]
+        for blk in list(self.down_blocks)[lo:hi]:
+            if isinstance(blk, CrossAttnDownBlock3D):
+                x, outs = blk.run(eng, x, si, reaches)
+            else:
+                x, outs = blk.run(eng, x, si)
+            skips += outs
+        return x, skips
+
+    def _run_up(self, eng, x, skips, si, lo, hi, final):
+        for blk in list(self.up_blocks)[lo:hi]:
+            x = blk.run(eng, x, skips, si)
+        if not final:
+            return x
+        x = self.conv_norm_out.run(eng, x, None, silu=True)
+        return self.conv_out.run(eng, x)
+
+    def _step_inputs(self, eng: Engine, x, timestep, encoder_hidden_states, audio_embedding, full_mask, face_mask, body_mask,
+                     motion_scale, B: int, F: int, ref_index=None, shard=None, time_proj=None):
+        """Validation + the per-forward conditioning every block shares (StepInputs)."""
         N, H, W, _ = x.shape
         dev = eng.device
         down = 2 ** self.num_upsamplers
@@ -411,19 +496,4 @@ class UNet3DConditionModel(nn.Module):
         scale = tuple(float(s) for s in motion_scale) if motion_scale is not None else (1.0, 1.0, 1.0)
         si = StepInputs(frames=F, temb_silu=temb_silu, clip=clip, seg2_index=seg2, audio_rows=audio_rows, masks=masks,
                         scale=scale, shard=shard)
-        reaches = self._motion_scale_reaches_audio()
-
-        # --- pre-process: conv_in (+ pose features fused as the residual) (unet_3d.py:517-519)
-        x = self.conv_in.run(eng, x, residual=pose)
-        skips = [x]
-        for blk in self.down_blocks:
-            if isinstance(blk, CrossAttnDownBlock3D):
-                x, outs = blk.run(eng, x, si, reaches)
-            else:
-                x, outs = blk.run(eng, x, si)
-            skips += outs
-        x = self.mid_block.run(eng, x, si)
-        for blk in self.up_blocks:
-            x = blk.run(eng, x, skips, si)
-        x = self.conv_norm_out.run(eng, x, None, silu=True)
-        return self.conv_out.run(eng, x)
+        return si

@@ -6,6 +6,6 @@ cat gpurun_out/r2_pytest4.log | tail -12
 timeout 300 python profiles/run_ops.py --time > gpurun_out/r2_ops_time4.txt 2>&1; cat gpurun_out/r2_ops_time4.txt
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --ops-out gpurun_out/r2_ops_step4.txt > gpurun_out/r2_bench4.json 2> gpurun_out/r2_bench4.err
 tail -42 gpurun_out/r2_bench4.err; cat gpurun_out/r2_bench4.json
-for f in "--fuse-ln 0" "--attn-v2 0" "--gn-split 0" "--fuse-ln 0 --gn-split 0 --attn-v2 0"; do
+for f in "--fuse-ln 0" "--attn-v2 0" "--gn-split 0" "--deep-batch 1" "--fuse-ln 0 --gn-split 0 --attn-v2 0 --deep-batch 1"; do
   echo "== $f"; timeout 300 python bench.py --quick --steps 3 --warmup 2 $f 2> gpurun_out/r2_ab4.err | tee -a gpurun_out/r2_ab4.jsonl; tail -2 gpurun_out/r2_ab4.err
 done

@@ -486,3 +486,34 @@ def test_decode_latents_chunked_and_frame_sharded_matches_the_sequential_referen
     assert res[0][2] == [2, 2] and res[1][2] == [2, 1]                      # 4 + 3 frames, two per call
     for _, o, _ in res:
         assert np.abs(o - ref).max() < 1e-5
+
+
+def test_forward_tokens_group_matches_unit_by_unit_on_cpu():
+    """Deep-level batching (UNet3DConditionModel.forward_tokens_group): three units -- two CFG windows and one single-branch
+    forward -- with the 16x16 / 8x8 levels run as one batch vs forward_tokens unit by unit (fake engine, float32)."""
+    spec, sd, unet = _tiny_unet()
+    L, latent, frames = 12, 16, 4
+    inp = make_inputs(spec, L, latent, seed=5)
+    attach_banks(unet, spec, make_banks(spec, latent), cfg=True)
+    eng = FakeEngine()
+    units, refs = [], []
+    for lo, branches in ((0, (0, 1)), (4, (0, 1)), (8, (1,))):
+        win = window_inputs(inp, list(range(lo, lo + frames)))
+        sel = list(branches)
+        rows = torch.cat([torch.arange(frames) + b * frames for b in branches])
+        un = dict(x=eng.ncfhw_to_tokens(win["sample"][sel]), pose=eng.ncfhw_to_tokens(win["pose_cond_fea"][sel]),
+                  ehs=win["encoder_hidden_states"][sel], audio=win["audio_embedding"][sel],
+                  full=[m[rows] for m in win["full_mask"]], face=[m[rows] for m in win["face_mask"]],
+                  body=[m[rows] for m in win["body_mask"]], B=len(branches), F=frames,
+                  ref=[None if b == 0 else b for b in branches])
+        units.append(un)
+        with torch.no_grad():
+            refs.append(unet.forward_tokens(eng, un["x"], torch.tensor(500), un["ehs"], un["audio"], un["pose"], un["full"],
+                                            un["face"], un["body"], inp["motion_scale"], un["B"], frames, ref_index=un["ref"]))
+    eng2 = FakeEngine()
+    with torch.no_grad():
+        outs = unet.forward_tokens_group(eng2, units, torch.tensor(500), inp["motion_scale"])
+    for o, r in zip(outs, refs):
+        assert o.shape == r.shape and rel_l2(o, r) < 2e-6
+    # fewer operator calls: the deep levels ran once for all three units
+    assert eng2.calls["gemm"] < eng.calls["gemm"] and eng2.calls["conv3x3"] < eng.calls["conv3x3"]
