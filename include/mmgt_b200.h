@@ -64,8 +64,10 @@ MMGT_API const char* mmgt_last_error(void);
  *         arrival barrier (grid limited to co-resident CTAs).  A/B switch.
  * flag 8: stride-2 and upsampling 3x3 convolutions as implicit GEMMs (TMA traversal stride 2; four sub-pixel 2x2-tap
  *         convolutions) (default 1); 0 = stage an im2col matrix and run the plain GEMM.  A/B switch.
- * flag 9: head dim <= 64 attention on the kernel with three rotating S buffers and P aliased over S (default 1);
- *         0 = the two-buffer kernel of round 1.  A/B switch. */
+ * flag 9: head dim <= 64 attention on the kernel with three rotating S buffers and P aliased over S; default 0 = the
+ *         two-buffer kernel, which measured 1.5 % faster per DDIM step (profiles/r2_ab_flags.md).  A/B switch.
+ * flag 10: temporal attention with head dim <= 80 on the row-coalesced kernel (one CTA per (batch, pixel), whole q|k|v rows
+ *         through double-buffered cp.async) (default 1); 0 = one warp per (batch, pixel, head).  A/B switch. */
 MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);
 
 /* Layout ------------------------------------------------------------------------------------- */

@@ -170,6 +170,7 @@ class TemporalBasicTransformerBlock(nn.Module):
         self._bank_list: List[torch.Tensor] = []
         self._bank_gen = 0         # bumped whenever ``bank`` is assigned: a freed bank's address can be handed out again
         self._bank_kv = None       # (key, k2, v2, buffer) projected reference keys / values
+        self.write_bank = False    # ReferenceNet write mode (mutual_self_attention.py:139-148): bank.append(norm1(x)), plain self-attention
         self._clip_pack = Pack()
 
     @property
@@ -224,8 +225,15 @@ class TemporalBasicTransformerBlock(nn.Module):
         heads = self.attn1.heads
         x = tok.view(rows, C)
         pk = self.attn1.packed(eng)
-        qkv = ln_qkv(eng, x, self.norm1, self.attn1).view(N, T, 3 * C)
-        bkv = self.bank_kv(eng)
+        if self.write_bank:
+            # write mode: the normalised hidden states ARE the reference features (one (B, T, C) tensor per block)
+            n1 = self.norm1.run(eng, x)
+            self._bank_list.append(n1.view(N, T, C).clone())
+            qkv = eng.gemm(n1, pk["qkv"]).view(N, T, 3 * C)
+            bkv = None
+        else:
+            qkv = ln_qkv(eng, x, self.norm1, self.attn1).view(N, T, 3 * C)
+            bkv = self.bank_kv(eng)
         k2, v2 = bkv if bkv is not None else (None, None)
         a = eng.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, k2=k2, v2=v2,
                           seg2_index=seg2_index if bkv is not None else None)

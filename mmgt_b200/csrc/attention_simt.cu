@@ -350,6 +350,128 @@ temporal_attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Temporal attention, row-coalesced form (head dim <= 80): one CTA of `heads` warps owns one (batch, pixel) at a time and
+// moves WHOLE token rows -- the F rows (q | k | v of all heads, 3C values, contiguous) come in through cp.async into a
+// double-buffered shared-memory stage, so every global access is a full 16-byte vector of a contiguous row (the per-head
+// kernel above fetches 80-byte head slices: 2.5 sectors each, one (b, t, head) per warp with nothing in flight while it
+// computes).  Warp h then runs the same m16n8k16 sequence on head h and writes O over its Q slice; the F output rows
+// (C values, contiguous) are stored by all threads.  The loads of pixel i + 1 are in flight during the math of pixel i.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int DK>
+__global__ void __launch_bounds__(512)
+temporal_attention_rows_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B, int F, int T_tok, int heads, int d,
+                               float scale_log2e) {
+  pdl_prologue();
+  constexpr int DP = DK + 8;
+  extern __shared__ __align__(16) uint8_t smem_u8[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthr = blockDim.x;
+  const int C = heads * d, cv = C >> 3, v3 = 3 * cv;                 // 16-byte vectors per C / per q|k|v row
+  const int stage_elems = 3 * heads * 16 * DP;                        // [q|k|v][head][16 rows][DP]
+  bf16* stage0 = reinterpret_cast<bf16*>(smem_u8);
+  // zero both stages once: rows >= F and columns >= d are never written (loads and O stores touch the valid region only)
+  for (int i = threadIdx.x; i < 2 * stage_elems / 8; i += nthr) reinterpret_cast<uint4*>(stage0)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  const int64_t items = (int64_t)B * T_tok;
+  auto issue = [&](int64_t item, int buf) {
+    if (item < items) {
+      const int t = item % T_tok, b = item / T_tok;
+      bf16* st = stage0 + (size_t)buf * stage_elems;
+      for (int i = threadIdx.x; i < F * v3; i += nthr) {
+        const int f = i / v3, v = i - f * v3;
+        const int which = v / cv, e = (v - which * cv) * 8;           // element inside C
+        const int h = e / d, c = e - h * d;
+        cp_async16(st + ((size_t)(which * heads + h) * 16 + f) * DP + c,
+                   qkv + (((int64_t)b * F + f) * T_tok + t) * (3 * C) + (size_t)v * 8);
+      }
+    }
+    cp_async_commit();
+  };
+  const int qrow = lane >> 2, qcol = (lane & 3) * 2;   // accumulator fragment coordinates
+  issue(blockIdx.x, 0);
+  int it = 0;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    issue(item + gridDim.x, buf ^ 1);
+    cp_async_wait<1>();
+    __syncthreads();
+    bf16* st = stage0 + (size_t)buf * stage_elems;
+    bf16* Qs = st + (size_t)warp * 16 * DP;
+    bf16* Ks = st + (size_t)(heads + warp) * 16 * DP;
+    bf16* Vs = st + (size_t)(2 * heads + warp) * 16 * DP;
+    const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(Qs), k_addr = (uint32_t)__cvta_generic_to_shared(Ks),
+                   v_addr = (uint32_t)__cvta_generic_to_shared(Vs);
+    // ---- S = Q K^T : two 16x8 accumulator tiles (keys 0-7, 8-15)
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < DK / 16; ++ks) {
+      uint32_t a[4], bb[4];
+      ldsm_x4(q_addr + (((lane & 7) + ((lane >> 3) & 1) * 8) * DP + ks * 16 + (lane >> 4) * 8) * 2, a);
+      ldsm_x4(k_addr + (((lane & 7) + (lane >> 4) * 8) * DP + ks * 16 + ((lane >> 3) & 1) * 8) * 2, bb);
+      mma_bf16_16816(s0, a, bb[0], bb[1]);
+      mma_bf16_16816(s1, a, bb[2], bb[3]);
+    }
+    float p[8] = {s0[0], s0[1], s1[0], s1[1], s0[2], s0[3], s1[2], s1[3]};  // [row lo: k0,k1,k8,k9 | row hi: ...]
+    const int kc[4] = {qcol, qcol + 1, qcol + 8, qcol + 9};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (kc[j] >= F) p[r * 4 + j] = -INFINITY;
+        mx = fmaxf(mx, p[r * 4 + j]);
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        p[r * 4 + j] = exp2f((p[r * 4 + j] - mx) * scale_log2e);
+        sum += p[r * 4 + j];
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p[r * 4 + j] *= inv;
+    }
+    const uint32_t pa[4] = {pack2(p[0], p[1]), pack2(p[4], p[5]), pack2(p[2], p[3]), pack2(p[6], p[7])};
+    __syncwarp();   // every lane is done reading this head's Q before it receives O
+    for (int n0 = 0; n0 < d; n0 += 16) {
+      uint32_t vb[4];
+      ldsm_x4_trans(v_addr + (((lane & 7) + ((lane >> 3) & 1) * 8) * DP + n0 + (lane >> 4) * 8) * 2, vb);
+      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(o0, pa, vb[0], vb[1]);
+      mma_bf16_16816(o1, pa, vb[2], vb[3]);
+      // valid rows / columns only: the zero padding of the stage must survive
+      if (qrow < F) *reinterpret_cast<uint32_t*>(Qs + qrow * DP + n0 + qcol) = pack2(o0[0], o0[1]);
+      if (qrow + 8 < F) *reinterpret_cast<uint32_t*>(Qs + (qrow + 8) * DP + n0 + qcol) = pack2(o0[2], o0[3]);
+      if (n0 + 8 < d) {
+        if (qrow < F) *reinterpret_cast<uint32_t*>(Qs + qrow * DP + n0 + 8 + qcol) = pack2(o1[0], o1[1]);
+        if (qrow + 8 < F) *reinterpret_cast<uint32_t*>(Qs + (qrow + 8) * DP + n0 + 8 + qcol) = pack2(o1[2], o1[3]);
+      }
+    }
+    __syncthreads();
+    {   // the F output rows of this pixel, C contiguous values each
+      const int t = item % T_tok, b = item / T_tok;
+      for (int i = threadIdx.x; i < F * cv; i += nthr) {
+        const int f = i / cv, e = (i - f * cv) * 8;
+        const int h = e / d, c = e - h * d;
+        *reinterpret_cast<uint4*>(out + (((int64_t)b * F + f) * T_tok + t) * C + e) =
+            *reinterpret_cast<const uint4*>(st + ((size_t)h * 16 + f) * DP + c);
+      }
+    }
+    __syncthreads();   // the stage is free for the loads of item + 2 * gridDim.x (issued at the top of the next iteration)
+  }
+  cp_async_wait<0>();
+}
+
 }  // namespace
 
 extern "C" int mmgt_attention(mmgt_ctx* ctx, const mmgt_attention_params* p, void* stream) {
@@ -397,6 +519,32 @@ extern "C" int mmgt_temporal_attention(mmgt_ctx* ctx, const void* qkv, void* out
   MMGT_CHECK_ARG(F <= 32, MMGT_E_UNSUPPORTED, "temporal_attention: F=%d > 32 (positional table max_len is 32)", F);
   MMGT_CHECK_ARG(d % 4 == 0, MMGT_E_UNSUPPORTED, "temporal_attention: head dim must be a multiple of 4");
   MMGT_CHECK_ARG(aligned16(qkv), MMGT_E_ALIGN, "temporal_attention: qkv must be 16B aligned");
+  if (dtype == MMGT_BF16 && ctx->use_tc && ctx->temporal_rows && F <= 16 && d % 8 == 0 && d <= 80 && heads <= 16) {
+    const int DK = (d + 15) / 16 * 16;
+    const size_t smem = (size_t)2 * 3 * heads * 16 * (DK + 8) * 2;
+    if ((int)smem <= ctx->max_smem_optin) {
+      const int per_sm = std::max(1, (int)((size_t)ctx->max_smem_optin / (smem + 1024)));
+      const int64_t items = (int64_t)B * T;
+      const int blocks = (int)std::min<int64_t>(items, (int64_t)ctx->num_sms * per_sm);
+      const float sl2 = scale * 1.4426950408889634f;
+#define RLAUNCH(DK_)                                                                                                       \
+  do {                                                                                                                     \
+    MMGT_CUDA_OK(mmgt_smem_optin(ctx, temporal_attention_rows_kernel<DK_>, ctx->max_smem_optin));                          \
+    MMGT_CUDA_OK(mmgt_launch(ctx, temporal_attention_rows_kernel<DK_>, dim3(blocks), dim3(heads * 32), smem, st,           \
+                             (const bf16*)qkv, (bf16*)out, B, F, T, heads, d, sl2));                                      \
+  } while (0)
+      switch (DK) {
+        case 16: RLAUNCH(16); break;
+        case 32: RLAUNCH(32); break;
+        case 48: RLAUNCH(48); break;
+        case 64: RLAUNCH(64); break;
+        default: RLAUNCH(80); break;
+      }
+#undef RLAUNCH
+      MMGT_LAUNCH_OK(ctx);
+      return 0;
+    }
+  }
   if (dtype == MMGT_BF16 && ctx->use_tc && F <= 16 && d % 8 == 0 && d <= 160) {
     const int DK = (d + 15) / 16 * 16;
     const size_t smem = (size_t)TMW * 3 * 16 * (DK + 8) * 2;

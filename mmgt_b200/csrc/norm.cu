@@ -78,7 +78,7 @@ gn_fused_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restric
                 int T_tok, int C1, int C2, int groups, float eps, int silu, int tok_per_block, int chunks) {
   constexpr int VEC = VecOf<T>::N;
   typedef typename VecOf<T>::type Raw;
-  constexpr int UNR = 4 / NV < 1 ? 1 : 4 / NV;   // 16-byte loads in flight per thread = UNR * NV (kept packed)
+  constexpr int UNR = 8 / NV < 1 ? 1 : 8 / NV;   // 16-byte loads in flight per thread = UNR * NV (kept packed)
   pdl_prologue();   // launched plainly (a memset node precedes it), but lets the NEXT kernel be scheduled early
   extern __shared__ float sm[];  // phase 1: [2][C] channel partial sums; phase 3: scale[C], shift[C]
   const int C = C1 + C2, Cv = C / VEC, C1v = C1 / VEC, cpg = C / groups;
@@ -234,7 +234,7 @@ gn_stats_kernel(const T* __restrict__ x1, const T* __restrict__ x2, double* __re
                 int groups, int tok_per_block) {
   constexpr int VEC = VecOf<T>::N;
   typedef typename VecOf<T>::type Raw;
-  constexpr int UNR = 4 / NV < 1 ? 1 : 4 / NV;
+  constexpr int UNR = 8 / NV < 1 ? 1 : 8 / NV;
   pdl_prologue();
   extern __shared__ float sm[];   // [2][rows_per_pass][C] per-thread partial sums
   const int C = C1 + C2, Cv = C / VEC, C1v = C1 / VEC, cpg = C / groups;
@@ -307,7 +307,7 @@ gn_apply_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restric
                 float eps, int silu, int tok_per_block) {
   constexpr int VEC = VecOf<T>::N;
   typedef typename VecOf<T>::type Raw;
-  constexpr int UNR = 4 / NV < 1 ? 1 : 4 / NV;
+  constexpr int UNR = 8 / NV < 1 ? 1 : 8 / NV;
   pdl_prologue();
   extern __shared__ float sm[];   // scale[C], shift[C]
   const int C = C1 + C2, Cv = C / VEC, C1v = C1 / VEC, cpg = C / groups;
@@ -651,7 +651,7 @@ extern "C" int mmgt_groupnorm(mmgt_ctx* ctx, const void* x1, const void* x2, voi
   if (ctx->gn_split) {
     // statistics kernel + normalise kernel: grid (token chunks, frames), ~8 CTAs per SM worth of chunks
     const int want = std::max(1, (ctx->num_sms * 8 + N - 1) / N);
-    const int unr = std::max(1, 4 / nv);
+    const int unr = std::max(1, 8 / nv);
     int tok_per_block = std::max((T + want - 1) / want, rpp * unr);
     tok_per_block = (tok_per_block + rpp - 1) / rpp * rpp;
     const int chunks = (T + tok_per_block - 1) / tok_per_block;

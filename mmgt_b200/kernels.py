@@ -46,7 +46,11 @@ class Engine:
         self._stats_ws = None
         self._conv_ws = None
         self.unfused_exchange = False   # A/B switch: GEMM + mmgt_row_exchange_copy instead of the fused epilogue
-        self.fuse_layernorm = True      # bf16 tensor-core tier: LayerNorm applied in the consuming GEMM's epilogue
+        # bf16 tensor-core tier: LayerNorm applied in the consuming GEMM's epilogue (row statistics kernel + rowstats /
+        # colsum).  Off by default: at the model's widths the GEMMs that consume a LayerNorm are paced by their epilogue
+        # (K = 320 .. 1280), and the extra epilogue work costs what the saved pass gains (479.6 vs 481.6 ms per step,
+        # profiles/r2_ab_flags.md).  Kept as a tested option (bench.py --fuse-ln 1).
+        self.fuse_layernorm = False
         self.prof = None          # optional: dict key -> [events..., flops, bytes] filled by bench.py's roofline pass
 
     # ------------------------------------------------------------------ per-launch timing (bench.py only)

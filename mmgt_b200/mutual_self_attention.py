@@ -71,7 +71,10 @@ class ReferenceAttentionControl:
             for i, m in enumerate(blocks):
                 m.bank = []
                 m.attn_weight = float(i) / float(len(blocks))
-                self._hooks.append(m.register_forward_pre_hook(_bank_write_hook))
+                if isinstance(m, TemporalBasicTransformerBlock):
+                    m.write_bank = True          # this package's ReferenceNet (unet_2d_condition.py): banked inside run()
+                else:
+                    self._hooks.append(m.register_forward_pre_hook(_bank_write_hook))
         elif reference_attn:
             blocks = _reader_blocks(unet, fusion_blocks)
             for i, m in enumerate(blocks):
@@ -114,7 +117,11 @@ class ReferenceAttentionControl:
             r.bank.clear()        # the projected K/V buffer stays allocated: a captured CUDA graph may still point at it
 
     def remove(self):
-        """Write mode: take the pre-hooks off the ReferenceNet again."""
+        """Write mode: take the pre-hooks / write flags off the ReferenceNet again."""
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        if self.mode == "write":
+            for m in _writer_blocks(self.unet, self.fusion_blocks, need_bank=False):
+                if isinstance(m, TemporalBasicTransformerBlock):
+                    m.write_bank = False

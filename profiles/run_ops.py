@@ -133,7 +133,7 @@ def main():
     ap.add_argument("ops", nargs="*")
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--attn-v1", action="store_true", help="A/B: the round-1 two-buffer attention kernel for head dim <= 64")
+    ap.add_argument("--attn-v2", action="store_true", help="A/B: the three-S-buffer attention kernel for head dim <= 64")
     ap.add_argument("--gn-fused", action="store_true", help="A/B: the round-1 single-kernel GroupNorm (spin barrier)")
     ap.add_argument("--conv-im2col", action="store_true", help="A/B: stride-2 / upsampling convs through a staged im2col matrix")
     ap.add_argument("--geglu-exact", action="store_true", help="A/B: erf GELU in the GEGLU epilogue")
@@ -141,7 +141,7 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     eng = get_engine(dev, torch.bfloat16)
-    eng.ctx.set_attention_v2(not args.attn_v1)
+    eng.ctx.set_attention_v2(args.attn_v2)
     eng.ctx.set_groupnorm_split(not args.gn_fused)
     eng.ctx.set_conv_implicit_all(not args.conv_im2col)
     eng.ctx.set_geglu_exact(args.geglu_exact)

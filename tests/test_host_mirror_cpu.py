@@ -517,3 +517,47 @@ def test_forward_tokens_group_matches_unit_by_unit_on_cpu():
         assert o.shape == r.shape and rel_l2(o, r) < 2e-6
     # fewer operator calls: the deep levels ran once for all three units
     assert eng2.calls["gemm"] < eng.calls["gemm"] and eng2.calls["conv3x3"] < eng.calls["conv3x3"]
+
+
+def _tiny_refnet(device="cpu"):
+    import json
+    from mmgt_b200.unet_2d_condition import UNet2DConditionModel
+    from oracle.reference_loader import SD15_CFG
+    from oracle.weights import make_state_dict
+    with open(os.path.join(GOLD, "refnet_spec.json")) as f:
+        spec = [(k, tuple(s)) for k, s in json.load(f)]
+    cfg = dict(SD15_CFG)
+    cfg.update(block_out_channels=list(TINY), down_block_types=["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"],
+               up_block_types=["UpBlock2D"] + ["CrossAttnUpBlock2D"] * 3, mid_block_type="UNetMidBlock2DCrossAttn")
+    net = UNet2DConditionModel.from_config(cfg)
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == spec        # the SD-1.5 2-D UNet's 686 tensors
+    net.load_state_dict(make_state_dict(spec, seed=8), strict=True)
+    return net.to(device)
+
+
+def _check_refnet_banks(net, tol):
+    from mmgt_b200.mutual_self_attention import ReferenceAttentionControl, _writer_blocks
+    from oracle.make_golden_refnet import refnet_inputs
+    g = np.load(os.path.join(GOLD, "refnet_tiny.npz"))
+    dev = next(net.parameters()).device
+    writer = ReferenceAttentionControl(net, do_classifier_free_guidance=True, mode="write", batch_size=1, fusion_blocks="full")
+    x, ehs = refnet_inputs()
+    out = net(x.to(dev), torch.zeros((), dtype=torch.long, device=dev), encoder_hidden_states=ehs.to(dev), return_dict=False)[0]
+    blocks = _writer_blocks(net, "full")
+    assert len(blocks) == 16 and all(len(b.bank) == 1 for b in blocks)
+    errs = [rel_l2(b.bank[0], torch.from_numpy(g[f"bank{i:02d}"])) for i, b in enumerate(blocks)]
+    e_out = rel_l2(out, torch.from_numpy(g["out"]))
+    assert max(errs) < tol and e_out < 2 * tol, (max(errs), e_out)
+    writer.clear()
+    writer.remove()
+    assert all(len(b.bank) == 0 and not b.write_bank for b in blocks)
+    return max(errs), e_out
+
+
+def test_reference_net_write_pass_host_mirror_on_cpu(monkeypatch):
+    """f1: the ReferenceNet (SD-1.5 2-D UNet = this package's UNet without motion / audio modules, one frame per sample)
+    in write mode on the fake engine vs banks produced by the reference's own classes (oracle/make_golden_refnet.py)."""
+    net = _tiny_refnet()
+    eng = FakeEngine()
+    monkeypatch.setattr(net, "_engine", lambda device: eng)
+    _check_refnet_banks(net, 2e-5)

@@ -461,11 +461,11 @@ def test_attention_two_segments(dev, dtype, tc, N, Lq, Lk, Lk2, heads, d):
             k2, v2 = bank[:, :, :C], bank[:, :, C:]
             idx = torch.tensor([(-1 if i % 3 == 0 else i % 2) for i in range(N)], dtype=torch.int32, device=dev)
             out = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
-            if tc and d <= 64:      # the round-1 two-buffer kernel (flag 9 off) must agree with the default one
-                eng.ctx.set_attention_v2(False)
-                old = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
+            if tc and d <= 64:      # the three-S-buffer kernel (flag 9) must agree with the default two-buffer one
                 eng.ctx.set_attention_v2(True)
-                assert rel_l2(out.float(), old.float()) < 4e-3
+                alt = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
+                eng.ctx.set_attention_v2(False)
+                assert rel_l2(out.float(), alt.float()) < 4e-3
             refs = []
             for n in range(N):
                 kk, vv = k[n:n + 1], v[n:n + 1]
@@ -480,7 +480,7 @@ def test_attention_two_segments(dev, dtype, tc, N, Lq, Lk, Lk2, heads, d):
         assert rel_l2(out.float(), ref) < (2e-5 if dtype == torch.float32 else 8e-3)
     finally:
         eng.ctx.set_tensor_cores(True)
-        eng.ctx.set_attention_v2(True)
+        eng.ctx.set_attention_v2(False)
 
 
 def test_attention_running_max_jumps_late(dev):
@@ -506,11 +506,13 @@ def test_attention_running_max_jumps_late(dev):
             assert torch.isfinite(out).all()
             assert rel_l2(out.float(), ref) < 1e-2, v2_kernel
     finally:
-        eng.ctx.set_attention_v2(True)
+        eng.ctx.set_attention_v2(False)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,Fr,T,heads,d", [(2, 12, 16, 8, 40), (1, 8, 64, 8, 8), (2, 4, 9, 8, 160), (1, 32, 4, 8, 80)])
+@pytest.mark.parametrize("B,Fr,T,heads,d", [(2, 12, 16, 8, 40), (1, 8, 64, 8, 8), (2, 4, 9, 8, 160), (1, 32, 4, 8, 80),
+                                            (2, 12, 1024, 8, 80), (1, 16, 333, 8, 40), (3, 5, 7, 8, 64), (2, 12, 4096, 8, 40),
+                                            (1, 3, 50, 4, 16), (24, 12, 64, 8, 160)])
 def test_temporal_attention(dev, dtype, B, Fr, T, heads, d):
     eng = eng_for(dev, dtype)
     C = heads * d
@@ -520,6 +522,13 @@ def test_temporal_attention(dev, dtype, B, Fr, T, heads, d):
     ref = _attn_ref(x[:, :, :C], x[:, :, C:2 * C], x[:, :, 2 * C:], heads)
     ref = ref.view(B, T, Fr, C).permute(0, 2, 1, 3).reshape(B * Fr * T, C)
     assert rel_l2(out.float(), ref) < (2e-5 if dtype == torch.float32 else 8e-3)
+    if dtype == torch.bfloat16:     # row-coalesced kernel (default for head dim <= 80) vs one warp per (batch, pixel, head)
+        try:
+            eng.ctx.set_temporal_rows(False)
+            old = eng.temporal_attention(qkv, B, Fr, T, heads)
+        finally:
+            eng.ctx.set_temporal_rows(True)
+        assert rel_l2(out.float(), old.float()) < 1e-3
 
 
 def test_mask_pyramid_bit_exact(dev):

@@ -68,6 +68,36 @@ def test_tiny_unet_matches_reference_golden(compute_dtype, tc, tol):
         unet._engine(torch.device("cuda", 0)).ctx.set_tensor_cores(True)
 
 
+def test_tiny_unet_optional_kernel_paths_match_reference_golden():
+    """The A/B alternatives that are NOT the default must stay correct through the whole UNet: LayerNorm folded into the
+    consuming GEMMs (Engine.fuse_layernorm), the three-S-buffer attention kernel, the single-kernel GroupNorm, the staged
+    im2col convolutions, the per-head temporal attention kernel, erf GELU in the GEGLU epilogue."""
+    g, spec, sd, unet, banks, win, frames, t = _setup("tiny", TINY, torch.bfloat16)
+    eng = unet._engine(torch.device("cuda", 0))
+    attach_banks(unet, spec, banks, cfg=True)
+    unet.train()
+    unet.enable_gradient_checkpointing()
+    ref = torch.from_numpy(g["out_scripts"])
+    base = rel_l2(run_cuda_unet(unet, win, t), ref)
+    try:
+        eng.fuse_layernorm = True
+        eng.ctx.set_attention_v2(True)
+        eng.ctx.set_groupnorm_split(False)
+        eng.ctx.set_conv_implicit_all(False)
+        eng.ctx.set_temporal_rows(False)
+        eng.ctx.set_geglu_exact(True)
+        alt = rel_l2(run_cuda_unet(unet, win, t), ref)
+    finally:
+        eng.fuse_layernorm = False
+        eng.ctx.set_attention_v2(False)
+        eng.ctx.set_groupnorm_split(True)
+        eng.ctx.set_conv_implicit_all(True)
+        eng.ctx.set_temporal_rows(True)
+        eng.ctx.set_geglu_exact(False)
+    print(f"tiny bf16: default kernels {base:.3e}, alternative kernels {alt:.3e}")
+    assert base < TOL_BF16_FWD and alt < TOL_BF16_FWD
+
+
 def test_tiny_unet_float32_vs_oracle_fresh_seed_and_ragged_window():
     """Oracle on the CPU vs CUDA on a different seed, 5 frames (ragged vs the 4-frame golden), timestep 999."""
     spec = UNetSpec(block_out_channels=TINY)
