@@ -379,17 +379,45 @@ temporal_attention_rows_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ 
   for (int i = threadIdx.x; i < 2 * stage_elems / 8; i += nthr) reinterpret_cast<uint4*>(stage0)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   const int64_t items = (int64_t)B * T_tok;
+  // Source / destination offsets of this thread's 16-byte vectors do not depend on the pixel: computed once (the
+  // divisions by runtime widths cost more than the copies they address), relative to the pixel's first row / the stage.
+  constexpr int MAXV = 12;                                            // F * v3 / nthr <= 16 * 3 * C / (8 * 32 * heads) = 0.1875 d
+  int src_off[MAXV], dst_off[MAXV];
+  const int n_in = F * v3;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = threadIdx.x + k * nthr;
+    src_off[k] = dst_off[k] = -1;
+    if (i < n_in) {
+      const int f = i / v3, v = i - f * v3;
+      const int which = v / cv, e = (v - which * cv) * 8;             // element inside C
+      const int h = e / d, c = e - h * d;
+      src_off[k] = f * T_tok * 3 * C + v * 8;
+      dst_off[k] = ((which * heads + h) * 16 + f) * DP + c;
+    }
+  }
+  constexpr int MAXO = 4;
+  int osrc[MAXO], odst[MAXO];
+  const int n_out = F * cv;
+#pragma unroll
+  for (int k = 0; k < MAXO; ++k) {
+    const int i = threadIdx.x + k * nthr;
+    osrc[k] = odst[k] = -1;
+    if (i < n_out) {
+      const int f = i / cv, e = (i - f * cv) * 8;
+      const int h = e / d, c = e - h * d;
+      osrc[k] = (h * 16 + f) * DP + c;
+      odst[k] = f * T_tok * C + e;
+    }
+  }
   auto issue = [&](int64_t item, int buf) {
     if (item < items) {
       const int t = item % T_tok, b = item / T_tok;
       bf16* st = stage0 + (size_t)buf * stage_elems;
-      for (int i = threadIdx.x; i < F * v3; i += nthr) {
-        const int f = i / v3, v = i - f * v3;
-        const int which = v / cv, e = (v - which * cv) * 8;           // element inside C
-        const int h = e / d, c = e - h * d;
-        cp_async16(st + ((size_t)(which * heads + h) * 16 + f) * DP + c,
-                   qkv + (((int64_t)b * F + f) * T_tok + t) * (3 * C) + (size_t)v * 8);
-      }
+      const bf16* base = qkv + ((int64_t)b * F * T_tok + t) * (3 * C);
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k)
+        if (src_off[k] >= 0) cp_async16(st + dst_off[k], base + src_off[k]);
     }
     cp_async_commit();
   };
@@ -460,12 +488,10 @@ temporal_attention_rows_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ 
     __syncthreads();
     {   // the F output rows of this pixel, C contiguous values each
       const int t = item % T_tok, b = item / T_tok;
-      for (int i = threadIdx.x; i < F * cv; i += nthr) {
-        const int f = i / cv, e = (i - f * cv) * 8;
-        const int h = e / d, c = e - h * d;
-        *reinterpret_cast<uint4*>(out + (((int64_t)b * F + f) * T_tok + t) * C + e) =
-            *reinterpret_cast<const uint4*>(st + ((size_t)h * 16 + f) * DP + c);
-      }
+      bf16* obase = out + ((int64_t)b * F * T_tok + t) * C;
+#pragma unroll
+      for (int k = 0; k < MAXO; ++k)
+        if (osrc[k] >= 0) *reinterpret_cast<uint4*>(obase + odst[k]) = *reinterpret_cast<const uint4*>(st + osrc[k]);
     }
     __syncthreads();   // the stage is free for the loads of item + 2 * gridDim.x (issued at the top of the next iteration)
   }
@@ -522,7 +548,10 @@ extern "C" int mmgt_temporal_attention(mmgt_ctx* ctx, const void* qkv, void* out
   if (dtype == MMGT_BF16 && ctx->use_tc && ctx->temporal_rows && F <= 16 && d % 8 == 0 && d <= 80 && heads <= 16) {
     const int DK = (d + 15) / 16 * 16;
     const size_t smem = (size_t)2 * 3 * heads * 16 * (DK + 8) * 2;
-    if ((int)smem <= ctx->max_smem_optin) {
+    const int nthr_rows = heads * 32, cvec = heads * d / 8;
+    const bool tables_ok = (F * 3 * cvec + nthr_rows - 1) / nthr_rows <= 12 && (F * cvec + nthr_rows - 1) / nthr_rows <= 4 &&
+                           (int64_t)F * T * 3 * heads * d < (1ll << 31);
+    if ((int)smem <= ctx->max_smem_optin && tables_ok) {
       const int per_sm = std::max(1, (int)((size_t)ctx->max_smem_optin / (smem + 1024)));
       const int64_t items = (int64_t)B * T;
       const int blocks = (int)std::min<int64_t>(items, (int64_t)ctx->num_sms * per_sm);

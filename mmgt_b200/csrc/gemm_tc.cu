@@ -507,20 +507,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(lane_grp * 32) << 16);
+      // TMEM loads run one chunk ahead (ping-pong registers): the tcgen05.ld of chunk i + 1 is in flight while chunk i goes
+      // through bias / activation / residual / store.  (Issued and waited for inside the chunk, the load latency was the
+      // top stall of the epilogue warps of every small-K GEMM: profiles/r2_gemm_epilogue.md.)
+      uint32_t rbuf[2][16], gbuf[GEGLU ? 2 : 1][16];
+      if (c_count > 0) {
+        const int c0 = c_begin * 16;
+        tmem_ld_x16(taddr + (GEGLU ? 2 * c0 : c0), rbuf[0]);
+        if (GEGLU) tmem_ld_x16(taddr + 2 * c0 + 16, gbuf[0]);
+      }
 #pragma unroll
       for (int i = 0; i < CH0; ++i) {
         if (i < c_count) {
           const int c = (c_begin + i) * 16;
-          uint32_t r[16];
+          uint32_t(&r)[16] = rbuf[i & 1];
+          uint32_t(&g)[16] = gbuf[GEGLU ? (i & 1) : 0];
           float v[16];
-          tmem_ld_x16(taddr + (GEGLU ? 2 * c : c), r);
+          tmem_ld_wait();                       // chunk i has landed
+          if (i + 1 < CH0 && i + 1 < c_count) {  // chunk i + 1 -> the other register set
+            const int cn = (c_begin + i + 1) * 16;
+            tmem_ld_x16(taddr + (GEGLU ? 2 * cn : cn), rbuf[(i + 1) & 1]);
+            if (GEGLU) tmem_ld_x16(taddr + 2 * cn + 16, gbuf[GEGLU ? ((i + 1) & 1) : 0]);
+          }
           if (GEGLU) {
-            uint32_t g[16];
-            tmem_ld_x16(taddr + 2 * c + 16, g);
             float bv[16], bg[16];
             lds16_f32(sv + 2 * c, bv);
             lds16_f32(sv + 2 * c + 16, bg);
-            tmem_ld_wait();
             if (args.rowstats) {          // fused LayerNorm (warp-uniform branch): rstd * acc + (-rstd * mean) * colsum + bias
               float cv[16], cg[16];
               lds16_f32(sv + 256 + 2 * c, cv);
@@ -547,7 +559,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             float bv[16];
             lds16_f32(sv + c, bv);
-            tmem_ld_wait();
             if (args.rowstats) {
               float cv[16];
               lds16_f32(sv + 256 + c, cv);

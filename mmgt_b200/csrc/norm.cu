@@ -649,8 +649,9 @@ extern "C" int mmgt_groupnorm(mmgt_ctx* ctx, const void* x1, const void* x2, voi
   const int rpp = GN_THREADS / lanes;
   const size_t smem = sizeof(float) * (2 * C + 2 * groups);
   if (ctx->gn_split) {
-    // statistics kernel + normalise kernel: grid (token chunks, frames), ~8 CTAs per SM worth of chunks
-    const int want = std::max(1, (ctx->num_sms * 8 + N - 1) / N);
+    // statistics kernel + normalise kernel: grid (token chunks, frames) = ONE resident wave (3 CTAs per SM): with 8 waves'
+    // worth of short CTAs the tail and the per-CTA prologue / reduction cost a quarter of the kernel
+    const int want = std::max(1, (ctx->num_sms * 3) / N);
     const int unr = std::max(1, 8 / nv);
     int tok_per_block = std::max((T + want - 1) / want, rpp * unr);
     tok_per_block = (tok_per_block + rpp - 1) / rpp * rpp;

@@ -49,8 +49,8 @@ def test_pose_guider_512_bf16_vs_oracle():
     assert rel_l2(y, ref) < 1e-2
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)], ids=["f32", "bf16tc"])
-def test_reference_net_write_pass_matches_reference_banks(dtype, tol):
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)], ids=["f32", "bf16tc"])
+def test_reference_net_write_pass_matches_reference_banks(dtype, tol):  # bf16: bank taps sit behind up to ~60 bf16-stored layers, same bound as the forward output (TOL_BF16_FWD)
     """ReferenceNet write pass on the kernels: 16 banks vs the reference's own write-mode controller + blocks."""
     from test_host_mirror_cpu import _check_refnet_banks, _tiny_refnet
     net = _tiny_refnet("cuda")
