@@ -23,11 +23,10 @@ constexpr int BK = 64;             // 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 320;            // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int EPI_STAGE_BYTES = 8 * 2048;        // per epilogue warp: 32 rows x 64 bytes of output, transposed before the store
-constexpr int EPI_VEC_BYTES = 2 * 3 * 256 * 4 + EPI_STAGE_BYTES;   // + [accumulator stage][bias | colsum | row bias][256] floats
+constexpr int EPI_VEC_BYTES = 2 * 3 * 256 * 4;   // [accumulator stage][bias | colsum | row bias][256 columns] floats
 
 __host__ __device__ constexpr int acc_stride(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
-__host__ __device__ constexpr int num_stages(int bn) { return bn >= 256 ? 4 : bn > 128 ? 5 : bn >= 128 ? 6 : 8; }
+__host__ __device__ constexpr int num_stages(int bn) { return bn >= 256 ? 4 : bn >= 128 ? 6 : 8; }
 
 struct TcArgs {
   int M, N_out, num_m_tiles, num_n_tiles, num_k_blocks;
@@ -294,13 +293,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // (Read with __ldg inside the chunk loop they were the top stall of the small-K GEMMs: every 16-column chunk waited a
   // full L2 round trip for 64 bytes -- profiles/r2_gemm_epilogue.md.)
   float* s_vec = reinterpret_cast<float*>(full_bar) + 64;       // 256 bytes after the barriers; [2][3][256] floats
-  // Output staging.  The accumulator arrives one ROW per thread (tcgen05.ld 32x32b), so a direct store makes every warp
-  // instruction touch 32 different 128-byte lines (32 x 32 bytes, row stride ldd): the LSU retires ~10 B/clk/SM of such
-  // stores, which capped every write-heavy GEMM of the 64x64 level at ~2.9 TB/s of effective traffic however fast the
-  // main loop ran (profiles/r2_gemm_epilogue.md).  Each epilogue warp therefore transposes 32 rows x 64 bytes (two
-  // 16-column chunks) through 2 KB of swizzled shared memory and stores them as 8 rows x 64 contiguous bytes per
-  // instruction (4x fewer lines per instruction, 16-byte lanes).
-  uint8_t* s_out = reinterpret_cast<uint8_t*>(s_vec + 2 * 768);
 
   const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
 
@@ -500,50 +492,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       bf16* drow = args.D + (int64_t)m * args.ldd;
       if (args.ex.direction != 0 && m_ok) drow = exchange_row_ptr<bf16>(args.ex, m);
-      // destination rows of the transposed store: in store step s this lane writes 16 bytes of row 8 s + lane / 4
-      uint64_t dst_row[4];
-      {
-        const uint64_t mine = m_ok ? reinterpret_cast<uint64_t>(drow) : 0ull;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          const int src = 8 * s + (lane >> 2);
-          const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)mine, src);
-          const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(mine >> 32), src);
-          dst_row[s] = ((uint64_t)hi << 32) | lo;
-        }
-      }
-      const uint32_t s_mine = smem_u32(s_out + (warp - 2) * 2048);
-      auto stage_chunk = [&](const float (&v)[16], int piece0) {      // this thread's row, 16-byte pieces piece0, piece0 + 1
-        uint32_t w[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-          w[e] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        const uint32_t sw = (lane >> 1) & 3;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_mine + lane * 64 + (((uint32_t)piece0 ^ sw) << 4)),
-                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_mine + lane * 64 + (((uint32_t)(piece0 + 1) ^ sw) << 4)),
-                     "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
-      };
-      auto flush_group = [&](int col0, int pieces) {                  // pieces = 2 (one chunk) or 4 (two chunks) per row
-        __syncwarp();
-        const int q = lane & 3;
-        if (q < pieces) {
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const int row = 8 * s + (lane >> 2);
-            if (dst_row[s]) {
-              uint4 val;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
-                           : "r"(s_mine + row * 64 + (((uint32_t)q ^ ((row >> 1) & 3)) << 4)));
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(dst_row[s]) + col0 + q * 8) = val;
-            }
-          }
-        }
-        __syncwarp();
-      };
       const float rs = (args.rowscale && m_ok ? args.rowscale[m] : 1.f) * args.alpha;
       const float* rb = nullptr;
       if (args.rowbias && m_ok && !rb_staged) {
@@ -647,10 +595,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 v[2 * e] += f.x; v[2 * e + 1] += f.y;
               }
             }
+            st_row32(drow + n_out0 + c, v, wide);
           }
-          // stage this chunk (rows past M stage garbage that no lane stores); flush every second chunk / after the last
-          stage_chunk(v, (i & 1) * 2);
-          if ((i & 1) || i + 1 == c_count) flush_group(n_out0 + (c_begin + (i & ~1)) * 16, (i & 1) ? 4 : 2);
           if (res_next) resv[i] = ld_row32(res_next + 16 * i, wide);
         }
       }
