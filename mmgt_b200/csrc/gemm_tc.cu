@@ -358,22 +358,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           cw = rem - ch * args.W;
         }
       }
-      for (int kb = 0; kb < args.num_k_blocks; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-        if (CONV) {
-          const int tap = kb / args.cin_blocks, cb = kb - tap * args.cin_blocks;
-          int x, y;
-          if (args.conv_mode == 0) { x = cw + tap % 3 - 1; y = ch + tap / 3 - 1; }
-          else if (args.conv_mode == 1) { x = 2 * cw + tap % 3 - 1; y = 2 * ch + tap / 3 - 1; }
-          else { x = cw + (tap & 1) - ((par & 1) ? 0 : 1); y = ch + (tap >> 1) - ((par & 2) ? 0 : 1); }
-          tma_load_4d(sa, &tmA, &full_bar[stage], cb * BK, x, y, cn);
-        } else {
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+      // One pass of this loop per k-block is the producer's whole job: it has to stay well under the MMA time of a k-block
+      // (320 clocks at BN = 160), so there is no division and no mode switch inside -- taps are an outer loop with the box
+      // origin fixed per tap, the k coordinate of B just counts up (it was ~90 instructions with a software division before:
+      // the conv at BN = 160 ran at the producer's pace, profiles/r2_mma_issue.md).
+      int kb_b = par * args.num_k_blocks * BK;                      // k coordinate of the B (weight) box
+      const int n0 = n_blk * BN;
+      if (CONV) {
+        const int taps = args.conv_mode == 2 ? 4 : 9, tw = args.conv_mode == 2 ? 2 : 3;
+        const int sc = args.conv_mode == 1 ? 2 : 1;
+        const int x0 = sc * cw - ((args.conv_mode == 2 && (par & 1)) ? 0 : 1);
+        const int y0 = sc * ch - ((args.conv_mode == 2 && (par & 2)) ? 0 : 1);
+        int tx = 0, ty = 0;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int x = x0 + tx, y = y0 + ty;
+          for (int cb = 0; cb < args.cin_blocks; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_4d(sa, &tmA, &full_bar[stage], cb * BK, x, y, cn);
+            tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb_b, n0);
+            kb_b += BK;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++tx == tw) { tx = 0; ++ty; }
         }
-        if (!BRES) tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], (par * args.num_k_blocks + kb) * BK, n_blk * BN);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      } else {
+        const int m0 = m_blk * BM;
+        for (int kb = 0; kb < args.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          if (!BRES) tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1 && elect_one_sync()) {
