@@ -67,7 +67,10 @@ MMGT_API const char* mmgt_last_error(void);
  * flag 9: head dim <= 64 attention on the kernel with three rotating S buffers and P aliased over S; default 0 = the
  *         two-buffer kernel, which measured 1.5 % faster per DDIM step (profiles/r2_ab_flags.md).  A/B switch.
  * flag 10: temporal attention with head dim <= 80 on the row-coalesced kernel (one CTA per (batch, pixel), whole q|k|v rows
- *         through double-buffered cp.async) (default 1); 0 = one warp per (batch, pixel, head).  A/B switch. */
+ *         through double-buffered cp.async) (default 1); 0 = one warp per (batch, pixel, head).  A/B switch.
+ * flag 11: tensor-core GEMM / conv launches whose epilogue needs only bias, a per-tile row bias, GEGLU or a residual take
+ *         a kernel instance with that epilogue compiled straight-line (default 1); 0 = always the general epilogue
+ *         with its run-time option branches.  A/B switch. */
 MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);
 
 /* Layout ------------------------------------------------------------------------------------- */

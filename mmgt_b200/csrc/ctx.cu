@@ -38,6 +38,7 @@ extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
   c->gn_split = 1;
   c->conv_implicit_all = 1;
   c->temporal_rows = 1;
+  c->lean_epilogue = 1;
   c->attn_v2 = 0;     // measured (profiles/r2_ab_flags.md): 475 vs 482 ms per step in favour of the two-buffer kernel
   *out = c;
   return 0;
@@ -68,6 +69,10 @@ extern "C" int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value) {
     return ctx->strict_tc;
   }
   if (flag == 5) return ctx->simt_launches;
+  if (flag == 11) {
+    if (value >= 0) ctx->lean_epilogue = value ? 1 : 0;
+    return ctx->lean_epilogue;
+  }
   if (flag == 10) {
     if (value >= 0) ctx->temporal_rows = value ? 1 : 0;
     return ctx->temporal_rows;

@@ -60,6 +60,7 @@ struct TcArgs {
   // BRES only: A ring depth (runtime: what is left of shared memory after the resident weight tile)
   int stages;
   int wide_io;   // D / residual rows are 32-byte aligned: 256-bit epilogue loads and stores
+  int epi;       // epilogue code variant picked by the host (see the EPI template parameter)
   // Row exchange (multi-GPU frame-shard <-> token-shard switch around the motion modules): when ex.direction != 0
   // the epilogue stores row m into the receive buffer of the shard that owns it -- local or a peer's, over NVLink --
   // so the all-to-all is part of the GEMM that produces the rows and overlaps its main loop tile by tile.
@@ -201,6 +202,35 @@ __device__ __forceinline__ void st_row32(bf16* p, const float (&v)[16], bool wid
   }
 }
 
+// Predicated forms for the straight-line epilogue: no branch around the instruction, so ptxas keeps the whole tile in one
+// basic block and overlaps neighbouring chunks.
+__device__ __forceinline__ void st_row32_if(bool pred, bf16* p, const float (&v)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %9, 0;\n\t"
+      "@q st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n\t"
+      "}" ::"l"(p),
+      "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"((int)pred)
+      : "memory");
+}
+__device__ __forceinline__ void ld_row32_if(bool pred, Row32& r, const bf16* p) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %9, 0;\n\t"
+      "@q ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+      "}"
+      : "+r"(r.w[0]), "+r"(r.w[1]), "+r"(r.w[2]), "+r"(r.w[3]), "+r"(r.w[4]), "+r"(r.w[5]), "+r"(r.w[6]), "+r"(r.w[7])
+      : "l"(p), "r"((int)pred));
+}
+
 __device__ __forceinline__ void lds16_f32(const float* src, float (&v)[16]) {    // shared memory, warp-uniform address (broadcast)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -265,7 +295,11 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // memory, every CTA keeps one n-block for its lifetime and only A tiles stream through the ring.  The
 // L2 -> SM fabric (~45 B/clk/SM), not the tensor pipe, bounds a 128 x BN tile that re-reads B per tile:
 // (128 + BN) * 128 B per k-block vs. 128 * 128 B with B resident.
-template <int BN, bool CONV, bool GEGLU, bool BRES>
+// EPI selects the epilogue code: 0 = every option behind (warp-uniform) run-time branches; 1 = "lean": bias (+ the
+// tile's staged row bias, pre-added in shared memory) [+ GEGLU], 256-bit stores; 2 = lean + residual.  The lean forms
+// are one straight-line block per tile: the general form's per-chunk option branches kept ptxas from interleaving
+// chunks and cost the epilogue warps 24 % "no instruction" + 13 % branch-resolve stalls (profiles/r2_gemm_epilogue.md).
+template <int BN, bool CONV, bool GEGLU, bool BRES, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs args) {
   constexpr int MAX_STAGES = 8;
@@ -443,6 +477,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // same chunk of tile `it + 1`, so every load has a whole tile period to land (for small K the epilogue, not the
     // main loop, is the critical path and nothing else would cover the HBM latency of these loads).
     Row32 resv[CH0];
+    if (EPI == 2) {
+#pragma unroll
+      for (int i = 0; i < CH0; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) resv[i].w[e] = 0u;
+    }
     int m_blk, n_blk;
     // output row of this thread in M tile mb (>= M: none).  Patch tiles (CONV, args.pw != 0) are not consecutive rows.
     auto row_of = [&](int mb) -> int {
@@ -488,10 +528,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool rb_staged = args.rowbias != nullptr && args.rb_tile_rows > 0;
       if (et < BN / 4) {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        reinterpret_cast<float4*>(sv)[et] = args.bias ? __ldg(reinterpret_cast<const float4*>(args.bias + n_blk * BN) + et) : z;
-        if (args.rowstats)
+        float4 b4 = args.bias ? __ldg(reinterpret_cast<const float4*>(args.bias + n_blk * BN) + et) : z;
+        if (EPI != 0 && !GEGLU && rb_staged) {      // lean: bias + row bias of the tile's group in one vector
+          int tile_row0 = m_blk * BM;
+          if (CONV && args.conv_mode == 2) tile_row0 = (m_blk >> 2) * BM;
+          int grp = tile_row0 / args.rb_tile_rows;
+          if (args.rowbias_mod > 0) grp %= args.rowbias_mod;
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(args.rowbias + (int64_t)grp * args.ld_rowbias + n_blk * BN) + et);
+          b4.x += r4.x; b4.y += r4.y; b4.z += r4.z; b4.w += r4.w;
+        }
+        reinterpret_cast<float4*>(sv)[et] = b4;
+        if (EPI == 0 && args.rowstats)
           reinterpret_cast<float4*>(sv + 256)[et] = __ldg(reinterpret_cast<const float4*>(args.colsum + n_blk * BN) + et);
-        if (rb_staged && et < OUT_COLS / 4) {
+        if (EPI == 0 && rb_staged && et < OUT_COLS / 4) {
           int tile_row0 = m_blk * BM;
           if (CONV && args.conv_mode == 2) tile_row0 = (m_blk >> 2) * BM;
           int grp = tile_row0 / args.rb_tile_rows;
@@ -529,6 +578,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // TMEM loads run one chunk ahead (ping-pong registers): the tcgen05.ld of chunk i + 1 is in flight while chunk i goes
       // through bias / activation / residual / store.  (Issued and waited for inside the chunk, the load latency was the
       // top stall of the epilogue warps of every small-K GEMM: profiles/r2_gemm_epilogue.md.)
+      if constexpr (EPI != 0) {
+        // ---- lean epilogue: straight-line, the only predicates are the row guard on the store and the prefetch
+        uint32_t rbuf[2][16], gbuf[GEGLU ? 2 : 1][16];
+        {
+          const int c0 = c_begin * 16;
+          tmem_ld_x16(taddr + (GEGLU ? 2 * c0 : c0), rbuf[0]);
+          if (GEGLU) tmem_ld_x16(taddr + 2 * c0 + 16, gbuf[0]);
+        }
+        bf16* dptr = drow + n_out0 + c_begin * 16;
+#pragma unroll
+        for (int i = 0; i < CH0; ++i) {
+          if (i < c_count) {
+            const int c = (c_begin + i) * 16;
+            uint32_t(&r)[16] = rbuf[i & 1];
+            uint32_t(&g)[16] = gbuf[GEGLU ? (i & 1) : 0];
+            float v[16];
+            tmem_ld_wait();
+            if (i + 1 < CH0 && i + 1 < c_count) {
+              const int cn = c + 16;
+              tmem_ld_x16(taddr + (GEGLU ? 2 * cn : cn), rbuf[(i + 1) & 1]);
+              if (GEGLU) tmem_ld_x16(taddr + 2 * cn + 16, gbuf[GEGLU ? ((i + 1) & 1) : 0]);
+            }
+            float bv[16];
+            lds16_f32(sv + (GEGLU ? 2 * c : c), bv);
+            if (GEGLU) {
+              float bg[16];
+              lds16_f32(sv + 2 * c + 16, bg);
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                v[e] = (__uint_as_float(r[e]) + bv[e]) * gelu_logistic(__uint_as_float(g[e]) + bg[e]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + bv[e];
+            }
+            if (EPI == 2) {        // rows >= M add whatever the slot holds; their store is predicated off
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&resv[i].w[0]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float2 f = __bfloat1622float2(h[e]);
+                v[2 * e] += f.x; v[2 * e + 1] += f.y;
+              }
+            }
+            st_row32_if(m_ok, dptr + 16 * i, v);
+            if (EPI == 2) ld_row32_if(res_next != nullptr, resv[i], res_next + 16 * i);
+          }
+        }
+      } else {
       uint32_t rbuf[2][16], gbuf[GEGLU ? 2 : 1][16];
       if (c_count > 0) {
         const int c0 = c_begin * 16;
@@ -619,6 +715,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (res_next) resv[i] = ld_row32(res_next + 16 * i, wide);
         }
       }
+      }   // EPI == 0
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -672,6 +769,14 @@ int make_map(mmgt_ctx* ctx, CUtensorMap* map, const void* base, int rank, const 
   return 0;
 }
 
+// The lean epilogue covers: bias, a row bias that is constant over each M tile (staged), GEGLU (logistic form), residual.
+int pick_epi(const mmgt_ctx* ctx, const TcArgs& a, bool geglu) {
+  if (!ctx->lean_epilogue || !a.wide_io || a.ex.direction != 0 || a.rowscale || a.alpha != 1.f || a.rowstats || a.act) return 0;
+  if (a.rowbias && (geglu || a.rb_tile_rows <= 0)) return 0;
+  if (geglu) return a.residual ? 0 : 1;
+  return a.residual ? 2 : 1;
+}
+
 int pick_bn(int N) {
   const int cand[5] = {256, 160, 128, 64, 32};
   for (int i = 0; i < 5; ++i)
@@ -693,16 +798,22 @@ int pick_bn_for(int N, int M, int num_sms) {
   return best;
 }
 
-template <int BN, bool CONV, bool GEGLU>
-int launch_tc(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
+template <int BN, bool CONV, bool GEGLU, int EPI>
+int launch_tc_epi(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
   constexpr int STAGES = num_stages(BN);
   constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + EPI_VEC_BYTES;
-  MMGT_CUDA_OK(mmgt_smem_optin(ctx, gemm_tc_kernel<BN, CONV, GEGLU, false>, smem));
+  MMGT_CUDA_OK(mmgt_smem_optin(ctx, gemm_tc_kernel<BN, CONV, GEGLU, false, EPI>, smem));
   const int tiles = a.num_m_tiles * a.num_n_tiles;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  MMGT_CUDA_OK(mmgt_launch(ctx, gemm_tc_kernel<BN, CONV, GEGLU, false>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, a));
+  MMGT_CUDA_OK(mmgt_launch(ctx, gemm_tc_kernel<BN, CONV, GEGLU, false, EPI>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, a));
   MMGT_LAUNCH_OK(ctx);
   return 0;
+}
+template <int BN, bool CONV, bool GEGLU>
+int launch_tc(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
+  if (a.epi == 1) return launch_tc_epi<BN, CONV, GEGLU, 1>(ctx, tmA, tmB, a, st);
+  if (!GEGLU && a.epi == 2) return launch_tc_epi<BN, CONV, false, 2>(ctx, tmA, tmB, a, st);
+  return launch_tc_epi<BN, CONV, GEGLU, 0>(ctx, tmA, tmB, a, st);
 }
 
 template <bool CONV>
@@ -753,13 +864,19 @@ bool plan_bres(int M, int N, int K, bool geglu, int num_sms, BresPlan* out) {
   return false;
 }
 
-template <int BN, bool GEGLU>
-int launch_bres(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, cudaStream_t st) {
-  MMGT_CUDA_OK(mmgt_smem_optin(ctx, gemm_tc_kernel<BN, false, GEGLU, true>, SMEM_OPTIN));
+template <int BN, bool GEGLU, int EPI>
+int launch_bres_epi(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, cudaStream_t st) {
+  MMGT_CUDA_OK(mmgt_smem_optin(ctx, gemm_tc_kernel<BN, false, GEGLU, true, EPI>, SMEM_OPTIN));
   const int smem = BRES_OVERHEAD + a.num_k_blocks * BN * BK * 2 + a.stages * A_STAGE_BYTES;
-  MMGT_CUDA_OK(mmgt_launch(ctx, gemm_tc_kernel<BN, false, GEGLU, true>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, a));
+  MMGT_CUDA_OK(mmgt_launch(ctx, gemm_tc_kernel<BN, false, GEGLU, true, EPI>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, a));
   MMGT_LAUNCH_OK(ctx);
   return 0;
+}
+template <int BN, bool GEGLU>
+int launch_bres(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, cudaStream_t st) {
+  if (a.epi == 1) return launch_bres_epi<BN, GEGLU, 1>(ctx, tmA, tmB, a, grid, st);
+  if (!GEGLU && a.epi == 2) return launch_bres_epi<BN, false, 2>(ctx, tmA, tmB, a, grid, st);
+  return launch_bres_epi<BN, GEGLU, 0>(ctx, tmA, tmB, a, grid, st);
 }
 
 int dispatch_bres(mmgt_ctx* ctx, const BresPlan& pl, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a,
@@ -848,6 +965,7 @@ int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
     for (int s = 0; s < p->exchange->k; ++s) w = w && aligned32(p->exchange->peer_base[s]);
     a.wide_io = w;
   }
+  a.epi = pick_epi(ctx, a, p->geglu_block != 0);
   if (bres) {
     a.stages = pl.stages;
     return dispatch_bres(ctx, pl, p->geglu_block != 0, tmA, tmB, a, st);
@@ -970,5 +1088,6 @@ int mmgt_conv3x3_tc(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, cudaStream_t st
     a.rb_tile_rows = (p->rowbias && !patch && tile_rows_per_group % BM == 0) ? tile_rows_per_group : 0;
   }
   a.H = Ht; a.W = Wt;
+  a.epi = pick_epi(ctx, a, false);
   return dispatch_tc<true>(ctx, bn, false, tmA, tmB, a, st);
 }

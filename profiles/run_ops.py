@@ -134,6 +134,7 @@ def main():
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--attn-v2", action="store_true", help="A/B: the three-S-buffer attention kernel for head dim <= 64")
+    ap.add_argument("--general-epilogue", action="store_true", help="A/B: GEMM / conv always through the general epilogue code")
     ap.add_argument("--gn-fused", action="store_true", help="A/B: the round-1 single-kernel GroupNorm (spin barrier)")
     ap.add_argument("--conv-im2col", action="store_true", help="A/B: stride-2 / upsampling convs through a staged im2col matrix")
     ap.add_argument("--geglu-exact", action="store_true", help="A/B: erf GELU in the GEGLU epilogue")
@@ -143,6 +144,7 @@ def main():
     eng = get_engine(dev, torch.bfloat16)
     eng.ctx.set_attention_v2(args.attn_v2)
     eng.ctx.set_groupnorm_split(not args.gn_fused)
+    eng.ctx.set_lean_epilogue(not args.general_epilogue)
     eng.ctx.set_conv_implicit_all(not args.conv_im2col)
     eng.ctx.set_geglu_exact(args.geglu_exact)
     ops = make_ops(eng, dev)

@@ -286,6 +286,86 @@ def test_conv3x3_fused_epilogue(dev, dtype, tc, case):
         eng.ctx.set_conv_implicit_all(True)
 
 
+LEAN_GEMMS = [(40003, 320, 320, False), (38021, 960, 320, False), (37999, 2560, 320, True), (257, 320, 320, False),
+              (1000, 960, 320, False), (513, 192, 64, False), (96, 1280, 1280, False), (130, 160, 72, False),
+              (3001, 320, 968, False), (6144, 1280, 1280, False), (300, 640, 64, True)]
+
+
+@pytest.mark.parametrize("M,N,K,geglu", LEAN_GEMMS)
+def test_gemm_specialised_epilogue_matches_general_epilogue(dev, M, N, K, geglu):
+    """flag 11: the straight-line epilogue instances (bias / per-tile row bias / GEGLU / residual) against the general
+    epilogue on the same launch: identical arithmetic except that bias + row bias are pre-added, so equal to ~1 bf16 ulp;
+    clipped last m-tile, column-slice destinations, in-place accumulate."""
+    from mmgt_b200.packing import geglu_interleave
+    eng = eng_for(dev, torch.bfloat16)
+    A = rnd(M, K, dev=dev, dtype=torch.bfloat16, seed=51)
+    W = rnd(N, K, dev=dev, dtype=torch.bfloat16, seed=52, scale=K ** -0.5)
+    bias = rnd(N, dev=dev, seed=53)
+    n_out = N // 2 if geglu else N
+    gb = 0
+    if geglu:
+        gb = eng.geglu_block(N)
+        W, bias = geglu_interleave(W, bias, gb)
+        W, bias = W.contiguous(), bias.contiguous()
+    res = None if geglu else rnd(M, n_out, dev=dev, dtype=torch.bfloat16, seed=54)
+    rpg = 256                      # a multiple of the 128-row tile: the row bias is staged per tile
+    rb = None if geglu else rnd((M + rpg - 1) // rpg, N, dev=dev, seed=55)
+    outs = {}
+    try:
+        for lean in (True, False):
+            eng.ctx.set_lean_epilogue(lean)
+            got = []
+            buf = torch.full((M + 3, n_out + 32), 7.0, device=dev, dtype=torch.bfloat16)
+            out = buf[:M, 16:16 + n_out]
+            eng.gemm(A, W, bias=bias, geglu_block=gb, out=out)                      # bias only
+            assert float(buf[:, :16].min()) == 7.0 and float(buf[:, 16 + n_out:].min()) == 7.0 and float(buf[M:].min()) == 7.0
+            got.append(out.clone())
+            if not geglu:
+                got.append(eng.gemm(A, W, bias=bias, residual=res))                  # + residual
+                got.append(eng.gemm(A, W, bias=bias, rowbias=rb, rows_per_group=rpg, residual=res))
+                got.append(eng.gemm(A, W))                                            # nothing at all
+                acc = res.clone()
+                eng.gemm(A, W, bias=bias, residual=acc, out=acc)                      # in place
+                got.append(acc)
+            outs[lean] = got
+    finally:
+        eng.ctx.set_lean_epilogue(True)
+    for a, b in zip(outs[True], outs[False]):
+        assert rel_l2(a.float(), b.float()) < 2e-3
+    assert torch.equal(outs[True][0], outs[False][0])       # bias only: the same operations in the same order
+    ref = A.float() @ W.float().t() + bias
+    if not geglu:
+        assert rel_l2(outs[True][1].float(), ref + res.float()) < 8e-3
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 320, 320, 1, 0), (3, 32, 32, 640, 320, 1, 0), (2, 64, 64, 320, 320, 2, 0),
+                                  (5, 8, 8, 1280, 1280, 1, 0), (3, 16, 16, 128, 64, 1, 0), (2, 32, 32, 640, 640, 1, 1)])
+def test_conv_specialised_epilogue_matches_general_epilogue(dev, case):
+    N, H, W, Cin, Cout, stride, up = case
+    eng = eng_for(dev, torch.bfloat16)
+    x = rnd(N, H, W, Cin, dev=dev, dtype=torch.bfloat16, seed=61)
+    w = rnd(Cout, 3, 3, Cin, dev=dev, dtype=torch.bfloat16, seed=62, scale=(9 * Cin) ** -0.5)
+    bias = rnd(Cout, dev=dev, seed=63)
+    rb = rnd(N, Cout, dev=dev, seed=65)
+    Ho, Wo = (2 * H, 2 * W) if up else (H // stride, W // stride)
+    res = rnd(N, Ho, Wo, Cout, dev=dev, dtype=torch.bfloat16, seed=64)
+    wsp = None
+    if up:
+        from mmgt_b200.packing import subpixel_pack
+        wsp = subpixel_pack(w.permute(0, 3, 1, 2).contiguous(), eng)
+    outs = {}
+    try:
+        for lean in (True, False):
+            eng.ctx.set_lean_epilogue(lean)
+            outs[lean] = [eng.conv3x3(x, w, bias=bias, stride=stride, upsample2x=bool(up), w_subpixel=wsp),
+                          eng.conv3x3(x, w, bias=bias, rowbias=rb, frames_per_group=1, residual=res, stride=stride,
+                                      upsample2x=bool(up), w_subpixel=wsp)]
+    finally:
+        eng.ctx.set_lean_epilogue(True)
+    assert torch.equal(outs[True][0], outs[False][0])
+    assert rel_l2(outs[True][1].float(), outs[False][1].float()) < 2e-3
+
+
 @pytest.mark.parametrize("dtype,tc", [(torch.float32, False), (torch.bfloat16, True)], ids=["f32", "bf16tc"])
 @pytest.mark.parametrize("act", [1, 2])
 def test_conv_and_gemm_activation_epilogue_and_rowbias_slices(dev, dtype, tc, act):
