@@ -313,7 +313,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int STAGES = BRES ? args.stages : num_stages(BN);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1 KB alignment by pointer arithmetic on the __shared__ array: an integer round trip makes every access through the
+  // derived pointers a GENERIC load / store (the epilogue's bias-vector reads were LD.E.128 in the global-memory queue,
+  // its top stall -- profiles/r2_gemm_epilogue.md)
+  uint8_t* smem_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_b = smem_base;                                                        // BRES: num_k_blocks weight tiles
   uint8_t* smem = smem_base + (BRES ? args.num_k_blocks * B_STAGE_BYTES : 0);         // ring
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
