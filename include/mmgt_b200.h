@@ -70,7 +70,10 @@ MMGT_API const char* mmgt_last_error(void);
  *         through double-buffered cp.async) (default 1); 0 = one warp per (batch, pixel, head).  A/B switch.
  * flag 11: tensor-core GEMM / conv launches whose epilogue needs only bias, a per-tile row bias, GEGLU or a residual take
  *         a kernel instance with that epilogue compiled straight-line (default 1); 0 = always the general epilogue
- *         with its run-time option branches.  A/B switch. */
+ *         with its run-time option branches.  A/B switch.
+ * flag 12: the specialised residual epilogues write their output tiles through TMA stores from swizzled shared-memory
+ *         boxes (default 1) where a tile is 128 consecutive output rows; 0 = one 32-byte store per lane and 16-column
+ *         chunk (32 different lines per warp instruction), as the non-residual epilogues always do.  A/B switch. */
 MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);
 
 /* Layout ------------------------------------------------------------------------------------- */

@@ -39,6 +39,7 @@ extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
   c->conv_implicit_all = 1;
   c->temporal_rows = 1;
   c->lean_epilogue = 1;
+  c->tma_store = 1;
   c->attn_v2 = 0;     // measured (profiles/r2_ab_flags.md): 475 vs 482 ms per step in favour of the two-buffer kernel
   *out = c;
   return 0;
@@ -69,6 +70,10 @@ extern "C" int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value) {
     return ctx->strict_tc;
   }
   if (flag == 5) return ctx->simt_launches;
+  if (flag == 12) {
+    if (value >= 0) ctx->tma_store = value ? 1 : 0;
+    return ctx->tma_store;
+  }
   if (flag == 11) {
     if (value >= 0) ctx->lean_epilogue = value ? 1 : 0;
     return ctx->lean_epilogue;

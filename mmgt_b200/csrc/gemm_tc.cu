@@ -24,9 +24,14 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 320;            // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int EPI_VEC_BYTES = 2 * 3 * 256 * 4;   // [accumulator stage][bias | colsum | row bias][256 columns] floats
+// Shared memory after the ring: barriers (256 B) + epilogue vectors, padded to a 1 KB boundary, then the staging boxes
+// of the TMA-store epilogue: per epilogue warp 32 rows x 64 B (two 16-column chunks) or x 32 B (one chunk).
+constexpr int EPI_FIXED_BYTES = 7168;
+static_assert(256 + EPI_VEC_BYTES <= EPI_FIXED_BYTES, "epilogue vectors overflow their slot");
+__host__ __device__ constexpr int epi_out_bytes(int tma_store) { return tma_store == 2 ? 16384 : tma_store == 1 ? 8192 : 0; }
 
 __host__ __device__ constexpr int acc_stride(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
-__host__ __device__ constexpr int num_stages(int bn) { return bn >= 256 ? 4 : bn >= 128 ? 6 : 8; }
+__host__ __device__ constexpr int num_stages(int bn) { return bn >= 256 ? 4 : bn >= 160 ? 5 : bn >= 128 ? 6 : 8; }
 
 struct TcArgs {
   int M, N_out, num_m_tiles, num_n_tiles, num_k_blocks;
@@ -61,6 +66,13 @@ struct TcArgs {
   int stages;
   int wide_io;   // D / residual rows are 32-byte aligned: 256-bit epilogue loads and stores
   int epi;       // epilogue code variant picked by the host (see the EPI template parameter)
+  // Lean epilogues only: output through TMA.  The row-per-lane 32-byte stores cost ~80-110 clk of LSU / L1 time per warp
+  // instruction (32 lanes = 32 different lines) and paced every GEMM of the path (profiles/r2_k_sweep_store_ablation.txt:
+  // 960x320 74.6 us with, 49.2 us without its stores).  Instead each warp writes its 32-row x 16-column chunks (bf16) into
+  // a swizzled shared-memory box and one lane hands the box to cp.async.bulk.tensor (tmD2: two chunks, 64-byte rows; tmD1:
+  // one chunk, the tail of an odd chunk count).  0: off.  1: one-chunk boxes only (shared memory is short).  2: both.
+  // Needs tiles of 128 consecutive output rows (plain GEMM, box-tiled conv); rows >= M / columns >= N are clipped by TMA.
+  int tma_store;
   // Row exchange (multi-GPU frame-shard <-> token-shard switch around the motion modules): when ex.direction != 0
   // the epilogue stores row m into the receive buffer of the shard that owns it -- local or a peer's, over NVLink --
   // so the all-to-all is part of the GEMM that produces the rows and overlaps its main loop tile by tile.
@@ -109,6 +121,18 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_src), "r"(c0),
+               "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -145,6 +169,13 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
+}
+// Scheduling fence on 16 registers: everything that consumes r[] is ordered after this point (and r[] stays live across
+// it), so a tcgen05.ld issued just before it into the OTHER register set really is in flight while r[] is processed --
+// without it ptxas sinks the next load below the arithmetic and reuses the same registers (no overlap at all).
+__device__ __forceinline__ void pin16(uint32_t (&r)[16]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+               "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -296,12 +327,14 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // L2 -> SM fabric (~45 B/clk/SM), not the tensor pipe, bounds a 128 x BN tile that re-reads B per tile:
 // (128 + BN) * 128 B per k-block vs. 128 * 128 B with B resident.
 // EPI selects the epilogue code: 0 = every option behind (warp-uniform) run-time branches; 1 = "lean": bias (+ the
-// tile's staged row bias, pre-added in shared memory) [+ GEGLU], 256-bit stores; 2 = lean + residual.  The lean forms
+// tile's staged row bias, pre-added in shared memory) [+ GEGLU], 256-bit stores; 2 = lean + residual; 3 / 4 = 1 / 2 with
+// the output tiles going through TMA stores (TcArgs::tma_store; only 4 is instantiated, see mmgt_gemm_tc).  The lean forms
 // are one straight-line block per tile: the general form's per-chunk option branches kept ptxas from interleaving
 // chunks and cost the epilogue warps 24 % "no instruction" + 13 % branch-resolve stalls (profiles/r2_gemm_epilogue.md).
 template <int BN, bool CONV, bool GEGLU, bool BRES, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs args) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD1, const TcArgs args) {
   constexpr int MAX_STAGES = 8;
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = BRES ? A_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;
@@ -330,6 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // (Read with __ldg inside the chunk loop they were the top stall of the small-K GEMMs: every 16-column chunk waited a
   // full L2 round trip for 64 bytes -- profiles/r2_gemm_epilogue.md.)
   float* s_vec = reinterpret_cast<float*>(full_bar) + 64;       // 256 bytes after the barriers; [2][3][256] floats
+  uint8_t* s_out = reinterpret_cast<uint8_t*>(full_bar) + EPI_FIXED_BYTES;   // 1 KB aligned: TMA-store boxes, one per warp
 
   const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
 
@@ -480,7 +514,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // same chunk of tile `it + 1`, so every load has a whole tile period to land (for small K the epilogue, not the
     // main loop, is the critical path and nothing else would cover the HBM latency of these loads).
     Row32 resv[CH0];
-    if (EPI == 2) {
+    constexpr bool RES = (EPI == 2 || EPI == 4);        // lean epilogue adds a residual
+    constexpr bool TMAST = (EPI == 4);                  // lean epilogue stores through TMA (two-chunk boxes + one-chunk tail)
+    if (RES) {
 #pragma unroll
       for (int i = 0; i < CH0; ++i)
 #pragma unroll
@@ -590,6 +626,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (GEGLU) tmem_ld_x16(taddr + 2 * c0 + 16, gbuf[0]);
         }
         bf16* dptr = drow + n_out0 + c_begin * 16;
+        const uint32_t my_out = smem_u32(s_out) + (warp - 2) * 2048;
 #pragma unroll
         for (int i = 0; i < CH0; ++i) {
           if (i < c_count) {
@@ -603,6 +640,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tmem_ld_x16(taddr + (GEGLU ? 2 * cn : cn), rbuf[(i + 1) & 1]);
               if (GEGLU) tmem_ld_x16(taddr + 2 * cn + 16, gbuf[GEGLU ? ((i + 1) & 1) : 0]);
             }
+            pin16(r);
+            if (GEGLU) pin16(g);
             float bv[16];
             lds16_f32(sv + (GEGLU ? 2 * c : c), bv);
             if (GEGLU) {
@@ -615,7 +654,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + bv[e];
             }
-            if (EPI == 2) {        // rows >= M add whatever the slot holds; their store is predicated off
+            if (RES) {        // rows >= M add whatever the slot holds; their store is predicated off
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&resv[i].w[0]);
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
@@ -623,8 +662,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 v[2 * e] += f.x; v[2 * e + 1] += f.y;
               }
             }
-            st_row32_if(m_ok, dptr + 16 * i, v);
-            if (EPI == 2) ld_row32_if(res_next != nullptr, resv[i], res_next + 16 * i);
+            if constexpr (TMAST) {
+              // chunk -> swizzled box -> TMA store.  Two-chunk boxes (64-byte rows, 64B swizzle: 16-byte unit ^= (row >> 1)
+              // & 3) while a partner chunk exists, else a one-chunk box (32-byte rows, 32B swizzle: unit ^= (row >> 2) & 1);
+              // either way the 8 lanes of a store phase hit 8 different bank groups.
+              const bool pair = (i & 1) || i + 1 < c_count;
+              if (!pair || !(i & 1)) {          // opening a box: the previous store has finished reading the buffer
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+              }
+              uint32_t w[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                w[e] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              uint32_t a0, a1;
+              if (pair) {
+                const uint32_t sw = (lane >> 1) & 3, u = (i & 1) * 2;
+                a0 = my_out + lane * 64 + ((u ^ sw) << 4);
+                a1 = my_out + lane * 64 + (((u + 1) ^ sw) << 4);
+              } else {
+                const uint32_t sw = (lane >> 2) & 1;
+                a0 = my_out + lane * 32 + (sw << 4);
+                a1 = my_out + lane * 32 + ((1 ^ sw) << 4);
+              }
+              sts_v4(a0, w[0], w[1], w[2], w[3]);
+              sts_v4(a1, w[4], w[5], w[6], w[7]);
+              if (!pair || (i & 1)) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0)
+                  tma_store_2d(pair ? &tmD2 : &tmD1, my_out, n_out0 + (pair ? c - 16 : c), m_blk * BM + lane_grp * 32);
+              }
+            } else {
+              st_row32_if(m_ok, dptr + 16 * i, v);
+            }
+            if (RES) ld_row32_if(res_next != nullptr, resv[i], res_next + 16 * i);
           }
         }
       } else {
@@ -723,6 +797,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (EPI >= 3 && lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
@@ -754,7 +829,7 @@ int resolve_encode(mmgt_ctx* ctx, EncodeTiledFn* fn) {
 }
 
 int make_map(mmgt_ctx* ctx, CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-             const uint32_t* box, const uint32_t* elem_strides = nullptr) {
+             const uint32_t* box, const uint32_t* elem_strides = nullptr, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn;
   int rc = resolve_encode(ctx, &fn);
   if (rc) return rc;
@@ -762,7 +837,7 @@ int make_map(mmgt_ctx* ctx, CUtensorMap* map, const void* base, int rank, const 
   if (elem_strides)
     for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     mmgt_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,
@@ -770,6 +845,17 @@ int make_map(mmgt_ctx* ctx, CUtensorMap* map, const void* base, int rank, const 
     return MMGT_E_INVALID;
   }
   return 0;
+}
+
+// Output maps of the TMA-store epilogue: (rows, cols) bf16 with row pitch ld; boxes of 32 rows x 32 / 16 columns.
+struct OutMaps { CUtensorMap d2, d1; };
+int make_out_maps(mmgt_ctx* ctx, OutMaps* o, const void* D, int64_t rows, int cols, int64_t ld) {
+  uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  uint64_t str[1] = {(uint64_t)ld * 2};
+  uint32_t box2[2] = {32, 32}, box1[2] = {16, 32};
+  int rc = make_map(ctx, &o->d2, D, 2, dims, str, box2, nullptr, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  return make_map(ctx, &o->d1, D, 2, dims, str, box1, nullptr, CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
 // The lean epilogue covers: bias, a row bias that is constant over each M tile (staged), GEGLU (logistic form), residual.
@@ -802,30 +888,33 @@ int pick_bn_for(int N, int M, int num_sms) {
 }
 
 template <int BN, bool CONV, bool GEGLU, int EPI>
-int launch_tc_epi(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
+int launch_tc_epi(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& tmD, const TcArgs& a, cudaStream_t st) {
   constexpr int STAGES = num_stages(BN);
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + EPI_VEC_BYTES;
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + EPI_FIXED_BYTES + epi_out_bytes(2);
+  static_assert(smem <= 232448, "streaming kernel exceeds the 227 KB opt-in");
   MMGT_CUDA_OK(mmgt_smem_optin(ctx, gemm_tc_kernel<BN, CONV, GEGLU, false, EPI>, smem));
   const int tiles = a.num_m_tiles * a.num_n_tiles;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  MMGT_CUDA_OK(mmgt_launch(ctx, gemm_tc_kernel<BN, CONV, GEGLU, false, EPI>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, a));
+  MMGT_CUDA_OK(mmgt_launch(ctx, gemm_tc_kernel<BN, CONV, GEGLU, false, EPI>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB,
+                           tmD.d2, tmD.d1, a));
   MMGT_LAUNCH_OK(ctx);
   return 0;
 }
 template <int BN, bool CONV, bool GEGLU>
-int launch_tc(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
-  if (a.epi == 1) return launch_tc_epi<BN, CONV, GEGLU, 1>(ctx, tmA, tmB, a, st);
-  if (!GEGLU && a.epi == 2) return launch_tc_epi<BN, CONV, false, 2>(ctx, tmA, tmB, a, st);
-  return launch_tc_epi<BN, CONV, GEGLU, 0>(ctx, tmA, tmB, a, st);
+int launch_tc(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& tmD, const TcArgs& a, cudaStream_t st) {
+  if (a.epi == 1) return launch_tc_epi<BN, CONV, GEGLU, 1>(ctx, tmA, tmB, tmD, a, st);
+  if (!GEGLU && a.epi == 2) return launch_tc_epi<BN, CONV, false, 2>(ctx, tmA, tmB, tmD, a, st);
+  if (!GEGLU && a.epi == 4) return launch_tc_epi<BN, CONV, false, 4>(ctx, tmA, tmB, tmD, a, st);
+  return launch_tc_epi<BN, CONV, GEGLU, 0>(ctx, tmA, tmB, tmD, a, st);
 }
 
 template <bool CONV>
-int dispatch_tc(mmgt_ctx* ctx, int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a,
-                cudaStream_t st) {
+int dispatch_tc(mmgt_ctx* ctx, int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& tmD,
+                const TcArgs& a, cudaStream_t st) {
 #define CASE(BN_)                                                              \
   case BN_:                                                                    \
-    if (!CONV && geglu) return launch_tc<BN_, false, true>(ctx, tmA, tmB, a, st); \
-    return launch_tc<BN_, CONV, false>(ctx, tmA, tmB, a, st);
+    if (!CONV && geglu) return launch_tc<BN_, false, true>(ctx, tmA, tmB, tmD, a, st); \
+    return launch_tc<BN_, CONV, false>(ctx, tmA, tmB, tmD, a, st);
   switch (bn) {
     CASE(256)
     CASE(160)
@@ -840,13 +929,13 @@ int dispatch_tc(mmgt_ctx* ctx, int bn, bool geglu, const CUtensorMap& tmA, const
 
 // ---- weight-stationary plan (BRES kernels)
 constexpr int SMEM_OPTIN = 232448;          // 227 KB per CTA on sm_100
-constexpr int BRES_OVERHEAD = 1024 + 256 + EPI_VEC_BYTES;   // alignment slack + barriers + epilogue vectors
+constexpr int BRES_OVERHEAD = 1024 + EPI_FIXED_BYTES;   // alignment slack + barriers + epilogue vectors
 
-struct BresPlan { int bn, stages, grid; };
+struct BresPlan { int bn, stages, grid, tma_store; };
 
 // Resident weights pay off when the (BN x K) tile fits next to >= 3 A stages, at least 90 % of the SMs get a CTA
 // (the grid must be a multiple of the n-tile count) and every CTA has a few m-tiles to amortise the weight load.
-bool plan_bres(int M, int N, int K, bool geglu, int num_sms, BresPlan* out) {
+bool plan_bres(int M, int N, int K, bool geglu, int num_sms, bool tma_store_ok, BresPlan* out) {
   const int kblocks = (K + BK - 1) / BK;
   const int m_tiles = (M + BM - 1) / BM;
   const int cand[4] = {256, 240, 160, 128};
@@ -855,44 +944,51 @@ bool plan_bres(int M, int N, int K, bool geglu, int num_sms, BresPlan* out) {
     if (N % bn || (geglu && bn % 32)) continue;
     const int n_tiles = N / bn;
     const int b_bytes = kblocks * bn * BK * 2;
-    int stages = (SMEM_OPTIN - BRES_OVERHEAD - b_bytes) / A_STAGE_BYTES;
+    // staging for the TMA-store epilogue: two-chunk boxes when >= 3 A stages still fit, else one-chunk boxes
+    int tma_store = (tma_store_ok && !geglu) ? 2 : 0;
+    if (tma_store == 2 && (SMEM_OPTIN - BRES_OVERHEAD - epi_out_bytes(2) - b_bytes) / A_STAGE_BYTES < 3) tma_store = 0;
+    int stages = (SMEM_OPTIN - BRES_OVERHEAD - epi_out_bytes(tma_store) - b_bytes) / A_STAGE_BYTES;
     if (stages > 8) stages = 8;
     if (stages < 3 || n_tiles > num_sms) continue;
     const int grid = (num_sms / n_tiles) * n_tiles;
     if (grid * 10 < num_sms * 9) continue;
     if (m_tiles < 4 * (grid / n_tiles)) continue;
-    out->bn = bn; out->stages = stages; out->grid = grid;
+    out->bn = bn; out->stages = stages; out->grid = grid; out->tma_store = tma_store;
     return true;
   }
   return false;
 }
 
 template <int BN, bool GEGLU, int EPI>
-int launch_bres_epi(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, cudaStream_t st) {
+int launch_bres_epi(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& tmD, const TcArgs& a, int grid,
+                    cudaStream_t st) {
   MMGT_CUDA_OK(mmgt_smem_optin(ctx, gemm_tc_kernel<BN, false, GEGLU, true, EPI>, SMEM_OPTIN));
-  const int smem = BRES_OVERHEAD + a.num_k_blocks * BN * BK * 2 + a.stages * A_STAGE_BYTES;
-  MMGT_CUDA_OK(mmgt_launch(ctx, gemm_tc_kernel<BN, false, GEGLU, true, EPI>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, a));
+  const int smem = BRES_OVERHEAD + epi_out_bytes(a.tma_store) + a.num_k_blocks * BN * BK * 2 + a.stages * A_STAGE_BYTES;
+  MMGT_CUDA_OK(mmgt_launch(ctx, gemm_tc_kernel<BN, false, GEGLU, true, EPI>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB,
+                           tmD.d2, tmD.d1, a));
   MMGT_LAUNCH_OK(ctx);
   return 0;
 }
 template <int BN, bool GEGLU>
-int launch_bres(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int grid, cudaStream_t st) {
-  if (a.epi == 1) return launch_bres_epi<BN, GEGLU, 1>(ctx, tmA, tmB, a, grid, st);
-  if (!GEGLU && a.epi == 2) return launch_bres_epi<BN, false, 2>(ctx, tmA, tmB, a, grid, st);
-  return launch_bres_epi<BN, GEGLU, 0>(ctx, tmA, tmB, a, grid, st);
+int launch_bres(mmgt_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& tmD, const TcArgs& a, int grid,
+                cudaStream_t st) {
+  if (a.epi == 1) return launch_bres_epi<BN, GEGLU, 1>(ctx, tmA, tmB, tmD, a, grid, st);
+  if (!GEGLU && a.epi == 2) return launch_bres_epi<BN, false, 2>(ctx, tmA, tmB, tmD, a, grid, st);
+  if (!GEGLU && a.epi == 4) return launch_bres_epi<BN, false, 4>(ctx, tmA, tmB, tmD, a, grid, st);
+  return launch_bres_epi<BN, GEGLU, 0>(ctx, tmA, tmB, tmD, a, grid, st);
 }
 
-int dispatch_bres(mmgt_ctx* ctx, const BresPlan& pl, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a,
-                  cudaStream_t st) {
+int dispatch_bres(mmgt_ctx* ctx, const BresPlan& pl, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                  const OutMaps& tmD, const TcArgs& a, cudaStream_t st) {
 #define CASE(BN_)                                                                    \
   case BN_:                                                                          \
-    if (geglu) return launch_bres<BN_, true>(ctx, tmA, tmB, a, pl.grid, st);         \
-    return launch_bres<BN_, false>(ctx, tmA, tmB, a, pl.grid, st);
+    if (geglu) return launch_bres<BN_, true>(ctx, tmA, tmB, tmD, a, pl.grid, st);    \
+    return launch_bres<BN_, false>(ctx, tmA, tmB, tmD, a, pl.grid, st);
   switch (pl.bn) {
     CASE(256)
     CASE(160)
     CASE(128)
-    case 240: return launch_bres<240, false>(ctx, tmA, tmB, a, pl.grid, st);
+    case 240: return launch_bres<240, false>(ctx, tmA, tmB, tmD, a, pl.grid, st);
   }
 #undef CASE
   mmgt_set_error("gemm_tc: no resident-weight kernel for BN=%d", pl.bn);
@@ -929,7 +1025,10 @@ bool mmgt_gemm_tc_supported(const mmgt_ctx* ctx, const mmgt_gemm_params* p) {
 
 int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
   BresPlan pl{};
-  const bool bres = ctx->use_bres && plan_bres(p->M, p->N, p->K, p->geglu_block != 0, ctx->num_sms, &pl);
+  // whether this launch will take a lean epilogue is only known once TcArgs is filled; the plan reserves staging for
+  // every launch that could (no exchange, TMA stores on) -- 16 KB of 227
+  const bool tma_store_ok = ctx->tma_store && ctx->lean_epilogue && !p->exchange;
+  const bool bres = ctx->use_bres && plan_bres(p->M, p->N, p->K, p->geglu_block != 0, ctx->num_sms, tma_store_ok, &pl);
   const int bn = bres ? pl.bn : pick_bn_for(p->N, p->M, ctx->num_sms);
   CUtensorMap tmA, tmB;
   {
@@ -969,11 +1068,25 @@ int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
     a.wide_io = w;
   }
   a.epi = pick_epi(ctx, a, p->geglu_block != 0);
-  if (bres) {
-    a.stages = pl.stages;
-    return dispatch_bres(ctx, pl, p->geglu_block != 0, tmA, tmB, a, st);
+  OutMaps tmD;
+  a.tma_store = (!tma_store_ok || a.epi == 0 || p->geglu_block) ? 0 : bres ? pl.tma_store : 2;
+  // Measured (profiles/r2_ab_flags.md): the TMA path wins where the epilogue also LOADS a residual row per lane (320x320 +
+  // residual 66.6 -> 54.3 us: half the LSU work), and loses slightly where it only stores (960x320 70.6 -> 74.7 us: the
+  // staging traffic competes with the MMA operand reads for shared-memory bandwidth).  One-chunk boxes alone serialise on
+  // the single buffer.  So: residual epilogues with room for two-chunk boxes only.
+  if (a.tma_store != 2 || a.epi != 2) a.tma_store = 0;
+  if (a.tma_store) a.epi = 4;
+  if (a.tma_store) {
+    int rc = make_out_maps(ctx, &tmD, p->D, p->M, a.N_out, p->ldd);
+    if (rc) return rc;
+  } else {
+    tmD.d2 = tmA; tmD.d1 = tmA;      // unused
   }
-  return dispatch_tc<false>(ctx, bn, p->geglu_block != 0, tmA, tmB, a, st);
+  if (bres) {
+    a.stages = pl.stages;      // planned with the staging boxes reserved; a general-epilogue launch just leaves them unused
+    return dispatch_bres(ctx, pl, p->geglu_block != 0, tmA, tmB, tmD, a, st);
+  }
+  return dispatch_tc<false>(ctx, bn, p->geglu_block != 0, tmA, tmB, tmD, a, st);
 }
 
 static bool conv_box(int W, int H, uint32_t* bw, uint32_t* bh, uint32_t* bn_frames) {
@@ -1092,5 +1205,14 @@ int mmgt_conv3x3_tc(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, cudaStream_t st
   }
   a.H = Ht; a.W = Wt;
   a.epi = pick_epi(ctx, a, false);
-  return dispatch_tc<true>(ctx, bn, false, tmA, tmB, a, st);
+  OutMaps tmD;
+  a.tma_store = (ctx->tma_store && a.epi == 2 && !patch && mode != 2) ? 2 : 0;     // tiles of 128 consecutive output rows
+  if (a.tma_store) a.epi = 4;
+  if (a.tma_store) {
+    int rc = make_out_maps(ctx, &tmD, p->y, a.M, p->Cout, p->Cout);
+    if (rc) return rc;
+  } else {
+    tmD.d2 = tmA; tmD.d1 = tmA;
+  }
+  return dispatch_tc<true>(ctx, bn, false, tmA, tmB, tmD, a, st);
 }

@@ -312,8 +312,9 @@ def test_gemm_specialised_epilogue_matches_general_epilogue(dev, M, N, K, geglu)
     rb = None if geglu else rnd((M + rpg - 1) // rpg, N, dev=dev, seed=55)
     outs = {}
     try:
-        for lean in (True, False):
-            eng.ctx.set_lean_epilogue(lean)
+        for lean in (True, "lane", False):
+            eng.ctx.set_lean_epilogue(bool(lean))
+            eng.ctx.set_tma_store(lean is True)      # flag 12: TMA stores from swizzled boxes vs one 32-byte store per lane
             got = []
             buf = torch.full((M + 3, n_out + 32), 7.0, device=dev, dtype=torch.bfloat16)
             out = buf[:M, 16:16 + n_out]
@@ -330,8 +331,11 @@ def test_gemm_specialised_epilogue_matches_general_epilogue(dev, M, N, K, geglu)
             outs[lean] = got
     finally:
         eng.ctx.set_lean_epilogue(True)
+        eng.ctx.set_tma_store(True)
     for a, b in zip(outs[True], outs[False]):
         assert rel_l2(a.float(), b.float()) < 2e-3
+    for a, b in zip(outs[True], outs["lane"]):               # the store path does not touch the arithmetic
+        assert torch.equal(a, b)
     assert torch.equal(outs[True][0], outs[False][0])       # bias only: the same operations in the same order
     ref = A.float() @ W.float().t() + bias
     if not geglu:
@@ -355,14 +359,17 @@ def test_conv_specialised_epilogue_matches_general_epilogue(dev, case):
         wsp = subpixel_pack(w.permute(0, 3, 1, 2).contiguous(), eng)
     outs = {}
     try:
-        for lean in (True, False):
-            eng.ctx.set_lean_epilogue(lean)
+        for lean in (True, "lane", False):
+            eng.ctx.set_lean_epilogue(bool(lean))
+            eng.ctx.set_tma_store(lean is True)
             outs[lean] = [eng.conv3x3(x, w, bias=bias, stride=stride, upsample2x=bool(up), w_subpixel=wsp),
                           eng.conv3x3(x, w, bias=bias, rowbias=rb, frames_per_group=1, residual=res, stride=stride,
                                       upsample2x=bool(up), w_subpixel=wsp)]
     finally:
         eng.ctx.set_lean_epilogue(True)
+        eng.ctx.set_tma_store(True)
     assert torch.equal(outs[True][0], outs[False][0])
+    assert torch.equal(outs[True][0], outs["lane"][0]) and torch.equal(outs[True][1], outs["lane"][1])
     assert rel_l2(outs[True][1].float(), outs[False][1].float()) < 2e-3
 
 
