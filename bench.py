@@ -332,7 +332,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             err = float((lat_dist.double() - solo.latents.double()).norm() / solo.latents.double().norm())
             parity = dict(latents_rel_l2_vs_n1=err, steps=2, tolerance=1e-2,
-                          what="2 DDIM steps: this run's schedule over all ranks vs all 20 forwards on rank 0 alone")
+                          what="2 DDIM steps: this run's schedule over all ranks vs all (window, CFG-branch) forwards on rank 0 alone")
             del solo
         barrier()
         flag = torch.tensor([0.0 if parity is None or parity["latents_rel_l2_vs_n1"] < 1e-2 else 1.0], device=dev)

@@ -16,5 +16,4 @@ run "" ""
 if [ "$N" = "8" ]; then
   run "_config4" "--config 4"
   run "_config5" "--config 5"
-  run "_whole_only" "--frame-shards 1"
 fi
