@@ -222,7 +222,7 @@ def run_ours(args):
     for name, setter in (("gn_split", eng.ctx.set_groupnorm_split), ("conv_implicit", eng.ctx.set_conv_implicit_all),
                          ("geglu_exact", eng.ctx.set_geglu_exact), ("attn_v2", eng.ctx.set_attention_v2),
                          ("temporal_rows", eng.ctx.set_temporal_rows), ("lean_epilogue", eng.ctx.set_lean_epilogue),
-                         ("tma_store", eng.ctx.set_tma_store)):
+                         ("tma_store", eng.ctx.set_tma_store), ("residual_mma", eng.ctx.set_residual_mma)):
         v = getattr(args, name)
         if v is not None:
             setter(bool(v))
@@ -308,7 +308,7 @@ def run_ours(args):
             print(json.dumps(dict(quick=True, ms_per_step=ms_per_step, value=value, n_gpus=world, config=args.config,
                                   flags=dict(gn_split=args.gn_split, conv_implicit=args.conv_implicit, geglu_exact=args.geglu_exact,
                                              fuse_ln=args.fuse_ln, attn_v2=args.attn_v2, deep_batch=args.deep_batch,
-                                             temporal_rows=args.temporal_rows, lean_epilogue=args.lean_epilogue, tma_store=args.tma_store), simt_launches=eng.ctx.simt_launches() - s0,
+                                             temporal_rows=args.temporal_rows, lean_epilogue=args.lean_epilogue, tma_store=args.tma_store, residual_mma=args.residual_mma), simt_launches=eng.ctx.simt_launches() - s0,
                                   gpu_launches=launches, clocks=clocks)), flush=True)
         pipe.close()
         if world > 1:
@@ -587,6 +587,7 @@ def main():
     ap.add_argument("--attn-v2", type=int, default=None, help="A/B: 1 / 0 three-S-buffer / round-1 attention kernel (head dim <= 64)")
     ap.add_argument("--deep-batch", type=int, default=None,
                     help="A/B: forwards whose 16x16 / 8x8 levels run as one batch (default: all of a rank's; 1 = unit by unit)")
+    ap.add_argument("--residual-mma", type=int, default=None, help="A/B: 1 / 0 residual through [R | I] k-blocks / per-lane loads")
     ap.add_argument("--tma-store", type=int, default=None, help="A/B: 1 / 0 lean epilogues store through TMA / per lane")
     ap.add_argument("--lean-epilogue", type=int, default=None, help="A/B: 1 / 0 specialised / general GEMM epilogue code")
     ap.add_argument("--temporal-rows", type=int, default=None, help="A/B: 1 / 0 row-coalesced / per-head temporal attention kernel")

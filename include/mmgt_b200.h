@@ -73,7 +73,11 @@ MMGT_API const char* mmgt_last_error(void);
  *         with its run-time option branches.  A/B switch.
  * flag 12: the specialised residual epilogues write their output tiles through TMA stores from swizzled shared-memory
  *         boxes (default 1) where a tile is 128 consecutive output rows; 0 = one 32-byte store per lane and 16-column
- *         chunk (32 different lines per warp instruction), as the non-residual epilogues always do.  A/B switch. */
+ *         chunk (32 different lines per warp instruction), as the non-residual epilogues always do.  A/B switch.
+ * flag 13: residual epilogues of the streaming tensor-core GEMM / conv kernels feed the residual through the tensor
+ *         cores -- extra k-blocks [residual tile | identity], exact in fp32 -- instead of loading a row per lane
+ *         (default 1); 0 = per-lane loads (+ flag 12).  The context owns the 256 x 256 bf16 identity (128 KB, allocated
+ *         in mmgt_ctx_create, freed in mmgt_ctx_destroy).  A/B switch. */
 MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);
 
 /* Layout ------------------------------------------------------------------------------------- */

@@ -181,6 +181,9 @@ class Context:
     def set_groupnorm_split(self, on: bool) -> bool:
         return bool(self.lib.mmgt_ctx_flag(self.handle, 7, 1 if on else 0))
 
+    def set_residual_mma(self, on: bool) -> bool:
+        return bool(self.lib.mmgt_ctx_flag(self.handle, 13, 1 if on else 0))
+
     def set_tma_store(self, on: bool) -> bool:
         return bool(self.lib.mmgt_ctx_flag(self.handle, 12, 1 if on else 0))
 

@@ -20,6 +20,8 @@ struct mmgt_ctx {
   void* encode_tiled;         // PFN of cuTensorMapEncodeTiled (resolved lazily through the runtime)
   int strict_tc;              // bf16 requests that no tensor-core kernel covers fail (MMGT_E_UNSUPPORTED) instead of
                               // running on the CUDA-core kernels
+  int residual_mma;           // residual epilogues of the streaming GEMM / conv kernels through [R | I] k-blocks (default 1; A/B)
+  void* identity;             // 256 x 256 bf16 identity on this device (B operand of those k-blocks), owned by the context
   int tma_store;              // lean epilogues write their tiles through TMA stores (default 1; 0 = per-lane stores, A/B)
   int lean_epilogue;          // tensor-core GEMM / conv: specialised straight-line epilogues where the options allow (default 1; A/B)
   int temporal_rows;          // temporal attention (head dim <= 80) on the row-coalesced cp.async kernel (default 1; A/B)

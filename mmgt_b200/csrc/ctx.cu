@@ -1,6 +1,7 @@
 // Context, error reporting, ABI version.
 #include <stdarg.h>
 #include <string.h>
+#include <vector>
 
 #include "common.cuh"
 
@@ -40,12 +41,25 @@ extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
   c->temporal_rows = 1;
   c->lean_epilogue = 1;
   c->tma_store = 1;
+  c->residual_mma = 1;
+  c->identity = nullptr;
+  {   // the one device allocation the context owns (128 KB): created here so that no launch ever allocates (graph capture)
+    std::vector<uint16_t> eye(256 * 256, 0);
+    for (int i = 0; i < 256; ++i) eye[i * 256 + i] = 0x3F80;      // bf16 1.0
+    if (cudaMalloc(&c->identity, eye.size() * 2) != cudaSuccess ||
+        cudaMemcpy(c->identity, eye.data(), eye.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError();
+      if (c->identity) cudaFree(c->identity);
+      c->identity = nullptr;                                       // residual_mma then stays unused
+    }
+  }
   c->attn_v2 = 0;     // measured (profiles/r2_ab_flags.md): 475 vs 482 ms per step in favour of the two-buffer kernel
   *out = c;
   return 0;
 }
 
 extern "C" int mmgt_ctx_destroy(mmgt_ctx* ctx) {
+  if (ctx && ctx->identity) cudaFree(ctx->identity);
   delete ctx;
   return 0;
 }
@@ -70,6 +84,10 @@ extern "C" int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value) {
     return ctx->strict_tc;
   }
   if (flag == 5) return ctx->simt_launches;
+  if (flag == 13) {
+    if (value >= 0) ctx->residual_mma = value ? 1 : 0;
+    return ctx->residual_mma;
+  }
   if (flag == 12) {
     if (value >= 0) ctx->tma_store = value ? 1 : 0;
     return ctx->tma_store;

@@ -73,6 +73,12 @@ struct TcArgs {
   // one chunk, the tail of an odd chunk count).  0: off.  1: one-chunk boxes only (shared memory is short).  2: both.
   // Needs tiles of 128 consecutive output rows (plain GEMM, box-tiled conv); rows >= M / columns >= N are clipped by TMA.
   int tma_store;
+  // Residual through the tensor cores (streaming kernels): after the K blocks of A x W^T the producer feeds res_kblocks
+  // more k-blocks whose A operand is the residual tile itself (rows x 64 columns, by TMA from the residual matrix: the
+  // kernel parameter tmD2 is that map) and whose B operand is a slice of an identity matrix (tmD1), so the accumulator
+  // ends up holding A W^T + R exactly (bf16 x 1.0 into fp32) and the epilogue neither loads nor adds anything per lane:
+  // the row-per-lane residual loads cost the LSU as much as the stores (profiles/r2_k_sweep_store_ablation.txt).
+  int res_kblocks;
   // Row exchange (multi-GPU frame-shard <-> token-shard switch around the motion modules): when ex.direction != 0
   // the epilogue stores row m into the receive buffer of the shard that owns it -- local or a peer's, over NVLink --
   // so the all-to-all is part of the GEMM that produces the rows and overlaps its main loop tile by tile.
@@ -465,6 +471,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (!BRES) {
+        for (int r = 0; r < args.res_kblocks; ++r) {        // [residual tile | identity] k-blocks (output rows m_blk * 128 ..)
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(sa, &tmD2, &full_bar[stage], n0 + r * BK, m_blk * BM);
+          tma_load_2d(sa + A_STAGE_BYTES, &tmD1, &full_bar[stage], r * BK, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
     }
   } else if (warp == 1 && elect_one_sync()) {
     // ===================== MMA issuer =====================
@@ -478,7 +494,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
-      for (int kb = 0; kb < args.num_k_blocks; ++kb) {
+      const int kb_total = args.num_k_blocks + (BRES ? 0 : args.res_kblocks);
+      for (int kb = 0; kb < kb_total; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -858,6 +875,22 @@ int make_out_maps(mmgt_ctx* ctx, OutMaps* o, const void* D, int64_t rows, int co
   return make_map(ctx, &o->d1, D, 2, dims, str, box1, nullptr, CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+// Residual-through-MMA operands: d2 = the residual matrix as an A operand (boxes of 128 rows x 64 columns), d1 = the
+// context's 256 x 256 identity as a B operand (boxes of bn rows x 64 columns).
+int make_residual_maps(mmgt_ctx* ctx, OutMaps* o, const void* R, int64_t rows, int cols, int64_t ld, int bn) {
+  {
+    uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+    uint64_t str[1] = {(uint64_t)ld * 2};
+    uint32_t box[2] = {BK, BM};
+    int rc = make_map(ctx, &o->d2, R, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  uint64_t dims[2] = {256, 256};
+  uint64_t str[1] = {256 * 2};
+  uint32_t box[2] = {BK, (uint32_t)bn};
+  return make_map(ctx, &o->d1, ctx->identity, 2, dims, str, box);
+}
+
 // The lean epilogue covers: bias, a row bias that is constant over each M tile (staged), GEGLU (logistic form), residual.
 int pick_epi(const mmgt_ctx* ctx, const TcArgs& a, bool geglu) {
   if (!ctx->lean_epilogue || !a.wide_io || a.ex.direction != 0 || a.rowscale || a.alpha != 1.f || a.rowstats || a.act) return 0;
@@ -938,8 +971,11 @@ struct BresPlan { int bn, stages, grid, tma_store; };
 bool plan_bres(int M, int N, int K, bool geglu, int num_sms, bool tma_store_ok, BresPlan* out) {
   const int kblocks = (K + BK - 1) / BK;
   const int m_tiles = (M + BM - 1) / BM;
-  const int cand[4] = {256, 240, 160, 128};
-  for (int i = 0; i < 4; ++i) {
+  // BN = 128 (the only width whose K = 640 weight tile fits) is not offered: at 128 x 128 the MMA reads as many operand
+  // bytes from shared memory per flop as the ring can deliver, three A stages are all that is left, and the streaming
+  // kernel at BN = 160 measured 19-33 % faster on every K = 640 shape (profiles/r2_bres_sweep.txt).
+  const int cand[3] = {256, 240, 160};
+  for (int i = 0; i < 3; ++i) {
     const int bn = cand[i];
     if (N % bn || (geglu && bn % 32)) continue;
     const int n_tiles = N / bn;
@@ -987,7 +1023,6 @@ int dispatch_bres(mmgt_ctx* ctx, const BresPlan& pl, bool geglu, const CUtensorM
   switch (pl.bn) {
     CASE(256)
     CASE(160)
-    CASE(128)
     case 240: return launch_bres<240, false>(ctx, tmA, tmB, tmD, a, pl.grid, st);
   }
 #undef CASE
@@ -1024,12 +1059,39 @@ bool mmgt_gemm_tc_supported(const mmgt_ctx* ctx, const mmgt_gemm_params* p) {
 }
 
 int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
+  const bool geglu = p->geglu_block != 0;
+  // ---- epilogue options first: they decide the kernel family
+  TcArgs a{};
+  a.M = p->M;
+  a.N_out = geglu ? p->N / 2 : p->N;
+  a.num_m_tiles = (p->M + BM - 1) / BM;
+  a.num_k_blocks = (p->K + BK - 1) / BK;
+  a.bias = p->bias; a.rowscale = p->rowscale; a.rowbias = p->rowbias;
+  a.residual = (const bf16*)p->residual; a.D = (bf16*)p->D;
+  a.ldd = p->ldd; a.ldr = p->ldr; a.rows_per_group = p->rows_per_group > 0 ? p->rows_per_group : 1; a.alpha = p->alpha;
+  a.ld_rowbias = p->ld_rowbias ? p->ld_rowbias : a.N_out; a.rowbias_mod = p->rowbias_mod;
+  a.rowstats = p->rowstats; a.colsum = p->colsum;
+  a.act = geglu ? (ctx->geglu_exact ? 3 : 0) : p->act;
+  a.rb_tile_rows = (p->rowbias && a.rows_per_group % BM == 0) ? a.rows_per_group : 0;
+  a.wide_io = aligned32(p->D) && p->ldd % 16 == 0 && (!p->residual || (aligned32(p->residual) && p->ldr % 16 == 0));
+  if (p->exchange) {
+    int rc = mmgt_row_exchange_check(p->exchange, p->M, "gemm");
+    if (rc) return rc;
+    a.ex = *p->exchange;
+    bool w = p->exchange->ld % 16 == 0 && (!p->residual || (aligned32(p->residual) && p->ldr % 16 == 0));
+    for (int s = 0; s < p->exchange->k; ++s) w = w && aligned32(p->exchange->peer_base[s]);
+    a.wide_io = w;
+  }
+  a.epi = pick_epi(ctx, a, geglu);
+  // residual epilogue: through the tensor cores on the streaming kernel where allowed, else TMA stores + per-lane loads
+  // Measured (profiles/r2_bres_sweep_residual.txt): the extra k-blocks pay only where the epilogue, not the main loop, paces
+  // the kernel -- 320x320 + residual 54.3 -> 47.2 us, but 640x640 97.2 -> 101.4, 640x2560 78.8 -> 82.9, 1280x1280 27.6 -> 30.7 us.
+  const bool res_mma = ctx->residual_mma && a.epi == 2 && ctx->identity != nullptr && p->K <= 512;
   BresPlan pl{};
-  // whether this launch will take a lean epilogue is only known once TcArgs is filled; the plan reserves staging for
-  // every launch that could (no exchange, TMA stores on) -- 16 KB of 227
-  const bool tma_store_ok = ctx->tma_store && ctx->lean_epilogue && !p->exchange;
-  const bool bres = ctx->use_bres && plan_bres(p->M, p->N, p->K, p->geglu_block != 0, ctx->num_sms, tma_store_ok, &pl);
+  const bool tma_store_ok = ctx->tma_store && a.epi == 2 && !res_mma;      // see the note at TcArgs::tma_store
+  const bool bres = ctx->use_bres && !res_mma && plan_bres(p->M, p->N, p->K, geglu, ctx->num_sms, tma_store_ok, &pl);
   const int bn = bres ? pl.bn : pick_bn_for(p->N, p->M, ctx->num_sms);
+  a.num_n_tiles = p->N / bn;
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->M};
@@ -1045,48 +1107,30 @@ int mmgt_gemm_tc(mmgt_ctx* ctx, const mmgt_gemm_params* p, cudaStream_t st) {
     int rc = make_map(ctx, &tmB, p->W, 2, dims, str, box);
     if (rc) return rc;
   }
-  TcArgs a{};
-  a.M = p->M;
-  a.N_out = p->geglu_block ? p->N / 2 : p->N;
-  a.num_m_tiles = (p->M + BM - 1) / BM;
-  a.num_n_tiles = p->N / bn;
-  a.num_k_blocks = (p->K + BK - 1) / BK;
-  a.bias = p->bias; a.rowscale = p->rowscale; a.rowbias = p->rowbias;
-  a.residual = (const bf16*)p->residual; a.D = (bf16*)p->D;
-  a.ldd = p->ldd; a.ldr = p->ldr; a.rows_per_group = p->rows_per_group > 0 ? p->rows_per_group : 1; a.alpha = p->alpha;
-  a.ld_rowbias = p->ld_rowbias ? p->ld_rowbias : a.N_out; a.rowbias_mod = p->rowbias_mod;
-  a.rowstats = p->rowstats; a.colsum = p->colsum;
-  a.act = p->geglu_block ? (ctx->geglu_exact ? 3 : 0) : p->act;
-  a.rb_tile_rows = (p->rowbias && a.rows_per_group % BM == 0) ? a.rows_per_group : 0;
-  a.wide_io = aligned32(p->D) && p->ldd % 16 == 0 && (!p->residual || (aligned32(p->residual) && p->ldr % 16 == 0));
-  if (p->exchange) {
-    int rc = mmgt_row_exchange_check(p->exchange, p->M, "gemm");
-    if (rc) return rc;
-    a.ex = *p->exchange;
-    bool w = p->exchange->ld % 16 == 0 && (!p->residual || (aligned32(p->residual) && p->ldr % 16 == 0));
-    for (int s = 0; s < p->exchange->k; ++s) w = w && aligned32(p->exchange->peer_base[s]);
-    a.wide_io = w;
-  }
-  a.epi = pick_epi(ctx, a, p->geglu_block != 0);
   OutMaps tmD;
-  a.tma_store = (!tma_store_ok || a.epi == 0 || p->geglu_block) ? 0 : bres ? pl.tma_store : 2;
-  // Measured (profiles/r2_ab_flags.md): the TMA path wins where the epilogue also LOADS a residual row per lane (320x320 +
-  // residual 66.6 -> 54.3 us: half the LSU work), and loses slightly where it only stores (960x320 70.6 -> 74.7 us: the
-  // staging traffic competes with the MMA operand reads for shared-memory bandwidth).  One-chunk boxes alone serialise on
-  // the single buffer.  So: residual epilogues with room for two-chunk boxes only.
-  if (a.tma_store != 2 || a.epi != 2) a.tma_store = 0;
-  if (a.tma_store) a.epi = 4;
-  if (a.tma_store) {
+  tmD.d2 = tmA; tmD.d1 = tmA;      // unused unless set below
+  // Measured (profiles/r2_ab_flags.md): the TMA-store path wins where the epilogue also LOADS a residual row per lane
+  // (320x320 + residual 66.6 -> 54.3 us: half the LSU work), and loses slightly where it only stores (960x320 70.6 ->
+  // 74.7 us: the staging traffic competes with the MMA operand reads for shared-memory bandwidth); one-chunk boxes alone
+  // serialise on the single buffer.  So: residual epilogues with room for two-chunk boxes only.
+  a.tma_store = !tma_store_ok ? 0 : bres ? pl.tma_store : 2;
+  if (a.tma_store != 2) a.tma_store = 0;
+  if (res_mma) {
+    int rc = make_residual_maps(ctx, &tmD, p->residual, p->M, a.N_out, p->ldr, bn);
+    if (rc) return rc;
+    a.res_kblocks = (bn + BK - 1) / BK;
+    a.residual = nullptr;
+    a.epi = 1;
+  } else if (a.tma_store) {
     int rc = make_out_maps(ctx, &tmD, p->D, p->M, a.N_out, p->ldd);
     if (rc) return rc;
-  } else {
-    tmD.d2 = tmA; tmD.d1 = tmA;      // unused
+    a.epi = 4;
   }
   if (bres) {
-    a.stages = pl.stages;      // planned with the staging boxes reserved; a general-epilogue launch just leaves them unused
-    return dispatch_bres(ctx, pl, p->geglu_block != 0, tmA, tmB, tmD, a, st);
+    a.stages = pl.stages;      // planned with the staging boxes reserved; a launch without them just leaves them unused
+    return dispatch_bres(ctx, pl, geglu, tmA, tmB, tmD, a, st);
   }
-  return dispatch_tc<false>(ctx, bn, p->geglu_block != 0, tmA, tmB, tmD, a, st);
+  return dispatch_tc<false>(ctx, bn, geglu, tmA, tmB, tmD, a, st);
 }
 
 static bool conv_box(int W, int H, uint32_t* bw, uint32_t* bh, uint32_t* bn_frames) {
@@ -1206,13 +1250,19 @@ int mmgt_conv3x3_tc(mmgt_ctx* ctx, const mmgt_conv3x3_params* p, cudaStream_t st
   a.H = Ht; a.W = Wt;
   a.epi = pick_epi(ctx, a, false);
   OutMaps tmD;
-  a.tma_store = (ctx->tma_store && a.epi == 2 && !patch && mode != 2) ? 2 : 0;     // tiles of 128 consecutive output rows
-  if (a.tma_store) a.epi = 4;
-  if (a.tma_store) {
+  tmD.d2 = tmA; tmD.d1 = tmA;
+  const bool row_tiles = !patch && mode != 2;                // tiles of 128 consecutive output rows
+  if (a.epi == 2 && row_tiles && ctx->residual_mma && ctx->identity && taps * p->Cin <= 512) {     // never: K >= 576 (see mmgt_gemm_tc)
+    int rc = make_residual_maps(ctx, &tmD, p->residual, a.M, p->Cout, p->Cout, bn);
+    if (rc) return rc;
+    a.res_kblocks = (bn + BK - 1) / BK;
+    a.residual = nullptr;
+    a.epi = 1;
+  } else if (a.epi == 2 && row_tiles && ctx->tma_store) {
     int rc = make_out_maps(ctx, &tmD, p->y, a.M, p->Cout, p->Cout);
     if (rc) return rc;
-  } else {
-    tmD.d2 = tmA; tmD.d1 = tmA;
+    a.tma_store = 2;
+    a.epi = 4;
   }
   return dispatch_tc<true>(ctx, bn, false, tmA, tmB, tmD, a, st);
 }

@@ -134,6 +134,7 @@ def main():
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--attn-v2", action="store_true", help="A/B: the three-S-buffer attention kernel for head dim <= 64")
+    ap.add_argument("--lane-residual", action="store_true", help="A/B: residual epilogues with per-lane loads instead of [R | I] k-blocks")
     ap.add_argument("--lane-stores", action="store_true", help="A/B: lean epilogues with per-lane stores instead of TMA stores")
     ap.add_argument("--general-epilogue", action="store_true", help="A/B: GEMM / conv always through the general epilogue code")
     ap.add_argument("--gn-fused", action="store_true", help="A/B: the round-1 single-kernel GroupNorm (spin barrier)")
@@ -147,6 +148,7 @@ def main():
     eng.ctx.set_groupnorm_split(not args.gn_fused)
     eng.ctx.set_lean_epilogue(not args.general_epilogue)
     eng.ctx.set_tma_store(not args.lane_stores)
+    eng.ctx.set_residual_mma(not args.lane_residual)
     eng.ctx.set_conv_implicit_all(not args.conv_im2col)
     eng.ctx.set_geglu_exact(args.geglu_exact)
     ops = make_ops(eng, dev)

@@ -146,7 +146,8 @@ def test_gemm_geglu(dev, dtype, tc, M, C):
 
 
 # Shapes that take the weight-stationary kernel (B tile resident in shared memory; needs many m-tiles per CTA):
-# BN = 160 (N=320), 240 (N=960), 128 (N=640, K=640), and the GEGLU BN = 256; M is ragged on purpose.
+# BN = 160 (N=320), 240 (N=960) and the GEGLU BN = 256; N = 640, K = 640 has no resident plan any more (both runs stream).
+# M is ragged on purpose.
 BRES_SHAPES = [(40003, 320, 320, False), (38021, 960, 320, False), (15001, 640, 640, False), (37999, 2560, 320, True),
                (40000, 320, 328, False)]
 
@@ -312,8 +313,9 @@ def test_gemm_specialised_epilogue_matches_general_epilogue(dev, M, N, K, geglu)
     rb = None if geglu else rnd((M + rpg - 1) // rpg, N, dev=dev, seed=55)
     outs = {}
     try:
-        for lean in (True, "lane", False):
+        for lean in ("mma", True, "lane", False):
             eng.ctx.set_lean_epilogue(bool(lean))
+            eng.ctx.set_residual_mma(lean == "mma")  # flag 13: residual through [R | I] k-blocks on the tensor cores
             eng.ctx.set_tma_store(lean is True)      # flag 12: TMA stores from swizzled boxes vs one 32-byte store per lane
             got = []
             buf = torch.full((M + 3, n_out + 32), 7.0, device=dev, dtype=torch.bfloat16)
@@ -332,7 +334,10 @@ def test_gemm_specialised_epilogue_matches_general_epilogue(dev, M, N, K, geglu)
     finally:
         eng.ctx.set_lean_epilogue(True)
         eng.ctx.set_tma_store(True)
+        eng.ctx.set_residual_mma(True)
     for a, b in zip(outs[True], outs[False]):
+        assert rel_l2(a.float(), b.float()) < 2e-3
+    for a, b in zip(outs["mma"], outs[False]):               # (acc + residual) + bias vs (acc + bias) + residual in fp32
         assert rel_l2(a.float(), b.float()) < 2e-3
     for a, b in zip(outs[True], outs["lane"]):               # the store path does not touch the arithmetic
         assert torch.equal(a, b)
@@ -359,8 +364,9 @@ def test_conv_specialised_epilogue_matches_general_epilogue(dev, case):
         wsp = subpixel_pack(w.permute(0, 3, 1, 2).contiguous(), eng)
     outs = {}
     try:
-        for lean in (True, "lane", False):
+        for lean in ("mma", True, "lane", False):
             eng.ctx.set_lean_epilogue(bool(lean))
+            eng.ctx.set_residual_mma(lean == "mma")
             eng.ctx.set_tma_store(lean is True)
             outs[lean] = [eng.conv3x3(x, w, bias=bias, stride=stride, upsample2x=bool(up), w_subpixel=wsp),
                           eng.conv3x3(x, w, bias=bias, rowbias=rb, frames_per_group=1, residual=res, stride=stride,
@@ -368,6 +374,9 @@ def test_conv_specialised_epilogue_matches_general_epilogue(dev, case):
     finally:
         eng.ctx.set_lean_epilogue(True)
         eng.ctx.set_tma_store(True)
+        eng.ctx.set_residual_mma(True)
+    assert torch.equal(outs["mma"][0], outs[False][0])
+    assert rel_l2(outs["mma"][1].float(), outs[False][1].float()) < 2e-3
     assert torch.equal(outs[True][0], outs[False][0])
     assert torch.equal(outs[True][0], outs["lane"][0]) and torch.equal(outs[True][1], outs["lane"][1])
     assert rel_l2(outs[True][1].float(), outs[False][1].float()) < 2e-3
