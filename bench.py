@@ -211,6 +211,9 @@ def run_ours(args):
     pipe.frame_shards, pipe.shard_remainder = shards, remainder
     pipe.use_cuda_graph = not args.no_graph
     pipe.deep_batch = args.deep_batch
+    pipe.deep_from = args.deep_from
+    pipe.level_batch = [int(v) for v in args.level_batch.split(",")] if args.level_batch else None
+    pipe.split_branches = None if args.split_branches is None else bool(args.split_branches)
     eng = unet._engine(dev)
     if args.no_tc:
         eng.ctx.set_tensor_cores(False)
@@ -307,7 +310,8 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps(dict(quick=True, ms_per_step=ms_per_step, value=value, n_gpus=world, config=args.config,
                                   flags=dict(gn_split=args.gn_split, conv_implicit=args.conv_implicit, geglu_exact=args.geglu_exact,
-                                             fuse_ln=args.fuse_ln, attn_v2=args.attn_v2, deep_batch=args.deep_batch,
+                                             fuse_ln=args.fuse_ln, attn_v2=args.attn_v2, deep_batch=args.deep_batch, deep_from=args.deep_from, level_batch=args.level_batch,
+                                             split_branches=args.split_branches,
                                              temporal_rows=args.temporal_rows, lean_epilogue=args.lean_epilogue, tma_store=args.tma_store, residual_mma=args.residual_mma), simt_launches=eng.ctx.simt_launches() - s0,
                                   gpu_launches=launches, clocks=clocks)), flush=True)
         pipe.close()
@@ -587,6 +591,12 @@ def main():
     ap.add_argument("--attn-v2", type=int, default=None, help="A/B: 1 / 0 three-S-buffer / round-1 attention kernel (head dim <= 64)")
     ap.add_argument("--deep-batch", type=int, default=None,
                     help="A/B: forwards whose 16x16 / 8x8 levels run as one batch (default: all of a rank's; 1 = unit by unit)")
+    ap.add_argument("--deep-from", type=int, default=None,
+                    help="A/B: first down block whose level runs batched over those forwards (default 2: 16x16 / 8x8; 1 adds 32x32)")
+    ap.add_argument("--level-batch", default=None,
+                    help="A/B: forwards per batch at each UNet level, e.g. 1,2,99,99 (overrides --deep-from)")
+    ap.add_argument("--split-branches", type=int, default=None,
+                    help="A/B: 1 = the CFG branches of a window are separate single-branch forwards (B = 1 units)")
     ap.add_argument("--residual-mma", type=int, default=None, help="A/B: 1 / 0 residual through [R | I] k-blocks / per-lane loads")
     ap.add_argument("--tma-store", type=int, default=None, help="A/B: 1 / 0 lean epilogues store through TMA / per lane")
     ap.add_argument("--lean-epilogue", type=int, default=None, help="A/B: 1 / 0 specialised / general GEMM epilogue code")

@@ -207,7 +207,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
 
   const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
-  const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  // Frames are taken in reverse launch order when a per-frame second segment exists: in the CFG batch the frames without it
+  // (half the key tiles) come first, and CTAs are dispatched in grid order, so the long CTAs would otherwise form the tail.
+  const int n = (args.has_seg2 && args.seg2_index) ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+  const int h = blockIdx.y, q0 = blockIdx.x * BQ;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -565,7 +568,10 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 2);
 
   const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
-  const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  // Frames are taken in reverse launch order when a per-frame second segment exists: in the CFG batch the frames without it
+  // (half the key tiles) come first, and CTAs are dispatched in grid order, so the long CTAs would otherwise form the tail.
+  const int n = (args.has_seg2 && args.seg2_index) ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+  const int h = blockIdx.y, q0 = blockIdx.x * BQ;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);

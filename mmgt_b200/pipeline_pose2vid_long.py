@@ -59,6 +59,15 @@ class DenoiseLoop:
         self._bank_ptrs = None
         # units whose 16x16 / 8x8 levels run as ONE batch (UNet3DConditionModel.forward_tokens_group); 1 = unit by unit
         self.deep_batch = 16
+        # first down block whose level runs batched over those units (2: the 16x16 / 8x8 levels; 1 adds the 32x32 level:
+        # 435.0 vs 440.5 ms per DDIM step, profiles/r2_ab_flags.md run 21 -- the level-1 GEMMs of ONE window are 768 tiles,
+        # 5.2 waves of 148 CTAs)
+        self.deep_from = 1
+        # units per batch at every level, e.g. [1, 2, 99, 99] (overrides deep_from; forward_tokens_group's level_batch)
+        self.level_batch = None
+        # deal the CFG branches of a whole window as two single-branch units (the 64x64 level of one branch is 31 MB per
+        # tensor -- it stays in the 126 MB L2 from the kernel that writes it to the kernel that reads it)
+        self.split_branches = False
 
     # ------------------------------------------------------------------ one-off preparation per video
     def prepare(self, latents, pose_fea, audio, full_mask, face_mask, lip_mask, encoder_hidden_states):
@@ -79,6 +88,9 @@ class DenoiseLoop:
         k = self.frame_shards
         shard = self.rank % k
         self.units, need_group = plan_rank(nw, nb, self.rank, self.world, k, self.shard_remainder)
+        if self.split_branches:                # whole (not frame-sharded) windows -> one unit per CFG branch, kept adjacent
+            self.units = [v for wi, br, sh in self.units
+                          for v in ([(wi, br, sh)] if sh or len(br) == 1 else [(wi, (b,), sh) for b in br])]
         if need_group:
             bad = [len(c) for c in self.windows if len(c) % k]
             if bad:
@@ -179,8 +191,9 @@ class DenoiseLoop:
     # ------------------------------------------------------------------ the hot loop
     def _forward_units(self, lat_tok):
         """This rank's (window, CFG-branch) forwards of one step.  Frame-sharded units run one by one (their motion modules
-        exchange rows with the peers); the others go through ``forward_tokens_group``: 64x64 / 32x32 levels unit by unit,
-        the 16x16 / 8x8 levels of ALL units as one batch (``deep_batch``)."""
+        exchange rows with the peers); the others go through ``forward_tokens_group``: the 64x64 level unit by unit, the
+        32x32 / 16x16 / 8x8 levels of ALL units as one batch (``deep_batch`` units, from down block ``deep_from`` on, or
+        ``level_batch`` units per level)."""
         eng, u = self.eng, self.unet
 
         def finish(e, out):
@@ -201,10 +214,11 @@ class DenoiseLoop:
         if not plain:
             return
         same_f = len({un["F"] for _, un in plain}) == 1
-        chunk = max(1, int(self.deep_batch)) if same_f else 1
+        chunk = max(1, int(self.deep_batch)) * (2 if self.split_branches else 1) if same_f else 1
         for i in range(0, len(plain), chunk):
             part = plain[i:i + chunk]
-            outs = u.forward_tokens_group(eng, [un for _, un in part], self.t_dev, self.motion_scale, time_proj=self._time_proj)
+            outs = u.forward_tokens_group(eng, [un for _, un in part], self.t_dev, self.motion_scale, time_proj=self._time_proj,
+                                          deep_from=int(self.deep_from), level_batch=self.level_batch)
             for (e, _), out in zip(part, outs):
                 finish(e, out)
 
@@ -351,6 +365,9 @@ class Pose2VideoPipeline:
         self.shard_remainder = False                                    # only the forwards left over by the whole deal
         self.use_cuda_graph = True
         self.deep_batch = None                                          # None = DenoiseLoop's default (all units of a rank)
+        self.deep_from = None                                           # None = DenoiseLoop's default (1)
+        self.level_batch = None                                         # units per batch at every level (overrides deep_from)
+        self.split_branches = None                                      # None = DenoiseLoop's default
         self.decode_chunk_size = 8                                      # frames per vae.decode call (the reference: 1)
         self.shard_decode = True                                        # multi-GPU: every rank decodes a slice of the frames
         self._loops = {}                                                # video shape -> captured DenoiseLoop
@@ -543,6 +560,12 @@ class Pose2VideoPipeline:
                                    self.process_group, self.frame_shards, shard_remainder=self.shard_remainder)
                 if self.deep_batch is not None:
                     loop.deep_batch = int(self.deep_batch)
+                if self.deep_from is not None:
+                    loop.deep_from = int(self.deep_from)
+                if self.level_batch is not None:
+                    loop.level_batch = [int(v) for v in self.level_batch]
+                if self.split_branches is not None:
+                    loop.split_branches = bool(self.split_branches)
                 loop.prepare(latents, pose_fea, audio, full, face, lip, ehs)
                 if self.use_cuda_graph and latents.is_cuda:
                     loop.capture_graph()

@@ -383,59 +383,106 @@ class UNet3DConditionModel(nn.Module):
         x = self.mid_block.run(eng, x, si)
         return self._run_up(eng, x, skips, si, 0, len(self.up_blocks), final=True)
 
-    def forward_tokens_group(self, eng: Engine, units, timestep, motion_scale, time_proj=None, deep_from: int = 2):
-        """Several independent forwards (context windows / CFG branches of one DDIM step) with the DEEP levels batched.
+    def forward_tokens_group(self, eng: Engine, units, timestep, motion_scale, time_proj=None, deep_from: int = 2,
+                             level_batch=None):
+        """Several independent forwards (context windows / CFG branches of one DDIM step) with the levels batched differently.
         ``units``: list of dicts(x, pose, ehs, audio, full, face, body, B, F, ref) -- the arguments of ``forward_tokens``.
-        The first ``deep_from`` down blocks (and the matching last up blocks: 64x64 and 32x32 latents at 512x512) run unit
-        by unit, so their tensors stay L2-sized; down blocks ``deep_from``.., the mid block and the first up blocks run ONCE on
-        the frames of all units concatenated (16x16 and 8x8: a 12-frame window gives those GEMMs M = 6144 / 1536 rows, 48 / 12
-        tiles for 148 SMs; ten windows fill the machine and amortise ~1200 launches).  Every layer is per sample / per
-        frame / per (sample, pixel), so the result is the same as ``forward_tokens`` unit by unit.  -> list of outputs."""
-        if len(units) == 1 or deep_from <= 0 or deep_from >= len(self.down_blocks):
+        ``level_batch[l]`` = how many consecutive units run down block l (and the matching up block) as ONE batch; the values
+        must not decrease with depth.  Default (``deep_from`` = 2): ``[1, 1, all, all]`` -- the 64x64 and 32x32 levels at
+        512x512 run unit by unit, so their tensors stay L2-sized, while the 16x16 / 8x8 levels, the mid block and the first up
+        blocks run ONCE on the frames of all units concatenated (a 12-frame window gives those GEMMs M = 6144 / 1536 rows,
+        48 / 12 tiles for 148 SMs; ten windows fill the machine and amortise ~1200 launches).  Consecutive levels with the
+        same batch form a stage; a stage runs its down blocks chunk by chunk, hands the concatenated result to the next
+        stage and runs its up blocks chunk by chunk on the rows that come back.  Every layer is per sample / per frame /
+        per (sample, pixel), so the result is the same as ``forward_tokens`` unit by unit.  -> list of outputs."""
+        nblk = len(self.down_blocks)
+        if level_batch is None:
+            level_batch = [1] * min(max(int(deep_from), 0), nblk) + [len(units)] * max(nblk - max(int(deep_from), 0), 0)
+        level_batch = [max(1, min(int(g), len(units))) for g in level_batch]
+        if len(level_batch) != nblk or any(a > b for a, b in zip(level_batch, level_batch[1:])):
+            raise ValueError(f"level_batch needs {nblk} non-decreasing entries, got {level_batch}")
+        if len(units) == 1 or level_batch[-1] == 1:
             return [self.forward_tokens(eng, u["x"], timestep, u["ehs"], u["audio"], u["pose"], u["full"], u["face"], u["body"],
                                         motion_scale, u["B"], u["F"], ref_index=u["ref"], time_proj=time_proj) for u in units]
         F = units[0]["F"]
         if any(u["F"] != F for u in units):
             raise ValueError("forward_tokens_group: all units must have the same number of frames per sample")
         reaches = self._motion_scale_reaches_audio()
-        n_up_deep = len(self.up_blocks) - deep_from
-        sis, tops, xs = [], [], []
-        for u in units:
-            si = self._step_inputs(eng, u["x"], timestep, u["ehs"], u["audio"], u["full"], u["face"], u["body"], motion_scale,
-                                   u["B"], u["F"], u["ref"], None, time_proj)
-            x, skips = self._run_down(eng, u["x"], u["pose"], si, reaches, 0, deep_from)
-            sis.append(si)
-            tops.append(skips)
-            xs.append(x)
-        # ---- deep levels: one batched pass over the frames of all units
-        Bt = sum(u["B"] for u in units)
+        stages = []                                    # (first down block, one past the last, units per batch)
+        for lvl, g in enumerate(level_batch):
+            if stages and stages[-1][2] == g:
+                stages[-1] = (stages[-1][0], lvl + 1, g)
+            else:
+                stages.append((lvl, lvl + 1, g))
+        sis = [self._step_inputs(eng, u["x"], timestep, u["ehs"], u["audio"], u["full"], u["face"], u["body"], motion_scale,
+                                 u["B"], u["F"], u["ref"], None, time_proj) for u in units]
+        nrows = [u["B"] * u["F"] for u in units]       # frames (= leading rows of every activation) per unit
         have_audio = sis[0].audio_rows is not None
-        masks = None
-        if have_audio:
-            masks = [None if lvl < deep_from else tuple(torch.cat([si.masks[lvl][r] for si in sis]) for r in range(3))
-                     for lvl in range(len(sis[0].masks))]
-        tp0 = sis[0].temb_silu
-        tproj = type(tp0)(tp0.all_proj[:1].expand(Bt, -1).contiguous(), tp0.offsets)       # same timestep for every sample
-        seg2 = None
-        if sis[0].seg2_index is not None:
-            seg2 = torch.cat([si.seg2_index for si in sis])
-            seg2._n_seg2 = sum(getattr(si.seg2_index, "_n_seg2", si.seg2_index.numel()) for si in sis)   # bench FLOP accounting
-        si_deep = StepInputs(frames=F, temb_silu=tproj, clip=torch.cat([si.clip for si in sis]), seg2_index=seg2,
-                             audio_rows=torch.cat([si.audio_rows for si in sis]) if have_audio else None, masks=masks,
-                             scale=sis[0].scale, shard=None)
-        X = torch.cat(xs)
-        x, deep_skips = self._run_down(eng, X, None, si_deep, reaches, deep_from, len(self.down_blocks), skips=[X])
-        x = self.mid_block.run(eng, x, si_deep)
-        y = self._run_up(eng, x, deep_skips, si_deep, 0, n_up_deep, final=False)
-        assert len(deep_skips) == 0
-        # ---- back to the units
-        outs, n0 = [], 0
-        for u, si, skips in zip(units, sis, tops):
-            n = u["B"] * u["F"]
-            skips.pop()                      # the last top skip is the deep input itself (consumed inside the batch)
-            outs.append(self._run_up(eng, y[n0:n0 + n], skips, si, n_up_deep, len(self.up_blocks), final=True))
-            n0 += n
-        return outs
+
+        def merged(ids, lo):
+            """StepInputs of the units ``ids`` run as one batch from down block ``lo`` on."""
+            if len(ids) == 1:
+                return sis[ids[0]]
+            part = [sis[i] for i in ids]
+            masks = None
+            if have_audio:
+                masks = [None if lvl < lo else tuple(torch.cat([si.masks[lvl][r] for si in part]) for r in range(3))
+                         for lvl in range(len(part[0].masks))]
+            tp0 = part[0].temb_silu
+            Bt = sum(units[i]["B"] for i in ids)
+            tproj = type(tp0)(tp0.all_proj[:1].expand(Bt, -1).contiguous(), tp0.offsets)   # same timestep for every sample
+            seg2 = None
+            if part[0].seg2_index is not None:
+                seg2 = torch.cat([si.seg2_index for si in part])
+                seg2._n_seg2 = sum(getattr(si.seg2_index, "_n_seg2", si.seg2_index.numel()) for si in part)   # bench FLOPs
+            return StepInputs(frames=F, temb_silu=tproj, clip=torch.cat([si.clip for si in part]), seg2_index=seg2,
+                              audio_rows=torch.cat([si.audio_rows for si in part]) if have_audio else None, masks=masks,
+                              scale=part[0].scale, shard=None)
+
+        def run_stage(s, ids, X):
+            """Down blocks of stage ``s`` and deeper, mid block, up blocks back to stage ``s`` for the units ``ids``;
+            ``X``: their concatenated input rows (None for the first stage: conv_in reads the units' own tensors)."""
+            lo, hi, g = stages[s]
+            last = s == len(stages) - 1
+            state, n0 = [], 0
+            for c0 in range(0, len(ids), g):
+                part = ids[c0:c0 + g]
+                n = sum(nrows[i] for i in part)
+                si = merged(part, lo)
+                if lo == 0:
+                    xp = units[part[0]]["x"] if len(part) == 1 else torch.cat([units[i]["x"] for i in part])
+                    pose = units[part[0]]["pose"] if len(part) == 1 else torch.cat([units[i]["pose"] for i in part])
+                    x, skips = self._run_down(eng, xp, pose, si, reaches, 0, hi)
+                else:
+                    xp = X[n0:n0 + n]
+                    x, skips = self._run_down(eng, xp, None, si, reaches, lo, hi, skips=[xp])
+                if last:
+                    x = self.mid_block.run(eng, x, si)
+                state.append((si, x, skips, n))
+                n0 += n
+            if not last:
+                Y = run_stage(s + 1, ids, state[0][1] if len(state) == 1 else torch.cat([st[1] for st in state]))
+            outs, n0 = [], 0
+            for si, x, skips, n in state:
+                if not last:
+                    skips.pop()                  # the last skip is the next stage's input itself (consumed inside its batch)
+                    x = Y[n0:n0 + n]
+                outs.append(self._run_up(eng, x, skips, si, nblk - hi, nblk - lo, final=(lo == 0)))
+                assert len(skips) == 0
+                n0 += n
+            return outs if lo == 0 else (outs[0] if len(outs) == 1 else torch.cat(outs))
+
+        outs = run_stage(0, list(range(len(units))), None)
+        if stages[0][2] == 1:
+            return outs
+        res = []                                        # first-stage chunks hold several units: back to one output per unit
+        it = iter(outs)
+        for c0 in range(0, len(units), stages[0][2]):
+            y, n0 = next(it), 0
+            for i in range(c0, min(c0 + stages[0][2], len(units))):
+                res.append(y[n0:n0 + nrows[i]])
+                n0 += nrows[i]
+        return res
 
     def _run_down(self, eng, x, pose, si, reaches, lo, hi, skips=None):
         if lo == 0:

@@ -57,7 +57,16 @@ def test_gemm_epilogue_row_exchange(dev, k, B, F, T, K, N, direction):
     src_R, _ = _relayout(R_full, direction, k, B, F, T)
     groups = FrameShardGroup.emulate(eng, k, B * (F // k) * T * N * 2)
     try:
+        # The exchange epilogue adds bias and residual per lane, (acc + bias) + r; the default small-K GEMM feeds the
+        # residual through [R | I] k-blocks on the tensor cores, (acc + r) + bias (ctx flag 13): same value up to the
+        # order of two float32 additions.  Bit-identity is asserted against the per-lane form, the default form is held
+        # to one bf16 rounding step of it.
+        default = [eng.gemm(src_A[s].contiguous(), W, bias=bias, residual=src_R[s].contiguous()) for s in range(k)]
+        eng.ctx.set_residual_mma(False)
         plain = [eng.gemm(src_A[s].contiguous(), W, bias=bias, residual=src_R[s].contiguous()) for s in range(k)]
+        for d, p_ in zip(default, plain):      # (the flag stays off below: the unfused leg is a plain GEMM + copy kernel)
+            err = (d.float() - p_.float()).abs()
+            assert bool((err <= 2.0 ** -7 * p_.float().abs() + 2e-6).all()), float(err.max())   # 2e-6: float32 rounding under cancellation
         # what each shard must receive = re-layout of the concatenated plain results
         if direction == 1:
             full = torch.stack([p.view(B, F // k, T, N) for p in plain], dim=1).reshape(B, F, T, N)   # (B, k, Fl, ..)
@@ -76,6 +85,7 @@ def test_gemm_epilogue_row_exchange(dev, k, B, F, T, K, N, direction):
             for s in range(k):
                 assert torch.equal(exs[s].recv, expect[s]), f"shard {s} fused={fused}"
     finally:
+        eng.ctx.set_residual_mma(True)
         eng.unfused_exchange = False
         groups[0].close()
 

@@ -94,6 +94,12 @@ def test_denoise_loop_and_pipeline_call_on_cpu(monkeypatch):
     assert rel_l2(loop.run(), refs[0]) < 2e-5
     loop.reload(*args(vids[1]))
     assert rel_l2(loop.run(), refs[1]) < 2e-5
+    # the CFG branches of every window as separate single-branch units, levels batched 1 / 2 / all / all units at a time
+    loop = DenoiseLoop(unet, DDIMSchedule.from_config(), n_steps, 3.5, motion_scale=vids[0]["motion_scale"])
+    loop.split_branches, loop.level_batch = True, [1, 2, 99, 99]
+    loop.prepare(*args(vids[0]))
+    assert [len(b) for _, b, _ in loop.units] == [1] * (2 * len(windows))
+    assert rel_l2(loop.run(), refs[0]) < 2e-5
 
     inp = vids[0]
     pipe = Pose2VideoPipeline(vae=None, image_encoder=None, reference_unet=None, denoising_unet=unet, pose_guider=None,
@@ -488,9 +494,11 @@ def test_decode_latents_chunked_and_frame_sharded_matches_the_sequential_referen
         assert np.abs(o - ref).max() < 1e-5
 
 
-def test_forward_tokens_group_matches_unit_by_unit_on_cpu():
+@pytest.mark.parametrize("deep_from", [1, 2, 3, [1, 2, 3, 3], [1, 1, 2, 3], [2, 2, 3, 3], [3, 3, 3, 3], [1, 2, 2, 2]])
+def test_forward_tokens_group_matches_unit_by_unit_on_cpu(deep_from):
     """Deep-level batching (UNet3DConditionModel.forward_tokens_group): three units -- two CFG windows and one single-branch
-    forward -- with the 16x16 / 8x8 levels run as one batch vs forward_tokens unit by unit (fake engine, float32)."""
+    forward -- with the levels from down block ``deep_from`` on (default 2: 16x16 / 8x8 at 512x512) run as one batch vs
+    forward_tokens unit by unit (fake engine, float32); a list = units per batch at each level (``level_batch``)."""
     spec, sd, unet = _tiny_unet()
     L, latent, frames = 12, 16, 4
     inp = make_inputs(spec, L, latent, seed=5)
@@ -512,7 +520,8 @@ def test_forward_tokens_group_matches_unit_by_unit_on_cpu():
                                             un["face"], un["body"], inp["motion_scale"], un["B"], frames, ref_index=un["ref"]))
     eng2 = FakeEngine()
     with torch.no_grad():
-        outs = unet.forward_tokens_group(eng2, units, torch.tensor(500), inp["motion_scale"])
+        kw = dict(level_batch=deep_from) if isinstance(deep_from, list) else dict(deep_from=deep_from)
+        outs = unet.forward_tokens_group(eng2, units, torch.tensor(500), inp["motion_scale"], **kw)
     for o, r in zip(outs, refs):
         assert o.shape == r.shape and rel_l2(o, r) < 2e-6
     # fewer operator calls: the deep levels ran once for all three units
