@@ -77,7 +77,10 @@ MMGT_API const char* mmgt_last_error(void);
  * flag 13: residual epilogues of the streaming tensor-core GEMM / conv kernels feed the residual through the tensor
  *         cores -- extra k-blocks [residual tile | identity], exact in fp32 -- instead of loading a row per lane
  *         (default 1); 0 = per-lane loads (+ flag 12).  The context owns the 256 x 256 bf16 identity (128 KB, allocated
- *         in mmgt_ctx_create, freed in mmgt_ctx_destroy).  A/B switch. */
+ *         in mmgt_ctx_create, freed in mmgt_ctx_destroy).  A/B switch.
+ * flag 14: head dim <= 64 attention on persistent CTAs (default 0 -- measured slower; 1 = when items > SMs): one CTA per SM walks the (frame, head, query tile)
+ *         items, the next item's loads and first Q K^T overlapping the merge-and-store tail of the current one; 0 = one
+ *         item per CTA; n >= 2 = always, on at most n CTAs (tests).  Same arithmetic, bit-identical results.  A/B switch. */
 MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);
 
 /* Layout ------------------------------------------------------------------------------------- */

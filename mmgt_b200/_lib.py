@@ -193,6 +193,10 @@ class Context:
     def set_temporal_rows(self, on: bool) -> bool:
         return bool(self.lib.mmgt_ctx_flag(self.handle, 10, 1 if on else 0))
 
+    def set_attention_persistent(self, on) -> int:
+        """False / 0: one item per CTA; True / 1: persistent CTAs when there are more items than SMs; n >= 2: always, n CTAs."""
+        return int(self.lib.mmgt_ctx_flag(self.handle, 14, int(on)))
+
     def set_attention_v2(self, on: bool) -> bool:
         return bool(self.lib.mmgt_ctx_flag(self.handle, 9, 1 if on else 0))
 

@@ -15,6 +15,8 @@
 // "uncond" half, mutual_self_attention.py:168-188) simply stop after the first segment.
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -838,6 +840,379 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------- head dim <= 64, persistent CTAs
+// Same contract and the same per-tile pipeline as attention_tc_kernel<1, 128>, but ONE CTA per SM that walks a list of
+// (frame, head, 128-query tile) items.  The ncu source-level profile of the one-item-per-CTA kernel at the config-2 level-0
+// shape (profiles/r2_ops_ncu.md, 6144 CTAs of 22-44 us on 148 SMs) shows ~5 % of all warp samples on the CTA-end
+// barrier / EXIT and another ~4 % on the wait for the first S of a CTA: with a single resident CTA per SM (512 TMEM
+// columns) nothing overlaps the barrier / TMEM set-up, the Q and first K loads and the merge-and-store tail of
+// consecutive CTAs.  Here the rings, barriers and TMEM live for the whole launch:
+//   * the producer runs ahead into the next item (Q is double buffered; the K / V rings simply continue), so the next
+//     item's first tiles are in shared memory before the current item's last PV retires;
+//   * the MMA warp issues QK(0), QK(1) of the next item as soon as the softmax groups have pulled the last S tiles of the
+//     current one, i.e. while group 0 still merges and stores;
+//   * group 1 starts the next item's tile 1 right after handing its (m, l) to group 0, so the MUFU pipe stays fed during
+//     the tail.
+// Ordering of the O accumulators across items needs no extra barrier: the first MMA that touches them again is PV(0) of
+// the next item (PV(1) is issued after it, the MMA warp issues in order), which waits for P(0) of that item, which
+// group 0 writes only after its merge has read O_0 and O_1 (tcgen05.wait::ld, then fence + mbarrier arrive).
+// Barrier phases run over launch-wide counters: K / V tiles (ring stages), tiles per softmax group (S / P hand-offs),
+// items (Q buffers, statistics buffers).  Items are dealt round-robin, the frames with a second segment first.
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
+                            const __grid_constant__ CUtensorMap tmV2, const AttnArgs args, const int q_tiles,
+                            const int num_items) {
+  static_assert(BN == 128, "2 S buffers + 2 O accumulators + 2 packed P buffers fill the 512 TMEM columns");
+  constexpr int DPAD = 64, KS = 4, VS = 3;
+  constexpr int Q_BYTES = BQ * DPAD * 2;
+  constexpr int KV_BYTES = BN * DPAD * 2;
+  constexpr int TM_S = 0, TM_O = 2 * BN, TM_P = TM_O + 2 * DPAD;
+  constexpr uint32_t IDESC_QK = idesc_bf16(BN, false);
+  const int qk_steps = (args.d + 15) >> 4;
+  const uint32_t IDESC_PV = idesc_bf16(qk_steps << 4, true);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                                                  // 2 buffers (item parity)
+  uint8_t* sK = sQ + 2 * Q_BYTES;
+  uint8_t* sV = sK + KS * KV_BYTES;
+  float* stats = reinterpret_cast<float*>(sV + VS * KV_BYTES);        // [item parity][128][2]: (m_ref, l) of group 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 2 * 2 * BQ);
+  uint64_t* q_full = bars;                     // 2
+  uint64_t* q_empty = q_full + 2;              // 2  (all QK of the item retired)
+  uint64_t* k_full = q_empty + 2;              // KS
+  uint64_t* k_empty = k_full + KS;
+  uint64_t* v_full = k_empty + KS;             // VS
+  uint64_t* v_empty = v_full + VS;
+  uint64_t* s_full = v_empty + VS;             // 2 (buffer == group == tile parity inside the item)
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 2;              // 2  ("PV of this group's tile retired": P buffer free, O_g stable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
+
+  const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) { mbar_init(&q_full[b], 1); mbar_init(&q_empty[b], 1); }
+    for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 4); mbar_init(&p_full[g], 4); mbar_init(&p_empty[g], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue();
+
+  // item -> (frame, head, first query row, second-segment row or -1, key tiles per segment); same for every role
+  const int per_frame = args.heads * q_tiles;
+  const bool reversed = args.has_seg2 && args.seg2_index;             // CFG batch: the frames without a second segment come first
+  struct Item { int n, h, q0, seg2, tiles1, tiles2; };
+  auto decode = [&](int w) {
+    Item it;
+    const int z = w / per_frame, r = w - z * per_frame;
+    it.n = reversed ? args.N - 1 - z : z;
+    it.h = r / q_tiles;
+    it.q0 = (r - it.h * q_tiles) * BQ;
+    it.seg2 = -1;
+    if (args.has_seg2) it.seg2 = args.seg2_index ? __ldg(args.seg2_index + it.n) : 0;
+    it.tiles1 = (args.Lk + BN - 1) / BN;
+    it.tiles2 = it.seg2 >= 0 ? (args.Lk2 + BN - 1) / BN : 0;
+    return it;
+  };
+
+  if (warp == 0 && elect_one_sync()) {
+    // ===================== TMA producer =====================
+    uint32_t kt0 = 0, vt0 = 0;                 // K / V tiles requested before this item
+    int itn = 0;
+    for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++itn) {
+      const Item im = decode(w);
+      const int num_tiles = im.tiles1 + im.tiles2;
+      const int qb = itn & 1;
+      mbar_wait(&q_empty[qb], ((itn >> 1) & 1) ^ 1);
+      mbar_expect_tx(&q_full[qb], Q_BYTES);
+      tma_load_3d(sQ + qb * Q_BYTES, &tmQ, &q_full[qb], 0, im.h, im.n * args.Lq + im.q0);
+      auto tile_row = [&](int j) {
+        const bool second = j >= im.tiles1;
+        return second ? im.seg2 * args.Lk2 + (j - im.tiles1) * BN : im.n * args.Lk + j * BN;
+      };
+      auto load_k = [&](int j) {
+        const uint32_t t = kt0 + j, st = t % KS;
+        mbar_wait(&k_empty[st], ((t / KS) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], KV_BYTES);
+        tma_load_3d(sK + st * KV_BYTES, j >= im.tiles1 ? &tmK2 : &tmK, &k_full[st], 0, im.h, tile_row(j));
+      };
+      auto load_v = [&](int j) {
+        const uint32_t t = vt0 + j, st = t % VS;
+        mbar_wait(&v_empty[st], ((t / VS) & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], KV_BYTES);
+        tma_load_3d(sV + st * KV_BYTES, j >= im.tiles1 ? &tmV2 : &tmV, &v_full[st], 0, im.h, tile_row(j));
+      };
+      // request order = consumption order of the MMA warp (QK runs two tiles ahead of PV), see attention_tc_kernel
+      for (int j = 0; j < KS && j < num_tiles; ++j) load_k(j);
+      for (int j = 0; j < VS && j < num_tiles; ++j) load_v(j);
+      for (int j = KS; j < KS + 2 && j < num_tiles; ++j) load_k(j);
+      for (int i = 0; i < num_tiles; ++i) {
+        if (i + VS < num_tiles) load_v(i + VS);
+        if (i + 2 + KS < num_tiles) load_k(i + 2 + KS);
+      }
+      kt0 += num_tiles;
+      vt0 += num_tiles;
+    }
+  } else if (warp == 1 && elect_one_sync()) {
+    // ===================== MMA issuer =====================
+    uint32_t kt0 = 0, vt0 = 0;
+    uint32_t gc_a = 0, gc_b = 0;               // tiles handed to softmax group 0 / 1 before this item
+    int itn = 0;
+    for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++itn) {
+      const Item im = decode(w);
+      const int num_tiles = im.tiles1 + im.tiles2;
+      const int qb = itn & 1;
+      const uint64_t dQ = desc_kmajor(smem_u32(sQ + qb * Q_BYTES));
+      auto issue_qk = [&](int j) {
+        const uint32_t t = kt0 + j, st = t % KS;
+        const int g = j & 1;
+        const uint32_t c = (g ? gc_b : gc_a) + (j >> 1);
+        mbar_wait(&k_full[st], (t / KS) & 1);
+        mbar_wait(&s_empty[g], (c & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + TM_S + g * BN;
+        const uint64_t dK = desc_kmajor(smem_u32(sK + st * KV_BYTES));
+#pragma unroll
+        for (int k = 0; k < DPAD / 16; ++k)
+          if (k < qk_steps) umma(tS, dQ + ((k * 32) >> 4), dK + ((k * 32) >> 4), IDESC_QK, k != 0);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[g]);
+        if (j == num_tiles - 1) umma_commit(&q_empty[qb]);      // every QK of the item has been issued: Q buffer free once they retire
+      };
+      auto issue_pv = [&](int j) {
+        const uint32_t t = vt0 + j, st = t % VS;
+        const int g = j & 1;
+        const uint32_t c = (g ? gc_b : gc_a) + (j >> 1);
+        mbar_wait(&v_full[st], (t / VS) & 1);
+        mbar_wait(&p_full[g], c & 1);
+        tc_fence_after();
+        const uint64_t dV = desc_mnmajor(smem_u32(sV + st * KV_BYTES), BN * 128);
+        const uint32_t tOg = tmem_base + TM_O + g * DPAD, tPg = tmem_base + TM_P + g * (BN / 2);
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k)
+          umma_ts(tOg, tPg + k * 8, dV + k * (2048 >> 4), IDESC_PV, ((j >> 1) | k) != 0);
+        umma_commit(&v_empty[st]);
+        umma_commit(&p_empty[g]);
+      };
+      mbar_wait(&q_full[qb], (itn >> 1) & 1);
+      issue_qk(0);
+      if (num_tiles > 1) issue_qk(1);
+      for (int j = 0; j < num_tiles; ++j) {
+        if (j + 2 < num_tiles) issue_qk(j + 2);
+        issue_pv(j);
+      }
+      kt0 += num_tiles;
+      vt0 += num_tiles;
+      gc_a += (num_tiles + 1) >> 1;
+      gc_b += num_tiles >> 1;
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax groups / merge / epilogue =====================
+    const int g = (warp - 2) >> 2;
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
+    const float c = args.scale_log2e;
+    // one live base register: O_g, P_g and S_g sit 64, 64 and 128 columns apart per group
+    static_assert(DPAD == 64 && BN == 128, "group strides below");
+    const uint32_t tG = tmem_base + lane_addr + g * 64;
+#define tO (tG + TM_O)
+#define tP (tG + TM_P)
+#define tS (tG + g * 64 + TM_S)
+    uint32_t cnt = 0;                          // tiles this group has taken since the launch began
+    int itn = 0;
+    for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++itn) {
+      int num_tiles;
+      const int tiles1 = (args.Lk + BN - 1) / BN;
+      {
+        const Item im = decode(w);           // only the tile count stays live across the tile loop; re-decoded for the store
+        num_tiles = im.tiles1 + im.tiles2;
+      }
+      float m_ref = -INFINITY, l_run = 0.f;
+      int it = 0;
+      for (int j = g; j < num_tiles; j += 2, ++it, ++cnt) {
+        const bool second = j >= tiles1;
+        const int seg_len = second ? args.Lk2 : args.Lk;
+        const int k0 = (second ? (j - tiles1) : j) * BN;
+        const int valid = min(BN, seg_len - k0);
+        mbar_wait(&s_full[g], cnt & 1);
+        tc_fence_after();
+        uint32_t sa[32], sb[32];
+        uint32_t pk[BN / 2];
+        float alpha_tile = 1.f;
+        float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+        auto chunk = [&](uint32_t (&sc)[32], const int ci) {
+          if (valid < BN) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (ci * 32 + i >= valid) sc[i] = 0xff800000u;   // -inf
+          }
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(sc[i + e]));
+          }
+          const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+          if ((mx - m_ref) * c > RESCALE_THRESHOLD) {
+            const float a = ex2_approx((m_ref - mx) * c);
+            m_ref = mx;
+            alpha_tile *= a;
+            l_run *= a;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) lsum[e] *= a;
+            const __nv_bfloat162 a2 = __float2bfloat162_rn(a);
+#pragma unroll
+            for (int i = 0; i < BN / 2; ++i) {
+              if (i < ci * 16) {
+                __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&pk[i]);
+                v = __hmul2(v, a2);
+                pk[i] = *reinterpret_cast<uint32_t*>(&v);
+              }
+            }
+          }
+          const float mc = m_ref * c;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sc[i]), c, -mc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sc[i + 1]), c, -mc));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(sc[i + 2]), c, -mc));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(sc[i + 3]), c, -mc));
+            pk[ci * 16 + i / 2] = pack_bf16(p0, p1);
+            pk[ci * 16 + i / 2 + 1] = pack_bf16(p2, p3);
+            lsum[0] += p0; lsum[1] += p1; lsum[2] += p2; lsum[3] += p3;
+          }
+        };
+        tmem_ld32(tS, sa);
+        tmem_ld_wait();
+        pin32(sa);
+#pragma unroll
+        for (int ci = 0; ci < BN / 32; ci += 2) {
+          tmem_ld32(tS + (ci + 1) * 32, sb);
+          chunk(sa, ci);
+          tmem_ld_wait();
+          pin32(sb);
+          if (ci + 2 < BN / 32) {
+            tmem_ld32(tS + (ci + 2) * 32, sa);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[g]);
+          }
+          chunk(sb, ci + 1);
+          if (ci + 2 < BN / 32) {
+            tmem_ld_wait();
+            pin32(sa);
+          }
+        }
+        l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+
+        if (cnt > 0) {
+          // this group's previous PV (of this item, or the last one of the previous item) retired: P buffer reusable
+          mbar_wait(&p_empty[g], (cnt - 1) & 1);
+          tc_fence_after();
+          if (it > 0 && __any_sync(0xffffffffu, alpha_tile != 1.f)) {
+#pragma unroll
+            for (int cc = 0; cc < DPAD / 32; ++cc) {
+              uint32_t o[32];
+              tmem_ld32(tO + cc * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha_tile);
+              tmem_st32(tO + cc * 32, o);
+            }
+            tmem_st_wait();
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < BN / 64; ++i) tmem_st32(tP + i * 32, pk + i * 32);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+      }
+
+      // ---- merge the two groups and store O / l (only the first d columns are real)
+      if (it > 0) {
+        mbar_wait(&p_empty[g], (cnt - 1) & 1);
+        tc_fence_after();
+      }
+      float* st_item = stats + (itn & 1) * 2 * BQ;
+      if (g == 1) {
+        st_item[2 * row] = m_ref;
+        st_item[2 * row + 1] = l_run;
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      tc_fence_after();
+      if (g == 0) {
+        const Item im = decode(w);
+        const float m1 = st_item[2 * row], l1 = st_item[2 * row + 1];
+        const bool has1 = num_tiles > 1;
+        const float m = has1 ? fmaxf(m_ref, m1) : m_ref;
+        const float a0 = ex2_approx((m_ref - m) * c);
+        const float a1 = has1 ? ex2_approx((m1 - m) * c) : 0.f;
+        const float inv = 1.f / (l_run * a0 + (has1 ? l1 * a1 : 0.f));
+        const float w0 = a0 * inv, w1 = a1 * inv;
+        const int q = im.q0 + row;
+        bf16* orow = args.out + ((int64_t)im.n * args.Lq + q) * args.ldo + im.h * args.d;
+        const uint32_t tO0 = tmem_base + TM_O + lane_addr, tO1 = tO0 + DPAD;
+#pragma unroll
+        for (int cc = 0; cc < DPAD / 32; ++cc) {
+          if (cc * 32 < args.d) {
+            uint32_t o[32], o1[32];
+            tmem_ld32(tO0 + cc * 32, o);
+            if (has1) tmem_ld32(tO1 + cc * 32, o1);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(o[i]) * w0 + (has1 ? __uint_as_float(o1[i]) * w1 : 0.f);
+            if (q < args.Lq) {
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg) {
+                const int col = cc * 32 + gg * 8;
+                if (col < args.d) {
+                  uint4 val;
+                  val.x = pack_bf16(f[gg * 8 + 0], f[gg * 8 + 1]);
+                  val.y = pack_bf16(f[gg * 8 + 2], f[gg * 8 + 3]);
+                  val.z = pack_bf16(f[gg * 8 + 4], f[gg * 8 + 5]);
+                  val.w = pack_bf16(f[gg * 8 + 6], f[gg * 8 + 7]);
+                  *reinterpret_cast<uint4*>(orow + col) = val;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+#undef tO
+#undef tP
+#undef tS
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -879,6 +1254,18 @@ int launch_attn(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaS
   dim3 grid((a.Lq + BQ - 1) / BQ, a.heads, a.N);
   MMGT_CUDA_OK(mmgt_launch(ctx, attention_tc_kernel<DCH, BN>, grid, dim3(NUM_THREADS), smem, st, maps[0], maps[1], maps[2], maps[3],
                            maps[4], a));
+  MMGT_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int launch_attn_persist(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaStream_t st) {
+  constexpr int smem = 2 * BQ * 64 * 2 + (4 + 3) * 128 * 64 * 2 + 2 * BQ * 8 + 1024 + 256;
+  MMGT_CUDA_OK(mmgt_smem_optin(ctx, attention_tc_persist_kernel<128>, smem));
+  const int q_tiles = (a.Lq + BQ - 1) / BQ;
+  const int64_t items = (int64_t)q_tiles * a.heads * a.N;
+  const int grid = (int)std::min<int64_t>(items, ctx->attn_persist >= 2 ? ctx->attn_persist : ctx->num_sms);
+  MMGT_CUDA_OK(mmgt_launch(ctx, attention_tc_persist_kernel<128>, dim3(grid), dim3(NUM_THREADS), smem, st, maps[0], maps[1], maps[2],
+                           maps[3], maps[4], a, q_tiles, (int)items));
   MMGT_LAUNCH_OK(ctx);
   return 0;
 }
@@ -925,7 +1312,13 @@ int mmgt_attention_tc(mmgt_ctx* ctx, const mmgt_attention_params* p, cudaStream_
   a.seg2_index = p->seg2_index; a.has_seg2 = p->k2 != nullptr;
   a.out = (bf16*)p->out; a.ldo = p->ldo;
   a.scale_log2e = p->scale * 1.4426950408889634f;
-  if (dch == 1) return ctx->attn_v2 ? launch_attn64(ctx, maps, a, st) : launch_attn<1, 128>(ctx, maps, a, st);
+  if (dch == 1) {
+    if (ctx->attn_v2) return launch_attn64(ctx, maps, a, st);
+    const int64_t items = (int64_t)((p->Lq + BQ - 1) / BQ) * p->heads * p->N;
+    if (items < (1ll << 31) && (ctx->attn_persist >= 2 || (ctx->attn_persist == 1 && items > ctx->num_sms)))
+      return launch_attn_persist(ctx, maps, a, st);
+    return launch_attn<1, 128>(ctx, maps, a, st);
+  }
   if (dch == 2) return launch_attn<2, 128>(ctx, maps, a, st);
   return launch_attn<3, 64>(ctx, maps, a, st);
 }

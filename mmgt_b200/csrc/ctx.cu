@@ -53,6 +53,7 @@ extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
       c->identity = nullptr;                                       // residual_mma then stays unused
     }
   }
+  c->attn_persist = 0;  // measured (profiles/r2_attention_v2.md): 2134 vs 1815 us per level-0 launch, 452 vs 442 ms per step in favour of one item per CTA
   c->attn_v2 = 0;     // measured (profiles/r2_ab_flags.md): 475 vs 482 ms per step in favour of the two-buffer kernel
   *out = c;
   return 0;
@@ -84,6 +85,10 @@ extern "C" int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value) {
     return ctx->strict_tc;
   }
   if (flag == 5) return ctx->simt_launches;
+  if (flag == 14) {
+    if (value >= 0) ctx->attn_persist = (int)value;      // 0 off, 1 auto, n >= 2: always, on at most n CTAs (tests)
+    return ctx->attn_persist;
+  }
   if (flag == 13) {
     if (value >= 0) ctx->residual_mma = value ? 1 : 0;
     return ctx->residual_mma;

@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""Key metrics per kernel from an `ncu --set full` report:  python profiles/summarize_ncu.py <rep> <out.md> [names...]"""
+"""Key metrics per kernel from an `ncu --set full` report:  python profiles/summarize_ncu.py <rep | raw.csv.gz> <out.md> [names...]
+
+<raw.csv.gz> = `ncu -i <rep> --page raw --csv | gzip` made on the GPU box (reports above ~60 MB do not travel back).
+A name may end in `*2` / `*3`: the operator launches that many kernels (two-kernel GroupNorm), all labelled with it."""
 import csv
 import io
 import re
@@ -32,8 +35,15 @@ def to_bytes(v, unit):
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    labels = sys.argv[3:]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    labels = []
+    for name in sys.argv[3:]:
+        base, _, rep_n = name.partition("*")
+        labels += [base] * (int(rep_n) if rep_n else 1)
+    if rep.endswith(".gz"):
+        import gzip
+        raw = gzip.open(rep, "rt").read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}

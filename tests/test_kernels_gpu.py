@@ -562,6 +562,15 @@ def test_attention_two_segments(dev, dtype, tc, N, Lq, Lk, Lk2, heads, d):
                 alt = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
                 eng.ctx.set_attention_v2(False)
                 assert rel_l2(out.float(), alt.float()) < 4e-3
+                # persistent CTAs (flag 14) walking many items each -- 3 and 7 CTAs for all (frame, head, query tile) items,
+                # frames with one and with two key segments mixed -- vs one item per CTA: same arithmetic, same bits
+                eng.ctx.set_attention_persistent(0)
+                one = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
+                for ctas in (3, 7):
+                    eng.ctx.set_attention_persistent(ctas)
+                    per = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
+                    assert torch.equal(per, one), ctas
+                eng.ctx.set_attention_persistent(0)
             refs = []
             for n in range(N):
                 kk, vv = k[n:n + 1], v[n:n + 1]
@@ -573,10 +582,17 @@ def test_attention_two_segments(dev, dtype, tc, N, Lq, Lk, Lk2, heads, d):
         else:
             out = eng.attention(q, k, v, heads)
             ref = _attn_ref(q, k, v, heads)
+            if tc and d <= 64:
+                eng.ctx.set_attention_persistent(0)
+                one = eng.attention(q, k, v, heads)
+                eng.ctx.set_attention_persistent(5)
+                assert torch.equal(eng.attention(q, k, v, heads), one)
+                eng.ctx.set_attention_persistent(0)
         assert rel_l2(out.float(), ref) < (2e-5 if dtype == torch.float32 else 8e-3)
     finally:
         eng.ctx.set_tensor_cores(True)
         eng.ctx.set_attention_v2(False)
+        eng.ctx.set_attention_persistent(0)
 
 
 def test_attention_running_max_jumps_late(dev):
@@ -596,13 +612,15 @@ def test_attention_running_max_jumps_late(dev):
     q, k, v, k2, v2 = (t.to(device=dev, dtype=torch.bfloat16) for t in (q, k, v, k2, v2))
     ref = _attn_ref(q, torch.cat([k, k2.expand(N, -1, -1)], 1), torch.cat([v, v2.expand(N, -1, -1)], 1), heads)
     try:
-        for v2_kernel in (True, False):
+        for v2_kernel, persist in ((True, 0), (False, 0), (False, 2)):
             eng.ctx.set_attention_v2(v2_kernel)
+            eng.ctx.set_attention_persistent(persist)
             out = eng.attention(q, k, v, heads, k2=k2, v2=v2)
             assert torch.isfinite(out).all()
-            assert rel_l2(out.float(), ref) < 1e-2, v2_kernel
+            assert rel_l2(out.float(), ref) < 1e-2, (v2_kernel, persist)
     finally:
         eng.ctx.set_attention_v2(False)
+        eng.ctx.set_attention_persistent(0)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
