@@ -197,6 +197,16 @@ class Context:
         """False / 0: one item per CTA; True / 1: persistent CTAs when there are more items than SMs; n >= 2: always, n CTAs."""
         return int(self.lib.mmgt_ctx_flag(self.handle, 14, int(on)))
 
+    def set_attention_q256(self, on) -> int:
+        """Head dim <= 64: 256 queries per CTA, one query tile and one MMA-issuing warp per softmax group (flag 15).
+        0 off; 1 on; 2-5 = A/B variants (2: early S hand-back, 3 / 4: + 1 / 2 of 4 score pairs through the FMA-pipe exp2,
+        5: FMA-pipe exp2 for 1 of 4 pairs without the early hand-back)."""
+        return int(self.lib.mmgt_ctx_flag(self.handle, 15, int(on)))
+
+    def set_attention_packed(self, on: bool) -> bool:
+        """Attention softmax loops on packed fp32 pairs (FFMA2 / FADD2), bit-identical to the scalar form (flag 16)."""
+        return bool(self.lib.mmgt_ctx_flag(self.handle, 16, 1 if on else 0))
+
     def set_attention_v2(self, on: bool) -> bool:
         return bool(self.lib.mmgt_ctx_flag(self.handle, 9, 1 if on else 0))
 

@@ -159,12 +159,101 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// Packed fp32 pairs (FFMA2 / FADD2 on sm_100): the softmax inner loop issues one instruction per two scores for the
+// scale-and-subtract and for the row sum.  Same IEEE operations as the scalar forms, so results do not change.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// p[0..3] = 2^(s[i..i+3] * c - mc), packed as two bf16 pairs into pk[0..1], added lane-wise to the four partial sums
+template <bool PACKED>
+__device__ __forceinline__ void exp4_pack_sum(const uint32_t* sc, float c, float mc, uint32_t* pk, float (&lsum)[4]) {
+  float p0, p1, p2, p3;
+  if constexpr (PACKED) {
+    const uint64_t c2 = pack_f32x2(c, c), nm2 = pack_f32x2(-mc, -mc);
+    float x0, x1, x2, x3;
+    unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sc[0]), __uint_as_float(sc[1])), c2, nm2), x0, x1);
+    unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sc[2]), __uint_as_float(sc[3])), c2, nm2), x2, x3);
+    p0 = ex2_approx(x0); p1 = ex2_approx(x1); p2 = ex2_approx(x2); p3 = ex2_approx(x3);
+    unpack_f32x2(add_f32x2(pack_f32x2(lsum[0], lsum[1]), pack_f32x2(p0, p1)), lsum[0], lsum[1]);
+    unpack_f32x2(add_f32x2(pack_f32x2(lsum[2], lsum[3]), pack_f32x2(p2, p3)), lsum[2], lsum[3]);
+  } else {
+    p0 = ex2_approx(fmaf(__uint_as_float(sc[0]), c, -mc));
+    p1 = ex2_approx(fmaf(__uint_as_float(sc[1]), c, -mc));
+    p2 = ex2_approx(fmaf(__uint_as_float(sc[2]), c, -mc));
+    p3 = ex2_approx(fmaf(__uint_as_float(sc[3]), c, -mc));
+    lsum[0] += p0; lsum[1] += p1; lsum[2] += p2; lsum[3] += p3;
+  }
+  pk[0] = pack_bf16(p0, p1);
+  pk[1] = pack_bf16(p2, p3);
+}
+
+// 2^x for a pair of scores on the FMA pipe instead of MUFU (x <= 8; anything below -126 comes out as 2^-126): round x to
+// the nearest integer n with the 1.5 * 2^23 trick, 2^(x - n) by a degree-3 minimax polynomial on [-0.5, 0.5] (relative error
+// 7.5e-5, 50 times below the bf16 rounding P goes through), n added into the exponent field.  Seven packed instructions,
+// two FMNMX and two LEA per pair against two MUFU.EX2: MUFU is the pipe that bounds head-dim-40 attention (16 results per
+// clock and SM), the FMA pipe has slots to spare.
+__device__ __forceinline__ void exp2_pair_fma(uint64_t x01, float& p0, float& p1) {
+  float x0, x1;
+  unpack_f32x2(x01, x0, x1);
+  const uint64_t xc = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t xr = add_f32x2(xc, pack_f32x2(12582912.f, 12582912.f));
+  const uint64_t nn = add_f32x2(xr, pack_f32x2(-12582912.f, -12582912.f));
+  const uint64_t f = fma_f32x2(nn, pack_f32x2(-1.f, -1.f), xc);
+  uint64_t p = fma_f32x2(pack_f32x2(0.05517149344086647f, 0.05517149344086647f), f, pack_f32x2(0.24261093139648438f, 0.24261093139648438f));
+  p = fma_f32x2(p, f, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+  p = fma_f32x2(p, f, pack_f32x2(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, r0, r1;
+  unpack_f32x2(p, q0, q1);
+  unpack_f32x2(xr, r0, r1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
+}
+// Eight scores: p = 2^(s * c - mc) as four bf16 pairs in pk[0..3], added lane-wise to the partial sums.  POLY of the four
+// pairs (0, 1 or 2) take the FMA-pipe exponential, the rest MUFU.EX2.
+template <int POLY>
+__device__ __forceinline__ void exp8_pack_sum(const uint32_t* sc, float c, float mc, uint32_t* pk, float (&lsum)[4]) {
+  const uint64_t c2 = pack_f32x2(c, c), nm2 = pack_f32x2(-mc, -mc);
+  uint64_t l01 = pack_f32x2(lsum[0], lsum[1]), l23 = pack_f32x2(lsum[2], lsum[3]);
+#pragma unroll
+  for (int pr = 0; pr < 4; ++pr) {
+    const uint64_t x = fma_f32x2(pack_f32x2(__uint_as_float(sc[2 * pr]), __uint_as_float(sc[2 * pr + 1])), c2, nm2);
+    float p0, p1;
+    if ((POLY >= 1 && pr == 3) || (POLY >= 2 && pr == 1)) {
+      exp2_pair_fma(x, p0, p1);
+    } else {
+      float x0, x1;
+      unpack_f32x2(x, x0, x1);
+      p0 = ex2_approx(x0);
+      p1 = ex2_approx(x1);
+    }
+    pk[pr] = pack_bf16(p0, p1);
+    if (pr & 1) l23 = add_f32x2(l23, pack_f32x2(p0, p1));
+    else l01 = add_f32x2(l01, pack_f32x2(p0, p1));
+  }
+  unpack_f32x2(l01, lsum[0], lsum[1]);
+  unpack_f32x2(l23, lsum[2], lsum[3]);
+}
 
 // DCH = ceil(d / 64) head-dim chunks (d_pad = 64 * DCH); BN = keys per tile.
 // Two independent softmax groups (warps 2-5 and 6-9) take alternate key tiles, each with its own running
 // maximum / row sum and its own O accumulator in TMEM (split-KV inside the CTA); the halves are merged in the
 // epilogue.  With two warps per scheduler the TMEM-load, MUFU and shared-store phases of the groups overlap.
-template <int DCH, int BN>
+template <int DCH, int BN, bool PACKED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
@@ -398,15 +487,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         const float mc = m_ref * c;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sc[i]), c, -mc));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sc[i + 1]), c, -mc));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(sc[i + 2]), c, -mc));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(sc[i + 3]), c, -mc));
-          pk[ci * 16 + i / 2] = pack_bf16(p0, p1);
-          pk[ci * 16 + i / 2 + 1] = pack_bf16(p2, p3);
-          lsum[0] += p0; lsum[1] += p1; lsum[2] += p2; lsum[3] += p3;
-        }
+        for (int i = 0; i < 32; i += 4) exp4_pack_sum<PACKED>(sc + i, c, mc, pk + ci * 16 + i / 2, lsum);
       };
       tmem_ld32(tS, sa);
       tmem_ld_wait();
@@ -1213,6 +1294,312 @@ attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
   }
 }
 
+// ------------------------------------------------------------------------------------------- head dim <= 64, 256 queries
+// Same contract as attention_tc_kernel<1, 128>; one CTA = one (frame, head, 256-query tile).  The source-level profile of
+// the 128-query kernel at the config-2 level-0 shape (profiles/r2_attention_q256.md) showed its softmax warps waiting for
+// S = Q K^T 16 % of their time and one of the two groups idle during the merge-and-store tail: with split-KV inside the
+// CTA the single MMA thread serves the groups strictly in turn (QK(j+2) for one group, PV(j), then the other group), so
+// whichever group runs ahead waits for the other, and the merge is the work of group 0 alone.  Here the two softmax
+// groups own DIFFERENT query tiles (rows 0-127 / 128-255) and walk the SAME key tiles:
+//   * every K / V tile is staged once for 256 queries (half the TMA / L2 -> shared traffic per query);
+//   * each group has its own MMA-issuing warp (warps 1 and 10): QK_g(j+1) goes out the moment group g has pulled S_g(j)
+//     out of tensor memory and PV_g(j) the moment its P is stored -- the groups are coupled only through the depth of
+//     the K / V rings (a stage is released when both issuers' MMAs on it have retired);
+//   * no merge: each group normalises and stores its own 128 rows.
+// Tensor memory: S_0, S_1 (2 x 128 columns), O_0, O_1 (2 x 64), P_0, P_1 (2 x 64 packed bf16 pairs) = 512 columns.
+constexpr int NUM_THREADS_Q256 = 352;   // TMA warp, MMA warp of group 0, 2 x 4 softmax warps, MMA warp of group 1
+
+// EARLY: S(j) is pulled into registers in two steps (columns 0-31, then 32-127 in one go during the first chunk's math) and
+//        handed back a quarter into the tile instead of three quarters, so Q K^T of the next tile has ~3/4 of a tile
+//        period to complete instead of 1/4;  POLY: pairs of every four that take the FMA-pipe exponential.
+template <bool EARLY, int POLY>
+__global__ void __launch_bounds__(NUM_THREADS_Q256, 1)
+attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
+                         const __grid_constant__ CUtensorMap tmV2, const AttnArgs args) {
+  constexpr int BN = 128, DPAD = 64;
+  constexpr int KS = 4, VS = 4;
+  constexpr int Q_BYTES = BQ * DPAD * 2;         // one 128-query tile
+  constexpr int KV_BYTES = BN * DPAD * 2;        // one K (or V) stage
+  constexpr int TM_S = 0, TM_O = 2 * BN, TM_P = TM_O + 2 * DPAD;
+  constexpr uint32_t IDESC_QK = idesc_bf16(BN, false);
+  const int qk_steps = (args.d + 15) >> 4;       // real k-steps of Q K^T; P V runs at N = 16 * qk_steps columns
+  const uint32_t IDESC_PV = idesc_bf16(qk_steps << 4, true);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                            // two query tiles
+  uint8_t* sK = sQ + 2 * Q_BYTES;
+  uint8_t* sV = sK + KS * KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + VS * KV_BYTES);
+  uint64_t* q_full = bars;                       // 1
+  uint64_t* k_full = bars + 1;                   // KS
+  uint64_t* k_empty = k_full + KS;               // KS, two arrivals: one commit per issuer
+  uint64_t* v_full = k_empty + KS;               // VS
+  uint64_t* v_empty = v_full + VS;               // VS, two arrivals
+  uint64_t* s_full = v_empty + VS;               // 2 (per group)
+  uint64_t* s_empty = s_full + 2;                // 2
+  uint64_t* p_full = s_empty + 2;                // 2
+  uint64_t* p_empty = p_full + 2;                // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
+
+  const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
+  // frames with the second key segment (twice the key tiles) first: see attention_tc_kernel
+  const int n = (args.has_seg2 && args.seg2_index) ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+  const int h = blockIdx.y, q0 = blockIdx.x * (2 * BQ);
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 2); }
+    for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 2); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 4); mbar_init(&p_full[g], 4); mbar_init(&p_empty[g], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue();
+
+  int seg2 = -1;
+  if (args.has_seg2) seg2 = args.seg2_index ? args.seg2_index[n] : 0;
+  const int tiles1 = (args.Lk + BN - 1) / BN;
+  const int tiles2 = seg2 >= 0 ? (args.Lk2 + BN - 1) / BN : 0;
+  const int num_tiles = tiles1 + tiles2;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      // ===================== TMA producer =====================
+      mbar_expect_tx(q_full, 2 * Q_BYTES);
+      tma_load_3d(sQ, &tmQ, q_full, 0, h, n * args.Lq + q0);
+      tma_load_3d(sQ + Q_BYTES, &tmQ, q_full, 0, h, n * args.Lq + q0 + BQ);   // past the tensor: zero fill
+      auto tile_row = [&](int j) { return j >= tiles1 ? seg2 * args.Lk2 + (j - tiles1) * BN : n * args.Lk + j * BN; };
+      auto load_k = [&](int j) {
+        const int st = j % KS;
+        mbar_wait(&k_empty[st], ((j / KS) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], KV_BYTES);
+        tma_load_3d(sK + st * KV_BYTES, j >= tiles1 ? &tmK2 : &tmK, &k_full[st], 0, h, tile_row(j));
+      };
+      auto load_v = [&](int j) {
+        const int st = j % VS;
+        mbar_wait(&v_empty[st], ((j / VS) & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], KV_BYTES);
+        tma_load_3d(sV + st * KV_BYTES, j >= tiles1 ? &tmV2 : &tmV, &v_full[st], 0, h, tile_row(j));
+      };
+      // Each issuer retires QK(j+1) before PV(j): K(i + KS) can be requested once both QK(i) are done, V(i + VS) once
+      // both PV(i) are -- in that order neither ring waits behind the other.
+      for (int j = 0; j < KS && j < num_tiles; ++j) load_k(j);
+      for (int j = 0; j < VS && j < num_tiles; ++j) load_v(j);
+      for (int i = 0; i < num_tiles; ++i) {
+        if (i + KS < num_tiles) load_k(i + KS);
+        if (i + VS < num_tiles) load_v(i + VS);
+      }
+    }
+  } else if (warp == 1 || warp == 10) {
+    if (elect_one_sync()) {
+      // ===================== MMA issuer of group g =====================
+      const int g = warp == 1 ? 0 : 1;
+      const uint32_t tS = tmem_base + TM_S + g * BN, tOg = tmem_base + TM_O + g * DPAD, tPg = tmem_base + TM_P + g * (BN / 2);
+      const uint64_t dQ = desc_kmajor(smem_u32(sQ + g * Q_BYTES));
+      auto issue_qk = [&](int j) {
+        const int st = j % KS;
+        mbar_wait(&k_full[st], (j / KS) & 1);
+        mbar_wait(&s_empty[g], (j & 1) ^ 1);          // group g has S(j - 1) in registers
+        tc_fence_after();
+        const uint64_t dK = desc_kmajor(smem_u32(sK + st * KV_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < qk_steps) umma(tS, dQ + ((k * 32) >> 4), dK + ((k * 32) >> 4), IDESC_QK, k != 0);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[g]);
+      };
+      auto issue_pv = [&](int j) {
+        const int st = j % VS;
+        mbar_wait(&v_full[st], (j / VS) & 1);
+        mbar_wait(&p_full[g], j & 1);
+        tc_fence_after();
+        const uint64_t dV = desc_mnmajor(smem_u32(sV + st * KV_BYTES), BN * 128);
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) umma_ts(tOg, tPg + k * 8, dV + k * (2048 >> 4), IDESC_PV, (j | k) != 0);
+        umma_commit(&v_empty[st]);
+        umma_commit(&p_empty[g]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < num_tiles; ++j) {
+        if (j + 1 < num_tiles) issue_qk(j + 1);
+        issue_pv(j);
+      }
+    }
+  } else {
+    // ===================== softmax group g: query rows g * 128 .. g * 128 + 127 =====================
+    const int g = (warp - 2) >> 2;
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;            // query row inside the group's tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
+    const float c = args.scale_log2e;
+    float m_ref = -INFINITY;   // reference maximum the stored O_g / l are relative to (raw score units)
+    float l_run = 0.f;
+    const uint32_t tS = tmem_base + TM_S + g * BN + lane_addr;
+    const uint32_t tO = tmem_base + TM_O + g * DPAD + lane_addr;
+    const uint32_t tP = tmem_base + TM_P + g * (BN / 2) + lane_addr;
+
+    for (int j = 0; j < num_tiles; ++j) {
+      const bool second = j >= tiles1;
+      const int seg_len = second ? args.Lk2 : args.Lk;
+      const int k0 = (second ? (j - tiles1) : j) * BN;
+      const int valid = min(BN, seg_len - k0);       // keys of this tile that exist
+      mbar_wait(&s_full[g], j & 1);
+      tc_fence_after();
+      // online softmax in 32-column chunks, the TMEM load of chunk i + 1 in flight during chunk i (see attention_tc_kernel)
+      uint32_t sa[32], sb[32];
+      uint32_t pk[BN / 2];
+      float alpha_tile = 1.f;
+      float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+      auto chunk = [&](uint32_t (&sc)[32], const int ci) {
+        if (valid < BN) {   // partial last tile of a segment (warp-uniform branch)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (ci * 32 + i >= valid) sc[i] = 0xff800000u;   // -inf
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(sc[i + e]));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        if ((mx - m_ref) * c > RESCALE_THRESHOLD) {              // true for the first chunk ever (m_ref = -inf)
+          const float a = ex2_approx((m_ref - mx) * c);          // 0 the first time
+          m_ref = mx;
+          alpha_tile *= a;
+          l_run *= a;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) lsum[e] *= a;
+          const __nv_bfloat162 a2 = __float2bfloat162_rn(a);
+#pragma unroll
+          for (int i = 0; i < BN / 2; ++i) {
+            if (i < ci * 16) {                                    // chunks of this tile that are already packed
+              __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&pk[i]);
+              v = __hmul2(v, a2);
+              pk[i] = *reinterpret_cast<uint32_t*>(&v);
+            }
+          }
+        }
+        const float mc = m_ref * c;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) exp8_pack_sum<POLY>(sc + i, c, mc, pk + ci * 16 + i / 2, lsum);
+      };
+      tmem_ld32(tS, sa);
+      tmem_ld_wait();
+      pin32(sa);
+      if constexpr (EARLY) {
+        uint32_t sc2[32], sd[32];
+        tmem_ld32(tS + 32, sb);                                   // all three in flight during chunk 0
+        tmem_ld32(tS + 64, sc2);
+        tmem_ld32(tS + 96, sd);
+        chunk(sa, 0);
+        tmem_ld_wait();
+        pin32(sb); pin32(sc2); pin32(sd);
+        tc_fence_before();                                        // S is in registers: hand the buffer back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[g]);
+        chunk(sb, 1);
+        chunk(sc2, 2);
+        chunk(sd, 3);
+      } else {
+#pragma unroll
+      for (int ci = 0; ci < BN / 32; ci += 2) {
+        tmem_ld32(tS + (ci + 1) * 32, sb);                        // in flight during chunk ci
+        chunk(sa, ci);
+        tmem_ld_wait();
+        pin32(sb);
+        if (ci + 2 < BN / 32) {
+          tmem_ld32(tS + (ci + 2) * 32, sa);                      // in flight during chunk ci + 1
+        } else {
+          tc_fence_before();                                      // S is in registers: hand the buffer back
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[g]);
+        }
+        chunk(sb, ci + 1);
+        if (ci + 2 < BN / 32) {
+          tmem_ld_wait();
+          pin32(sa);
+        }
+      }
+      }
+      l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+
+      if (j > 0) {
+        mbar_wait(&p_empty[g], (j - 1) & 1);   // this group's previous PV retired: P buffer reusable, O_g stable
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha_tile != 1.f)) {
+#pragma unroll
+          for (int cc = 0; cc < DPAD / 32; ++cc) {
+            uint32_t o[32];
+            tmem_ld32(tO + cc * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha_tile);
+            tmem_st32(tO + cc * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < BN / 64; ++i) tmem_st32(tP + i * 32, pk + i * 32);   // lane = query row, column = key pair
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+    }
+
+    // ---- normalise and store this group's rows (only the first d columns are real)
+    if (num_tiles > 0) {
+      mbar_wait(&p_empty[g], (num_tiles - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.f / l_run;
+      const int q = q0 + g * BQ + row;
+      bf16* orow = args.out + ((int64_t)n * args.Lq + q) * args.ldo + h * args.d;
+#pragma unroll
+      for (int cc = 0; cc < DPAD / 32; ++cc) {
+        if (cc * 32 < args.d) {                      // warp-uniform
+          uint32_t o[32];
+          tmem_ld32(tO + cc * 32, o);
+          tmem_ld_wait();
+          if (q < args.Lq) {
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) {
+              const int col = cc * 32 + gg * 8;
+              if (col < args.d) {
+                uint4 val;
+                val.x = pack_bf16(__uint_as_float(o[gg * 8 + 0]) * inv, __uint_as_float(o[gg * 8 + 1]) * inv);
+                val.y = pack_bf16(__uint_as_float(o[gg * 8 + 2]) * inv, __uint_as_float(o[gg * 8 + 3]) * inv);
+                val.z = pack_bf16(__uint_as_float(o[gg * 8 + 4]) * inv, __uint_as_float(o[gg * 8 + 5]) * inv);
+                val.w = pack_bf16(__uint_as_float(o[gg * 8 + 6]) * inv, __uint_as_float(o[gg * 8 + 7]) * inv);
+                *reinterpret_cast<uint4*>(orow + col) = val;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1245,15 +1632,26 @@ int encode_qkv_map(mmgt_ctx* ctx, CUtensorMap* map, const void* base, int d, int
   return 0;
 }
 
-template <int DCH, int BN>
+template <int DCH, int BN, bool PACKED>
 int launch_attn(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaStream_t st) {
   constexpr bool p_tmem = (2 * BN + 2 * 64 * DCH + BN) <= 512;
   constexpr int smem = BQ * 64 * DCH * 2 + (k_stages(DCH) + v_stages(DCH)) * BN * 64 * DCH * 2 + (p_tmem ? 0 : 2 * BQ * BN * 2) + BQ * 8 + 1024 + 256;
   static_assert(smem <= 232448, "shared memory budget");
-  MMGT_CUDA_OK(mmgt_smem_optin(ctx, attention_tc_kernel<DCH, BN>, smem));
+  MMGT_CUDA_OK(mmgt_smem_optin(ctx, attention_tc_kernel<DCH, BN, PACKED>, smem));
   dim3 grid((a.Lq + BQ - 1) / BQ, a.heads, a.N);
-  MMGT_CUDA_OK(mmgt_launch(ctx, attention_tc_kernel<DCH, BN>, grid, dim3(NUM_THREADS), smem, st, maps[0], maps[1], maps[2], maps[3],
+  MMGT_CUDA_OK(mmgt_launch(ctx, attention_tc_kernel<DCH, BN, PACKED>, grid, dim3(NUM_THREADS), smem, st, maps[0], maps[1], maps[2], maps[3],
                            maps[4], a));
+  MMGT_LAUNCH_OK(ctx);
+  return 0;
+}
+
+template <bool EARLY, int POLY>
+int launch_attn_q256(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaStream_t st) {
+  constexpr int smem = 2 * BQ * 64 * 2 + (4 + 4) * 128 * 64 * 2 + 1024 + 256;
+  MMGT_CUDA_OK(mmgt_smem_optin(ctx, attention_tc_q256_kernel<EARLY, POLY>, smem));
+  dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.N);
+  MMGT_CUDA_OK(mmgt_launch(ctx, attention_tc_q256_kernel<EARLY, POLY>, grid, dim3(NUM_THREADS_Q256), smem, st, maps[0], maps[1],
+                           maps[2], maps[3], maps[4], a));
   MMGT_LAUNCH_OK(ctx);
   return 0;
 }
@@ -1312,13 +1710,24 @@ int mmgt_attention_tc(mmgt_ctx* ctx, const mmgt_attention_params* p, cudaStream_
   a.seg2_index = p->seg2_index; a.has_seg2 = p->k2 != nullptr;
   a.out = (bf16*)p->out; a.ldo = p->ldo;
   a.scale_log2e = p->scale * 1.4426950408889634f;
+  const bool pk = ctx->attn_packed != 0;   // flag 16: FFMA2 / FADD2 in the softmax loops
   if (dch == 1) {
     if (ctx->attn_v2) return launch_attn64(ctx, maps, a, st);
     const int64_t items = (int64_t)((p->Lq + BQ - 1) / BQ) * p->heads * p->N;
     if (items < (1ll << 31) && (ctx->attn_persist >= 2 || (ctx->attn_persist == 1 && items > ctx->num_sms)))
       return launch_attn_persist(ctx, maps, a, st);
-    return launch_attn<1, 128>(ctx, maps, a, st);
+    // 256 queries per CTA once both softmax groups have rows of their own (flag 15)
+    if (ctx->attn_q256 && p->Lq > BQ) {
+      switch (ctx->attn_q256) {            // A/B variants: S hand-back point, share of FMA-pipe exponentials
+        case 2: return launch_attn_q256<true, 0>(ctx, maps, a, st);
+        case 3: return launch_attn_q256<true, 1>(ctx, maps, a, st);
+        case 4: return launch_attn_q256<true, 2>(ctx, maps, a, st);
+        case 5: return launch_attn_q256<false, 1>(ctx, maps, a, st);
+        default: return launch_attn_q256<false, 0>(ctx, maps, a, st);
+      }
+    }
+    return pk ? launch_attn<1, 128, true>(ctx, maps, a, st) : launch_attn<1, 128, false>(ctx, maps, a, st);
   }
-  if (dch == 2) return launch_attn<2, 128>(ctx, maps, a, st);
-  return launch_attn<3, 64>(ctx, maps, a, st);
+  if (dch == 2) return pk ? launch_attn<2, 128, true>(ctx, maps, a, st) : launch_attn<2, 128, false>(ctx, maps, a, st);
+  return pk ? launch_attn<3, 64, true>(ctx, maps, a, st) : launch_attn<3, 64, false>(ctx, maps, a, st);
 }

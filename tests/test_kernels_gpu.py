@@ -533,6 +533,7 @@ def _attn_ref(q, k, v, heads):
     return (s.softmax(-1) @ vh).transpose(1, 2).reshape(n, lq, c)
 
 
+ATTN_Q256_DEFAULT = 1       # mmgt_ctx_flag(15) default (csrc/ctx.cu)
 ATTN_CASES = [(4, 64, 64, 64, 8, 40), (3, 100, 100, 100, 8, 8), (2, 256, 256, 0, 8, 80), (2, 70, 32, 0, 8, 40),
               (2, 64, 64, 64, 8, 160), (6, 16, 16, 16, 8, 32), (3, 1024, 1024, 1024, 8, 40), (2, 4096, 4096, 4096, 8, 40),
               (2, 300, 300, 300, 8, 80), (2, 256, 256, 256, 8, 160), (2, 1024, 32, 0, 8, 80), (3, 200, 136, 72, 8, 16),
@@ -565,12 +566,14 @@ def test_attention_two_segments(dev, dtype, tc, N, Lq, Lk, Lk2, heads, d):
                 # persistent CTAs (flag 14) walking many items each -- 3 and 7 CTAs for all (frame, head, query tile) items,
                 # frames with one and with two key segments mixed -- vs one item per CTA: same arithmetic, same bits
                 eng.ctx.set_attention_persistent(0)
+                eng.ctx.set_attention_q256(False)        # the persistent kernel walks 128-query items
                 one = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
                 for ctas in (3, 7):
                     eng.ctx.set_attention_persistent(ctas)
                     per = eng.attention(q, k, v, heads, k2=k2, v2=v2, seg2_index=idx)
                     assert torch.equal(per, one), ctas
                 eng.ctx.set_attention_persistent(0)
+                eng.ctx.set_attention_q256(ATTN_Q256_DEFAULT)
             refs = []
             for n in range(N):
                 kk, vv = k[n:n + 1], v[n:n + 1]
@@ -584,15 +587,61 @@ def test_attention_two_segments(dev, dtype, tc, N, Lq, Lk, Lk2, heads, d):
             ref = _attn_ref(q, k, v, heads)
             if tc and d <= 64:
                 eng.ctx.set_attention_persistent(0)
+                eng.ctx.set_attention_q256(False)
                 one = eng.attention(q, k, v, heads)
                 eng.ctx.set_attention_persistent(5)
                 assert torch.equal(eng.attention(q, k, v, heads), one)
                 eng.ctx.set_attention_persistent(0)
+                eng.ctx.set_attention_q256(ATTN_Q256_DEFAULT)
         assert rel_l2(out.float(), ref) < (2e-5 if dtype == torch.float32 else 8e-3)
     finally:
         eng.ctx.set_tensor_cores(True)
         eng.ctx.set_attention_v2(False)
         eng.ctx.set_attention_persistent(0)
+        eng.ctx.set_attention_q256(ATTN_Q256_DEFAULT)
+
+
+@pytest.mark.parametrize("N,Lq,Lk,Lk2,heads,d", ATTN_CASES + [(2, 257, 129, 384, 8, 40), (5, 512, 512, 512, 8, 40), (1, 2304, 2304, 0, 8, 40)])
+def test_attention_kernel_variants(dev, N, Lq, Lk, Lk2, heads, d):
+    """Flags 15 / 16 of the tensor-core attention: packed fp32 pairs (FFMA2 / FADD2) must not change a bit of either kernel;
+    the 256-query kernel (one query tile + one MMA-issuing warp per softmax group, no split-KV merge) against float32."""
+    if Lq < 64:
+        pytest.skip("tensor-core attention needs Lq >= 64")
+    eng = eng_for(dev, torch.bfloat16)
+    C = heads * d
+    q = rnd(N, Lq, 3 * C, dev=dev, dtype=torch.bfloat16, seed=71)[:, :, :C]
+    kvbuf = rnd(N, Lk, 3 * C, dev=dev, dtype=torch.bfloat16, seed=73)
+    k, v = kvbuf[:, :, C:2 * C], kvbuf[:, :, 2 * C:]
+    kw = {}
+    if Lk2:
+        bank = rnd(2, Lk2, 2 * C, dev=dev, dtype=torch.bfloat16, seed=72)
+        idx = torch.tensor([(-1 if i % 3 == 0 else i % 2) for i in range(N)], dtype=torch.int32, device=dev)
+        kw = dict(k2=bank[:, :, :C], v2=bank[:, :, C:], seg2_index=idx)
+    refs = []
+    for n in range(N):
+        kk, vv = k[n:n + 1], v[n:n + 1]
+        if Lk2 and kw["seg2_index"][n] >= 0:
+            i = int(kw["seg2_index"][n])
+            kk, vv = torch.cat([kk, kw["k2"][i:i + 1]], 1), torch.cat([vv, kw["v2"][i:i + 1]], 1)
+        refs.append(_attn_ref(q[n:n + 1], kk, vv, heads))
+    ref = torch.cat(refs)
+    outs = {}
+    try:
+        for q256, packed in ((0, False), (0, True), (1, True), (2, True), (3, True), (4, True), (5, True)):
+            eng.ctx.set_attention_q256(q256)
+            eng.ctx.set_attention_packed(packed)
+            outs[q256, packed] = o = eng.attention(q, k, v, heads, **kw)
+            assert torch.isfinite(o).all(), (q256, packed)
+            assert rel_l2(o.float(), ref) < 8e-3, (q256, packed)
+    finally:
+        eng.ctx.set_attention_q256(ATTN_Q256_DEFAULT)
+        eng.ctx.set_attention_packed(True)
+    assert torch.equal(outs[0, False], outs[0, True])         # packed pairs: same IEEE operations
+    assert torch.equal(outs[1, True], outs[2, True])          # where S is handed back does not touch the arithmetic
+    assert torch.equal(outs[3, True], outs[5, True])
+    if d <= 64 and Lq > 128:                                   # FMA-pipe exp2 (7.5e-5 relative) vs MUFU: far inside bf16 rounding
+        assert rel_l2(outs[3, True].float(), outs[1, True].float()) < 2e-3
+        assert rel_l2(outs[4, True].float(), outs[1, True].float()) < 2e-3
 
 
 def test_attention_running_max_jumps_late(dev):
@@ -612,15 +661,19 @@ def test_attention_running_max_jumps_late(dev):
     q, k, v, k2, v2 = (t.to(device=dev, dtype=torch.bfloat16) for t in (q, k, v, k2, v2))
     ref = _attn_ref(q, torch.cat([k, k2.expand(N, -1, -1)], 1), torch.cat([v, v2.expand(N, -1, -1)], 1), heads)
     try:
-        for v2_kernel, persist in ((True, 0), (False, 0), (False, 2)):
+        for v2_kernel, persist, q256 in ((True, 0, 0), (False, 0, 0), (False, 2, 0), (False, 0, 1), (False, 0, 3), (False, 0, 4)):
             eng.ctx.set_attention_v2(v2_kernel)
             eng.ctx.set_attention_persistent(persist)
+            eng.ctx.set_attention_q256(q256)
+            eng.ctx.set_attention_packed(bool(q256))
             out = eng.attention(q, k, v, heads, k2=k2, v2=v2)
             assert torch.isfinite(out).all()
-            assert rel_l2(out.float(), ref) < 1e-2, (v2_kernel, persist)
+            assert rel_l2(out.float(), ref) < 1e-2, (v2_kernel, persist, q256)
     finally:
         eng.ctx.set_attention_v2(False)
         eng.ctx.set_attention_persistent(0)
+        eng.ctx.set_attention_q256(ATTN_Q256_DEFAULT)
+        eng.ctx.set_attention_packed(True)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
