@@ -81,9 +81,12 @@ MMGT_API const char* mmgt_last_error(void);
  * flag 14: head dim <= 64 attention on persistent CTAs (default 0 -- measured slower; 1 = when items > SMs): one CTA per SM walks the (frame, head, query tile)
  *         items, the next item's loads and first Q K^T overlapping the merge-and-store tail of the current one; 0 = one
  *         item per CTA; n >= 2 = always, on at most n CTAs (tests).  Same arithmetic, bit-identical results.  A/B switch.
- * flag 15: head dim <= 64 attention with 256 queries per CTA (default 1): the two softmax groups own different query
+ * flag 15: head dim <= 64 attention with 256 queries per CTA (default 5): the two softmax groups own different query
  *         tiles and walk the same key tiles, each with its own MMA-issuing warp; no split-KV merge.  0 = 128-query CTAs
- *         whose groups take alternate key tiles.  A/B switch.
+ *         whose groups take alternate key tiles.  Variants of the 256-query kernel: 1 = every exponential on MUFU.EX2;
+ *         5 = one score pair in four through a degree-3 polynomial on the FMA pipe (7.5e-5 relative, far inside the bf16
+ *         rounding of P); 2 / 3 / 4 = S handed back to the MMA warp a quarter into the tile, with 0 / 1 / 2 pairs in four
+ *         on the FMA pipe (measured slower).  A/B switch.
  * flag 16: attention softmax loops on packed fp32 pairs (fma.rn.f32x2 / add.rn.f32x2; default 1).  Same IEEE operations
  *         as the scalar form: bit-identical results.  A/B switch. */
 MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);

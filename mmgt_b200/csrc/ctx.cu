@@ -54,7 +54,7 @@ extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
     }
   }
   c->attn_persist = 0;  // measured (profiles/r2_attention_v2.md): 2134 vs 1815 us per level-0 launch, 452 vs 442 ms per step in favour of one item per CTA
-  c->attn_q256 = 1;    // measured (profiles/r2_attention_q256.md): 1576 vs 1815 us per level-0 launch, 417 vs 435 ms per step
+  c->attn_q256 = 5;    // measured (profiles/r2_attention_q256.md): 1476 vs 1815 us per level-0 launch, 413 vs 435 ms per step
   c->attn_packed = 1;
   c->attn_v2 = 0;     // measured (profiles/r2_ab_flags.md): 475 vs 482 ms per step in favour of the two-buffer kernel
   *out = c;

@@ -533,7 +533,7 @@ def _attn_ref(q, k, v, heads):
     return (s.softmax(-1) @ vh).transpose(1, 2).reshape(n, lq, c)
 
 
-ATTN_Q256_DEFAULT = 1       # mmgt_ctx_flag(15) default (csrc/ctx.cu)
+ATTN_Q256_DEFAULT = 5       # mmgt_ctx_flag(15) default (csrc/ctx.cu)
 ATTN_CASES = [(4, 64, 64, 64, 8, 40), (3, 100, 100, 100, 8, 8), (2, 256, 256, 0, 8, 80), (2, 70, 32, 0, 8, 40),
               (2, 64, 64, 64, 8, 160), (6, 16, 16, 16, 8, 32), (3, 1024, 1024, 1024, 8, 40), (2, 4096, 4096, 4096, 8, 40),
               (2, 300, 300, 300, 8, 80), (2, 256, 256, 256, 8, 160), (2, 1024, 32, 0, 8, 80), (3, 200, 136, 72, 8, 16),
