@@ -224,7 +224,7 @@ def run_ours(args):
         eng.ctx.set_pdl(bool(args.pdl))
     for name, setter in (("gn_split", eng.ctx.set_groupnorm_split), ("conv_implicit", eng.ctx.set_conv_implicit_all),
                          ("geglu_exact", eng.ctx.set_geglu_exact), ("attn_v2", eng.ctx.set_attention_v2), ("attn_persist", eng.ctx.set_attention_persistent),
-                         ("attn_q256", eng.ctx.set_attention_q256), ("attn_packed", eng.ctx.set_attention_packed),
+                         ("attn_q256", eng.ctx.set_attention_q256), ("attn_packed", eng.ctx.set_attention_packed), ("ln_persist", eng.ctx.set_layernorm_persistent),
                          ("temporal_rows", eng.ctx.set_temporal_rows), ("lean_epilogue", eng.ctx.set_lean_epilogue),
                          ("tma_store", eng.ctx.set_tma_store), ("residual_mma", eng.ctx.set_residual_mma)):
         v = getattr(args, name)
@@ -311,7 +311,7 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps(dict(quick=True, ms_per_step=ms_per_step, value=value, n_gpus=world, config=args.config,
                                   flags=dict(gn_split=args.gn_split, conv_implicit=args.conv_implicit, geglu_exact=args.geglu_exact,
-                                             fuse_ln=args.fuse_ln, attn_v2=args.attn_v2, attn_persist=args.attn_persist, attn_q256=args.attn_q256, attn_packed=args.attn_packed, deep_batch=args.deep_batch, deep_from=args.deep_from, level_batch=args.level_batch,
+                                             fuse_ln=args.fuse_ln, attn_v2=args.attn_v2, attn_persist=args.attn_persist, attn_q256=args.attn_q256, attn_packed=args.attn_packed, ln_persist=args.ln_persist, deep_batch=args.deep_batch, deep_from=args.deep_from, level_batch=args.level_batch,
                                              split_branches=args.split_branches,
                                              temporal_rows=args.temporal_rows, lean_epilogue=args.lean_epilogue, tma_store=args.tma_store, residual_mma=args.residual_mma), simt_launches=eng.ctx.simt_launches() - s0,
                                   gpu_launches=launches, clocks=clocks)), flush=True)
@@ -591,6 +591,7 @@ def main():
     ap.add_argument("--geglu-exact", type=int, default=None, help="A/B: 1 = erf GELU in the GEGLU epilogue")
     ap.add_argument("--attn-v2", type=int, default=None, help="A/B: 1 / 0 three-S-buffer / round-1 attention kernel (head dim <= 64)")
     ap.add_argument("--attn-q256", type=int, default=None, help="A/B: 1 / 0 256-query / 128-query CTAs in the head dim <= 64 attention kernel")
+    ap.add_argument("--ln-persist", type=int, default=None, help="A/B: LayerNorm grid: 0 = 16 blocks per SM, 1 = one exact persistent wave, 2 = + prefetch")
     ap.add_argument("--attn-packed", type=int, default=None, help="A/B: 1 / 0 packed fp32 pairs (FFMA2 / FADD2) in the attention softmax loops")
     ap.add_argument("--attn-persist", type=int, default=None, help="A/B: 1 / 0 persistent / one-item-per-CTA attention kernel (head dim <= 64)")
     ap.add_argument("--deep-batch", type=int, default=None,

@@ -203,6 +203,10 @@ class Context:
         5: FMA-pipe exp2 for 1 of 4 pairs without the early hand-back)."""
         return int(self.lib.mmgt_ctx_flag(self.handle, 15, int(on)))
 
+    def set_layernorm_persistent(self, mode) -> int:
+        """LayerNorm grid (flag 17): 0 = up to 16 blocks per SM, 1 = one exact wave of persistent blocks, 2 = + next-row prefetch."""
+        return int(self.lib.mmgt_ctx_flag(self.handle, 17, int(mode)))
+
     def set_attention_packed(self, on: bool) -> bool:
         """Attention softmax loops on packed fp32 pairs (FFMA2 / FADD2), bit-identical to the scalar form (flag 16)."""
         return bool(self.lib.mmgt_ctx_flag(self.handle, 16, 1 if on else 0))

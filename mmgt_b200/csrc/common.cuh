@@ -25,6 +25,7 @@ struct mmgt_ctx {
   int tma_store;              // lean epilogues write their tiles through TMA stores (default 1; 0 = per-lane stores, A/B)
   int lean_epilogue;          // tensor-core GEMM / conv: specialised straight-line epilogues where the options allow (default 1; A/B)
   int temporal_rows;          // temporal attention (head dim <= 80) on the row-coalesced cp.async kernel (default 1; A/B)
+  int ln_persist;             // LayerNorm on one exact wave of persistent blocks with next-row prefetch (A/B)
   int attn_q256;              // head dim <= 64: 256 queries per CTA, one query tile + one MMA-issuing warp per softmax group (A/B)
   int attn_packed;            // attention softmax loops on packed fp32 pairs (FFMA2 / FADD2); same arithmetic (A/B)
   int attn_persist;           // head dim <= 64: one persistent CTA per SM walking (frame, head, query tile) items: 0 off (default: measured faster), 1 when

@@ -56,6 +56,7 @@ extern "C" int mmgt_ctx_create(mmgt_ctx** out, int device) {
   c->attn_persist = 0;  // measured (profiles/r2_attention_v2.md): 2134 vs 1815 us per level-0 launch, 452 vs 442 ms per step in favour of one item per CTA
   c->attn_q256 = 5;    // measured (profiles/r2_attention_q256.md): 1476 vs 1815 us per level-0 launch, 413 vs 435 ms per step
   c->attn_packed = 1;
+  c->ln_persist = 0;
   c->attn_v2 = 0;     // measured (profiles/r2_ab_flags.md): 475 vs 482 ms per step in favour of the two-buffer kernel
   *out = c;
   return 0;
@@ -87,6 +88,10 @@ extern "C" int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value) {
     return ctx->strict_tc;
   }
   if (flag == 5) return ctx->simt_launches;
+  if (flag == 17) {
+    if (value >= 0) ctx->ln_persist = (int)value;
+    return ctx->ln_persist;
+  }
   if (flag == 15) {
     if (value >= 0) ctx->attn_q256 = (int)value;
     return ctx->attn_q256;

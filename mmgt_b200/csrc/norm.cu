@@ -443,25 +443,43 @@ layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __rest
 // normalises 32 / G rows at a time and every lane has VPL independent loads in flight (the one-warp-per-row
 // kernel below issues 1-2 loads per lane between two dependent shuffle reductions: latency-bound at C = 320).
 // gamma / beta sit in shared memory and are read as float4.
-template <typename T, int VPL, int G>
+// The row a lane group works on next is fetched (as raw 16-byte vectors) before the arithmetic and the stores of the current
+// one, so with an exact-wave persistent grid (flag 17) every resident warp always has VPL loads in flight.
+template <typename T, int VPL, int G, bool PREFETCH>
 __global__ void __launch_bounds__(256)
 layernorm_grp_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ pe, int64_t rows, int C, int T_tok, int F,
                      float eps) {
   constexpr int VEC = VecOf<T>::N;
+  typedef typename VecOf<T>::type Raw;
   extern __shared__ float gb[];   // gamma[C], beta[C]
   pdl_prologue();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { gb[i] = gamma[i]; gb[C + i] = beta[i]; }
-  __syncthreads();
   const int gl = threadIdx.x % G;
   const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int64_t ngrp = (int64_t)gridDim.x * blockDim.x / G;
+  Raw nxt[VPL];
+  if (PREFETCH && grp < rows) {
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) nxt[j] = *reinterpret_cast<const Raw*>(x + grp * C + (size_t)(gl + j * G) * VEC);
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { gb[i] = gamma[i]; gb[C + i] = beta[i]; }
+  __syncthreads();
   const float inv_c = 1.f / (float)C;
   for (int64_t row = grp; row < rows; row += ngrp) {
     float v[VPL][VEC];
-    const T* xr = x + row * C;
+    if constexpr (PREFETCH) {
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) load_vec<T>(xr + (size_t)(gl + j * G) * VEC, v[j]);
+      for (int j = 0; j < VPL; ++j) unpack_vec<T>(nxt[j], v[j]);
+      if (row + ngrp < rows) {
+        const T* xn = x + (row + ngrp) * C;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) nxt[j] = *reinterpret_cast<const Raw*>(xn + (size_t)(gl + j * G) * VEC);
+      }
+    } else {
+      const T* xr = x + row * C;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) load_vec<T>(xr + (size_t)(gl + j * G) * VEC, v[j]);
+    }
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < VPL; ++j)
@@ -506,10 +524,18 @@ template <typename T, int VPL, int G>
 void launch_ln_grp(mmgt_ctx* ctx, const void* x, void* y, const float* gamma, const float* beta, const float* pe,
                    int64_t rows, int C, int T_tok, int F, float eps, cudaStream_t st) {
   const int rows_per_block = 256 / G;
-  // two resident waves of row groups per SM slot keep the tail short
-  const int64_t blocks = std::min<int64_t>((rows + rows_per_block - 1) / rows_per_block, (int64_t)ctx->num_sms * 16);
-  mmgt_launch(ctx, layernorm_grp_kernel<T, VPL, G>, dim3((int)blocks), dim3(256), sizeof(float) * 2 * C, st, (const T*)x, (T*)y,
-              gamma, beta, pe, rows, C, T_tok, F, eps);
+  const int64_t need = (rows + rows_per_block - 1) / rows_per_block;
+  // flag 17 = 1: exactly one wave of resident blocks (3 per SM) walking the rows; = 2: the same with the next row of a lane
+  // group prefetched during the arithmetic of the current one (118 registers -> 2 blocks per SM; VPL <= 5 only);
+  // 0: up to 16 blocks per SM (5.3 waves at the 64 x 64 level, the last one a third full)
+  if (ctx->ln_persist == 2 && VPL <= 5) {
+    mmgt_launch(ctx, layernorm_grp_kernel<T, VPL, G, (VPL <= 5)>, dim3((int)std::min<int64_t>(need, (int64_t)ctx->num_sms * 2)),
+                dim3(256), sizeof(float) * 2 * C, st, (const T*)x, (T*)y, gamma, beta, pe, rows, C, T_tok, F, eps);
+    return;
+  }
+  const int64_t blocks = std::min<int64_t>(need, (int64_t)ctx->num_sms * (ctx->ln_persist ? 3 : 16));
+  mmgt_launch(ctx, layernorm_grp_kernel<T, VPL, G, false>, dim3((int)blocks), dim3(256), sizeof(float) * 2 * C, st, (const T*)x,
+              (T*)y, gamma, beta, pe, rows, C, T_tok, F, eps);
 }
 
 // Picks (VPL, G) with VPL * G == C / VEC for the widths of the full model (320 / 640 / 1280); false => generic kernel.

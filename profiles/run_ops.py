@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--attn-v2", action="store_true", help="A/B: the three-S-buffer attention kernel for head dim <= 64")
     ap.add_argument("--attn-q256", type=int, default=None, help="A/B: flag 15")
     ap.add_argument("--attn-packed", type=int, default=None, help="A/B: flag 16")
+    ap.add_argument("--ln-persist", type=int, default=None, help="A/B: flag 17")
     ap.add_argument("--attn-persist", action="store_true", help="A/B: head dim <= 64 attention on persistent CTAs (flag 14) instead of one (frame, head, query tile) per CTA")
     ap.add_argument("--lane-residual", action="store_true", help="A/B: residual epilogues with per-lane loads instead of [R | I] k-blocks")
     ap.add_argument("--lane-stores", action="store_true", help="A/B: lean epilogues with per-lane stores instead of TMA stores")
@@ -151,6 +152,8 @@ def main():
     eng.ctx.set_attention_persistent(1 if args.attn_persist else 0)
     if args.attn_q256 is not None:
         eng.ctx.set_attention_q256(int(args.attn_q256))
+    if args.ln_persist is not None:
+        eng.ctx.set_layernorm_persistent(int(args.ln_persist))
     if args.attn_packed is not None:
         eng.ctx.set_attention_packed(bool(args.attn_packed))
     eng.ctx.set_groupnorm_split(not args.gn_fused)

@@ -15,7 +15,7 @@ tail -2 gpurun_out/r2_ncu_step.err; wc -l gpurun_out/r2_launches_step.csv
 python profiles/summarize_launches.py gpurun_out/r2_launches_step.csv gpurun_out/r2_launches_step --all > /dev/null 2>&1; head -24 gpurun_out/r2_launches_step.md; rm -f gpurun_out/r2_launches_step.csv
 OPS="attn_d40 attn_d40_self attn_d80 gemm_960x320 gemm_320x320_res gemm_geglu_2560x320 gemm_320x1280_res gemm_320x968_res conv3x3_320_320 conv3x3_1280_1280 conv3x3_320_320_stride2 conv3x3_640_640_upsample2x groupnorm_320_silu groupnorm_1280_silu layernorm_320 temporal_attn_d40 audio_attention_fused_d40"
 timeout 900 ncu --set full --clock-control none --profile-from-start off -f -o /tmp/r2_ops_final python profiles/run_ops.py $OPS > gpurun_out/r2_ncu_ops_final.log 2>&1
-python profiles/summarize_ncu.py /tmp/r2_ops_final.ncu-rep gpurun_out/r2_ops_ncu.md $OPS > /dev/null 2>&1; cat gpurun_out/r2_ops_ncu.md | cut -c1-260
+python profiles/summarize_ncu.py /tmp/r2_ops_final.ncu-rep gpurun_out/r2_ops_ncu.md ${OPS//_silu/_silu*2} > /dev/null 2>&1; cat gpurun_out/r2_ops_ncu.md | cut -c1-260
 ncu -i /tmp/r2_ops_final.ncu-rep --page raw --csv 2>/dev/null | gzip > gpurun_out/r2_ops_ncu_raw.csv.gz
 timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/r2_attn_d40_final python profiles/run_ops.py attn_d40 > /dev/null 2>&1
 ls -la gpurun_out/ | tail -20; du -sh gpurun_out

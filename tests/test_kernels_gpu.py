@@ -79,6 +79,28 @@ def test_layernorm_and_positional_encoding(dev, dtype, C):
     assert rel_l2(eng.layernorm(x, g, b, pe=pe, T=T, F=Fr).float(), ref + pe[frame]) < (2e-6 if dtype == torch.float32 else 5e-3)
 
 
+@pytest.mark.parametrize("C,rows", [(320, 40000), (640, 9001), (1280, 3000), (320, 37)])
+def test_layernorm_grid_variants_bit_identical(dev, C, rows):
+    """Flag 17: exact-wave persistent LayerNorm grids (every lane group walks several rows, with and without the next-row
+    prefetch) must reproduce the default grid bit for bit, with the motion module's positional table too."""
+    eng = eng_for(dev, torch.bfloat16)
+    x = rnd(rows, C, dev=dev, dtype=torch.bfloat16, seed=17) * 2 + 0.5
+    g, b = rnd(C, dev=dev, seed=18) * 0.1 + 1, rnd(C, dev=dev, seed=19) * 0.1
+    pe = rnd(24, C, dev=dev, seed=20)
+    T = max(1, rows // 24)
+    try:
+        outs = []
+        for mode in (0, 1, 2):
+            eng.ctx.set_layernorm_persistent(mode)
+            outs.append((eng.layernorm(x, g, b), eng.layernorm(x[:T * 24], g, b, pe=pe, T=T, F=24)))
+    finally:
+        eng.ctx.set_layernorm_persistent(LN_PERSIST_DEFAULT)
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
+    assert rel_l2(outs[0][0].float(), ref) < 5e-3
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])
+
+
 def _gemm_ref(A, W, bias, rowscale, rowbias, rpg, residual, alpha, geglu):
     acc = A.float() @ W.float().t()
     if bias is not None:
@@ -533,6 +555,7 @@ def _attn_ref(q, k, v, heads):
     return (s.softmax(-1) @ vh).transpose(1, 2).reshape(n, lq, c)
 
 
+LN_PERSIST_DEFAULT = 0        # mmgt_ctx_flag(17) default (csrc/ctx.cu)
 ATTN_Q256_DEFAULT = 5       # mmgt_ctx_flag(15) default (csrc/ctx.cu)
 ATTN_CASES = [(4, 64, 64, 64, 8, 40), (3, 100, 100, 100, 8, 8), (2, 256, 256, 0, 8, 80), (2, 70, 32, 0, 8, 40),
               (2, 64, 64, 64, 8, 160), (6, 16, 16, 16, 8, 32), (3, 1024, 1024, 1024, 8, 40), (2, 4096, 4096, 4096, 8, 40),
