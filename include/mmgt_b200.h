@@ -85,8 +85,10 @@ MMGT_API const char* mmgt_last_error(void);
  *         tiles and walk the same key tiles, each with its own MMA-issuing warp; no split-KV merge.  0 = 128-query CTAs
  *         whose groups take alternate key tiles.  Variants of the 256-query kernel: 1 = every exponential on MUFU.EX2;
  *         5 = one score pair in four through a degree-3 polynomial on the FMA pipe (7.5e-5 relative, far inside the bf16
- *         rounding of P); 2 / 3 / 4 = S handed back to the MMA warp a quarter into the tile, with 0 / 1 / 2 pairs in four
- *         on the FMA pipe (measured slower).  A/B switch.
+ *         rounding of P); 4 = two pairs in four (measured slower); 2 / 6 = 1 / 5 with a suspend-time hint on the mbarrier
+ *         waits of the single-thread TMA / MMA roles.  A/B switch.
+ * flag 17: LayerNorm grid: 0 = up to 16 blocks per SM (default), 1 = one exact wave of persistent blocks, 2 = the same with
+ *         the next row of a lane group prefetched.  Bit-identical results.  A/B switch.
  * flag 16: attention softmax loops on packed fp32 pairs (fma.rn.f32x2 / add.rn.f32x2; default 1).  Same IEEE operations
  *         as the scalar form: bit-identical results.  A/B switch. */
 MMGT_API int64_t mmgt_ctx_flag(mmgt_ctx* ctx, int flag, int64_t value);

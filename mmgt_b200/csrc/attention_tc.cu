@@ -64,6 +64,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// The same wait with a suspend-time hint: the single-thread TMA / MMA roles wait most of a tile period per event; with the
+// default (short) time limit their try_wait + branch loops issue ~45 M instructions per launch on three of the four
+// schedulers, next to the softmax warps (ncu source page, profiles/r2_attention_q256.md).  The thread still resumes as soon
+// as the phase completes.
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(hint_ns)
+        : "memory");
+  } while (!done);
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
@@ -1309,10 +1328,10 @@ attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 // Tensor memory: S_0, S_1 (2 x 128 columns), O_0, O_1 (2 x 64), P_0, P_1 (2 x 64 packed bf16 pairs) = 512 columns.
 constexpr int NUM_THREADS_Q256 = 352;   // TMA warp, MMA warp of group 0, 2 x 4 softmax warps, MMA warp of group 1
 
-// EARLY: S(j) is pulled into registers in two steps (columns 0-31, then 32-127 in one go during the first chunk's math) and
-//        handed back a quarter into the tile instead of three quarters, so Q K^T of the next tile has ~3/4 of a tile
-//        period to complete instead of 1/4;  POLY: pairs of every four that take the FMA-pipe exponential.
-template <bool EARLY, int POLY>
+// HINT: the TMA / MMA threads wait with a 4 us suspend-time hint (mbar_wait_hint);  POLY: pairs of every four that take
+// the FMA-pipe exponential.  (Handing S back a quarter into the tile instead of three quarters -- all four 32-column
+// chunks of S in registers early -- measured no gain: 1579 vs 1584 us, and 1553 vs 1476 us together with POLY = 1.)
+template <bool HINT, int POLY>
 __global__ void __launch_bounds__(NUM_THREADS_Q256, 1)
 attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
@@ -1372,6 +1391,10 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const int tiles1 = (args.Lk + BN - 1) / BN;
   const int tiles2 = seg2 >= 0 ? (args.Lk2 + BN - 1) / BN : 0;
   const int num_tiles = tiles1 + tiles2;
+  auto wait = [](uint64_t* bar, uint32_t parity) {     // waits of the single-thread roles
+    if constexpr (HINT) mbar_wait_hint(bar, parity, 4000u);
+    else mbar_wait(bar, parity);
+  };
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -1382,13 +1405,13 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       auto tile_row = [&](int j) { return j >= tiles1 ? seg2 * args.Lk2 + (j - tiles1) * BN : n * args.Lk + j * BN; };
       auto load_k = [&](int j) {
         const int st = j % KS;
-        mbar_wait(&k_empty[st], ((j / KS) & 1) ^ 1);
+        wait(&k_empty[st], ((j / KS) & 1) ^ 1);
         mbar_expect_tx(&k_full[st], KV_BYTES);
         tma_load_3d(sK + st * KV_BYTES, j >= tiles1 ? &tmK2 : &tmK, &k_full[st], 0, h, tile_row(j));
       };
       auto load_v = [&](int j) {
         const int st = j % VS;
-        mbar_wait(&v_empty[st], ((j / VS) & 1) ^ 1);
+        wait(&v_empty[st], ((j / VS) & 1) ^ 1);
         mbar_expect_tx(&v_full[st], KV_BYTES);
         tma_load_3d(sV + st * KV_BYTES, j >= tiles1 ? &tmV2 : &tmV, &v_full[st], 0, h, tile_row(j));
       };
@@ -1409,8 +1432,8 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const uint64_t dQ = desc_kmajor(smem_u32(sQ + g * Q_BYTES));
       auto issue_qk = [&](int j) {
         const int st = j % KS;
-        mbar_wait(&k_full[st], (j / KS) & 1);
-        mbar_wait(&s_empty[g], (j & 1) ^ 1);          // group g has S(j - 1) in registers
+        wait(&k_full[st], (j / KS) & 1);
+        wait(&s_empty[g], (j & 1) ^ 1);               // group g has S(j - 1) in registers
         tc_fence_after();
         const uint64_t dK = desc_kmajor(smem_u32(sK + st * KV_BYTES));
 #pragma unroll
@@ -1421,8 +1444,8 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       };
       auto issue_pv = [&](int j) {
         const int st = j % VS;
-        mbar_wait(&v_full[st], (j / VS) & 1);
-        mbar_wait(&p_full[g], j & 1);
+        wait(&v_full[st], (j / VS) & 1);
+        wait(&p_full[g], j & 1);
         tc_fence_after();
         const uint64_t dV = desc_mnmajor(smem_u32(sV + st * KV_BYTES), BN * 128);
 #pragma unroll
@@ -1430,7 +1453,7 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         umma_commit(&v_empty[st]);
         umma_commit(&p_empty[g]);
       };
-      mbar_wait(q_full, 0);
+      wait(q_full, 0);
       issue_qk(0);
       for (int j = 0; j < num_tiles; ++j) {
         if (j + 1 < num_tiles) issue_qk(j + 1);
@@ -1499,21 +1522,6 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_ld32(tS, sa);
       tmem_ld_wait();
       pin32(sa);
-      if constexpr (EARLY) {
-        uint32_t sc2[32], sd[32];
-        tmem_ld32(tS + 32, sb);                                   // all three in flight during chunk 0
-        tmem_ld32(tS + 64, sc2);
-        tmem_ld32(tS + 96, sd);
-        chunk(sa, 0);
-        tmem_ld_wait();
-        pin32(sb); pin32(sc2); pin32(sd);
-        tc_fence_before();                                        // S is in registers: hand the buffer back
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[g]);
-        chunk(sb, 1);
-        chunk(sc2, 2);
-        chunk(sd, 3);
-      } else {
 #pragma unroll
       for (int ci = 0; ci < BN / 32; ci += 2) {
         tmem_ld32(tS + (ci + 1) * 32, sb);                        // in flight during chunk ci
@@ -1532,7 +1540,6 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           tmem_ld_wait();
           pin32(sa);
         }
-      }
       }
       l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
 
@@ -1645,12 +1652,12 @@ int launch_attn(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaS
   return 0;
 }
 
-template <bool EARLY, int POLY>
+template <bool HINT, int POLY>
 int launch_attn_q256(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaStream_t st) {
   constexpr int smem = 2 * BQ * 64 * 2 + (4 + 4) * 128 * 64 * 2 + 1024 + 256;
-  MMGT_CUDA_OK(mmgt_smem_optin(ctx, attention_tc_q256_kernel<EARLY, POLY>, smem));
+  MMGT_CUDA_OK(mmgt_smem_optin(ctx, attention_tc_q256_kernel<HINT, POLY>, smem));
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.N);
-  MMGT_CUDA_OK(mmgt_launch(ctx, attention_tc_q256_kernel<EARLY, POLY>, grid, dim3(NUM_THREADS_Q256), smem, st, maps[0], maps[1],
+  MMGT_CUDA_OK(mmgt_launch(ctx, attention_tc_q256_kernel<HINT, POLY>, grid, dim3(NUM_THREADS_Q256), smem, st, maps[0], maps[1],
                            maps[2], maps[3], maps[4], a));
   MMGT_LAUNCH_OK(ctx);
   return 0;
@@ -1718,12 +1725,12 @@ int mmgt_attention_tc(mmgt_ctx* ctx, const mmgt_attention_params* p, cudaStream_
       return launch_attn_persist(ctx, maps, a, st);
     // 256 queries per CTA once both softmax groups have rows of their own (flag 15)
     if (ctx->attn_q256 && p->Lq > BQ) {
-      switch (ctx->attn_q256) {            // A/B variants: S hand-back point, share of FMA-pipe exponentials
+      switch (ctx->attn_q256) {            // A/B variants: share of FMA-pipe exponentials, suspend-time hint
+        case 1: return launch_attn_q256<false, 0>(ctx, maps, a, st);
         case 2: return launch_attn_q256<true, 0>(ctx, maps, a, st);
-        case 3: return launch_attn_q256<true, 1>(ctx, maps, a, st);
-        case 4: return launch_attn_q256<true, 2>(ctx, maps, a, st);
-        case 5: return launch_attn_q256<false, 1>(ctx, maps, a, st);
-        default: return launch_attn_q256<false, 0>(ctx, maps, a, st);
+        case 4: return launch_attn_q256<false, 2>(ctx, maps, a, st);
+        case 6: return launch_attn_q256<true, 1>(ctx, maps, a, st);
+        default: return launch_attn_q256<false, 1>(ctx, maps, a, st);
       }
     }
     return pk ? launch_attn<1, 128, true>(ctx, maps, a, st) : launch_attn<1, 128, false>(ctx, maps, a, st);
