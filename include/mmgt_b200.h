@@ -85,8 +85,9 @@ MMGT_API const char* mmgt_last_error(void);
  *         tiles and walk the same key tiles, each with its own MMA-issuing warp; no split-KV merge.  0 = 128-query CTAs
  *         whose groups take alternate key tiles.  Variants of the 256-query kernel: 1 = every exponential on MUFU.EX2;
  *         5 = one score pair in four through a degree-3 polynomial on the FMA pipe (7.5e-5 relative, far inside the bf16
- *         rounding of P); 4 = two pairs in four (measured slower); 2 / 6 = 1 / 5 with a suspend-time hint on the mbarrier
- *         waits of the single-thread TMA / MMA roles.  A/B switch.
+ *         rounding of P); 4 = two pairs in four (measured slower); 8 / 7 / 9 = 1 / 5 / 4 with the softmax row sums taken
+ *         from the tensor cores (P x ones into accumulator columns 48-63, head dim <= 48) instead of register sums.
+ *         A/B switch.
  * flag 17: LayerNorm grid: 0 = up to 16 blocks per SM (default), 1 = one exact wave of persistent blocks, 2 = the same with
  *         the next row of a lane group prefetched.  Bit-identical results.  A/B switch.
  * flag 16: attention softmax loops on packed fp32 pairs (fma.rn.f32x2 / add.rn.f32x2; default 1).  Same IEEE operations

@@ -199,8 +199,8 @@ class Context:
 
     def set_attention_q256(self, on) -> int:
         """Head dim <= 64: 256 queries per CTA, one query tile and one MMA-issuing warp per softmax group (flag 15).
-        0 off; 1 = every exponential on MUFU; 5 = 1 of 4 score pairs through the FMA-pipe exp2 (default); 4 = 2 of 4;
-        2 / 6 = 1 / 5 with suspend-time hints on the waits of the TMA / MMA threads."""
+        0 off; 1 = every exponential on MUFU; 5 = 1 of 4 score pairs through the FMA-pipe exp2; 4 = 2 of 4;
+        8 / 7 / 9 = 1 / 5 / 4 with the softmax row sums from the tensor cores (P x ones into spare accumulator columns)."""
         return int(self.lib.mmgt_ctx_flag(self.handle, 15, int(on)))
 
     def set_layernorm_persistent(self, mode) -> int:

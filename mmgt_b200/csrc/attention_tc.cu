@@ -64,25 +64,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-// The same wait with a suspend-time hint: the single-thread TMA / MMA roles wait most of a tile period per event; with the
-// default (short) time limit their try_wait + branch loops issue ~45 M instructions per launch on three of the four
-// schedulers, next to the softmax warps (ncu source page, profiles/r2_attention_q256.md).  The thread still resumes as soon
-// as the phase completes.
-__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(hint_ns)
-        : "memory");
-  } while (!done);
-}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
@@ -244,10 +225,12 @@ __device__ __forceinline__ void exp2_pair_fma(uint64_t x01, float& p0, float& p1
 }
 // Eight scores: p = 2^(s * c - mc) as four bf16 pairs in pk[0..3], added lane-wise to the partial sums.  POLY of the four
 // pairs (0, 1 or 2) take the FMA-pipe exponential, the rest MUFU.EX2.
-template <int POLY>
+// SUM = false: the row sums come from the tensor cores (P x ones), nothing is added here.
+template <int POLY, bool SUM>
 __device__ __forceinline__ void exp8_pack_sum(const uint32_t* sc, float c, float mc, uint32_t* pk, float (&lsum)[4]) {
   const uint64_t c2 = pack_f32x2(c, c), nm2 = pack_f32x2(-mc, -mc);
-  uint64_t l01 = pack_f32x2(lsum[0], lsum[1]), l23 = pack_f32x2(lsum[2], lsum[3]);
+  uint64_t l01 = 0, l23 = 0;
+  if constexpr (SUM) { l01 = pack_f32x2(lsum[0], lsum[1]); l23 = pack_f32x2(lsum[2], lsum[3]); }
 #pragma unroll
   for (int pr = 0; pr < 4; ++pr) {
     const uint64_t x = fma_f32x2(pack_f32x2(__uint_as_float(sc[2 * pr]), __uint_as_float(sc[2 * pr + 1])), c2, nm2);
@@ -261,11 +244,15 @@ __device__ __forceinline__ void exp8_pack_sum(const uint32_t* sc, float c, float
       p1 = ex2_approx(x1);
     }
     pk[pr] = pack_bf16(p0, p1);
-    if (pr & 1) l23 = add_f32x2(l23, pack_f32x2(p0, p1));
-    else l01 = add_f32x2(l01, pack_f32x2(p0, p1));
+    if constexpr (SUM) {
+      if (pr & 1) l23 = add_f32x2(l23, pack_f32x2(p0, p1));
+      else l01 = add_f32x2(l01, pack_f32x2(p0, p1));
+    }
   }
-  unpack_f32x2(l01, lsum[0], lsum[1]);
-  unpack_f32x2(l23, lsum[2], lsum[3]);
+  if constexpr (SUM) {
+    unpack_f32x2(l01, lsum[0], lsum[1]);
+    unpack_f32x2(l23, lsum[2], lsum[3]);
+  }
 }
 
 // DCH = ceil(d / 64) head-dim chunks (d_pad = 64 * DCH); BN = keys per tile.
@@ -1328,10 +1315,14 @@ attention_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 // Tensor memory: S_0, S_1 (2 x 128 columns), O_0, O_1 (2 x 64), P_0, P_1 (2 x 64 packed bf16 pairs) = 512 columns.
 constexpr int NUM_THREADS_Q256 = 352;   // TMA warp, MMA warp of group 0, 2 x 4 softmax warps, MMA warp of group 1
 
-// HINT: the TMA / MMA threads wait with a 4 us suspend-time hint (mbar_wait_hint);  POLY: pairs of every four that take
-// the FMA-pipe exponential.  (Handing S back a quarter into the tile instead of three quarters -- all four 32-column
-// chunks of S in registers early -- measured no gain: 1579 vs 1584 us, and 1553 vs 1476 us together with POLY = 1.)
-template <bool HINT, int POLY>
+// LMMA: the softmax row sums l = sum_k P[row, k] are produced by the tensor cores -- after P_g(j) V(j) the group's issuer adds
+//       P_g(j) x ones (N = 16, B = a 2 KB shared-memory tile of bf16 1.0) into columns 48-63 of O_g, which P V at head dim
+//       <= 48 (N = 48) leaves free -- instead of 16 FADD2 per 32 scores in the softmax warps; the lazy rescale of O_g covers
+//       those columns, the epilogue reads l from column 48.  The normalisation then uses exactly the bf16 weights the
+//       numerator was accumulated with.  Head dims 49-64 (P V at N = 64) keep the register sums.
+// POLY: score pairs of every four that take the FMA-pipe exponential.  (Measured without gain and removed: S handed back to
+//       the MMA warp a quarter into the tile, suspend-time hints on the waits of the TMA / MMA threads: r2_ab_flags.md.)
+template <bool LMMA, int POLY>
 __global__ void __launch_bounds__(NUM_THREADS_Q256, 1)
 attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
@@ -1350,7 +1341,8 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint8_t* sQ = smem;                            // two query tiles
   uint8_t* sK = sQ + 2 * Q_BYTES;
   uint8_t* sV = sK + KS * KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + VS * KV_BYTES);
+  uint8_t* sOnes = sV + VS * KV_BYTES;           // LMMA: 16 rows x 128 B of bf16 1.0 (any operand layout reads ones)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + 2048);
   uint64_t* q_full = bars;                       // 1
   uint64_t* k_full = bars + 1;                   // KS
   uint64_t* k_empty = k_full + KS;               // KS, two arrivals: one commit per issuer
@@ -1380,6 +1372,10 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  if constexpr (LMMA) {
+    for (int i = threadIdx.x; i < 512; i += NUM_THREADS_Q256) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+    fence_async_smem();                           // generic-proxy stores -> visible to the tensor-core (async) proxy
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1391,11 +1387,6 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const int tiles1 = (args.Lk + BN - 1) / BN;
   const int tiles2 = seg2 >= 0 ? (args.Lk2 + BN - 1) / BN : 0;
   const int num_tiles = tiles1 + tiles2;
-  auto wait = [](uint64_t* bar, uint32_t parity) {     // waits of the single-thread roles
-    if constexpr (HINT) mbar_wait_hint(bar, parity, 4000u);
-    else mbar_wait(bar, parity);
-  };
-
   if (warp == 0) {
     if (elect_one_sync()) {
       // ===================== TMA producer =====================
@@ -1405,13 +1396,13 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       auto tile_row = [&](int j) { return j >= tiles1 ? seg2 * args.Lk2 + (j - tiles1) * BN : n * args.Lk + j * BN; };
       auto load_k = [&](int j) {
         const int st = j % KS;
-        wait(&k_empty[st], ((j / KS) & 1) ^ 1);
+        mbar_wait(&k_empty[st], ((j / KS) & 1) ^ 1);
         mbar_expect_tx(&k_full[st], KV_BYTES);
         tma_load_3d(sK + st * KV_BYTES, j >= tiles1 ? &tmK2 : &tmK, &k_full[st], 0, h, tile_row(j));
       };
       auto load_v = [&](int j) {
         const int st = j % VS;
-        wait(&v_empty[st], ((j / VS) & 1) ^ 1);
+        mbar_wait(&v_empty[st], ((j / VS) & 1) ^ 1);
         mbar_expect_tx(&v_full[st], KV_BYTES);
         tma_load_3d(sV + st * KV_BYTES, j >= tiles1 ? &tmV2 : &tmV, &v_full[st], 0, h, tile_row(j));
       };
@@ -1429,11 +1420,12 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       // ===================== MMA issuer of group g =====================
       const int g = warp == 1 ? 0 : 1;
       const uint32_t tS = tmem_base + TM_S + g * BN, tOg = tmem_base + TM_O + g * DPAD, tPg = tmem_base + TM_P + g * (BN / 2);
-      const uint64_t dQ = desc_kmajor(smem_u32(sQ + g * Q_BYTES));
+      const uint64_t dQ = desc_kmajor(smem_u32(sQ + g * Q_BYTES)), dOnes = desc_kmajor(smem_u32(sOnes));
+      constexpr uint32_t IDESC_L = idesc_bf16(16, false);
       auto issue_qk = [&](int j) {
         const int st = j % KS;
-        wait(&k_full[st], (j / KS) & 1);
-        wait(&s_empty[g], (j & 1) ^ 1);               // group g has S(j - 1) in registers
+        mbar_wait(&k_full[st], (j / KS) & 1);
+        mbar_wait(&s_empty[g], (j & 1) ^ 1);               // group g has S(j - 1) in registers
         tc_fence_after();
         const uint64_t dK = desc_kmajor(smem_u32(sK + st * KV_BYTES));
 #pragma unroll
@@ -1444,16 +1436,20 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       };
       auto issue_pv = [&](int j) {
         const int st = j % VS;
-        wait(&v_full[st], (j / VS) & 1);
-        wait(&p_full[g], j & 1);
+        mbar_wait(&v_full[st], (j / VS) & 1);
+        mbar_wait(&p_full[g], j & 1);
         tc_fence_after();
         const uint64_t dV = desc_mnmajor(smem_u32(sV + st * KV_BYTES), BN * 128);
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) umma_ts(tOg, tPg + k * 8, dV + k * (2048 >> 4), IDESC_PV, (j | k) != 0);
         umma_commit(&v_empty[st]);
+        if constexpr (LMMA) {                        // row sums: O_g[:, 48..63] += P_g(j) x ones
+#pragma unroll
+          for (int k = 0; k < BN / 16; ++k) umma_ts(tOg + 48, tPg + k * 8, dOnes, IDESC_L, (j | k) != 0);
+        }
         umma_commit(&p_empty[g]);
       };
-      wait(q_full, 0);
+      mbar_wait(q_full, 0);
       issue_qk(0);
       for (int j = 0; j < num_tiles; ++j) {
         if (j + 1 < num_tiles) issue_qk(j + 1);
@@ -1502,9 +1498,11 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           const float a = ex2_approx((m_ref - mx) * c);          // 0 the first time
           m_ref = mx;
           alpha_tile *= a;
-          l_run *= a;
+          if constexpr (!LMMA) {
+            l_run *= a;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) lsum[e] *= a;
+            for (int e = 0; e < 4; ++e) lsum[e] *= a;
+          }
           const __nv_bfloat162 a2 = __float2bfloat162_rn(a);
 #pragma unroll
           for (int i = 0; i < BN / 2; ++i) {
@@ -1517,7 +1515,7 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
         const float mc = m_ref * c;
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) exp8_pack_sum<POLY>(sc + i, c, mc, pk + ci * 16 + i / 2, lsum);
+        for (int i = 0; i < 32; i += 8) exp8_pack_sum<POLY, !LMMA>(sc + i, c, mc, pk + ci * 16 + i / 2, lsum);
       };
       tmem_ld32(tS, sa);
       tmem_ld_wait();
@@ -1541,7 +1539,7 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           pin32(sa);
         }
       }
-      l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+      if constexpr (!LMMA) l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
 
       if (j > 0) {
         mbar_wait(&p_empty[g], (j - 1) & 1);   // this group's previous PV retired: P buffer reusable, O_g stable
@@ -1571,27 +1569,26 @@ attention_tc_q256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (num_tiles > 0) {
       mbar_wait(&p_empty[g], (num_tiles - 1) & 1);
       tc_fence_after();
-      const float inv = 1.f / l_run;
       const int q = q0 + g * BQ + row;
       bf16* orow = args.out + ((int64_t)n * args.Lq + q) * args.ldo + h * args.d;
+      uint32_t o[2][32];
+      tmem_ld32(tO, o[0]);
+      if (LMMA || args.d > 32) tmem_ld32(tO + 32, o[1]);     // warp-uniform
+      tmem_ld_wait();
+      const float inv = 1.f / (LMMA ? __uint_as_float(o[1][16]) : l_run);   // column 48 = sum_k P[row, k]
+      if (q < args.Lq) {
 #pragma unroll
-      for (int cc = 0; cc < DPAD / 32; ++cc) {
-        if (cc * 32 < args.d) {                      // warp-uniform
-          uint32_t o[32];
-          tmem_ld32(tO + cc * 32, o);
-          tmem_ld_wait();
-          if (q < args.Lq) {
+        for (int cc = 0; cc < DPAD / 32; ++cc) {
 #pragma unroll
-            for (int gg = 0; gg < 4; ++gg) {
-              const int col = cc * 32 + gg * 8;
-              if (col < args.d) {
-                uint4 val;
-                val.x = pack_bf16(__uint_as_float(o[gg * 8 + 0]) * inv, __uint_as_float(o[gg * 8 + 1]) * inv);
-                val.y = pack_bf16(__uint_as_float(o[gg * 8 + 2]) * inv, __uint_as_float(o[gg * 8 + 3]) * inv);
-                val.z = pack_bf16(__uint_as_float(o[gg * 8 + 4]) * inv, __uint_as_float(o[gg * 8 + 5]) * inv);
-                val.w = pack_bf16(__uint_as_float(o[gg * 8 + 6]) * inv, __uint_as_float(o[gg * 8 + 7]) * inv);
-                *reinterpret_cast<uint4*>(orow + col) = val;
-              }
+          for (int gg = 0; gg < 4; ++gg) {
+            const int col = cc * 32 + gg * 8;
+            if (col < args.d) {
+              uint4 val;
+              val.x = pack_bf16(__uint_as_float(o[cc][gg * 8 + 0]) * inv, __uint_as_float(o[cc][gg * 8 + 1]) * inv);
+              val.y = pack_bf16(__uint_as_float(o[cc][gg * 8 + 2]) * inv, __uint_as_float(o[cc][gg * 8 + 3]) * inv);
+              val.z = pack_bf16(__uint_as_float(o[cc][gg * 8 + 4]) * inv, __uint_as_float(o[cc][gg * 8 + 5]) * inv);
+              val.w = pack_bf16(__uint_as_float(o[cc][gg * 8 + 6]) * inv, __uint_as_float(o[cc][gg * 8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + col) = val;
             }
           }
         }
@@ -1652,12 +1649,12 @@ int launch_attn(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaS
   return 0;
 }
 
-template <bool HINT, int POLY>
+template <bool LMMA, int POLY>
 int launch_attn_q256(mmgt_ctx* ctx, const CUtensorMap* maps, const AttnArgs& a, cudaStream_t st) {
-  constexpr int smem = 2 * BQ * 64 * 2 + (4 + 4) * 128 * 64 * 2 + 1024 + 256;
-  MMGT_CUDA_OK(mmgt_smem_optin(ctx, attention_tc_q256_kernel<HINT, POLY>, smem));
+  constexpr int smem = 2 * BQ * 64 * 2 + (4 + 4) * 128 * 64 * 2 + 2048 + 1024 + 256;
+  MMGT_CUDA_OK(mmgt_smem_optin(ctx, attention_tc_q256_kernel<LMMA, POLY>, smem));
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.heads, a.N);
-  MMGT_CUDA_OK(mmgt_launch(ctx, attention_tc_q256_kernel<HINT, POLY>, grid, dim3(NUM_THREADS_Q256), smem, st, maps[0], maps[1],
+  MMGT_CUDA_OK(mmgt_launch(ctx, attention_tc_q256_kernel<LMMA, POLY>, grid, dim3(NUM_THREADS_Q256), smem, st, maps[0], maps[1],
                            maps[2], maps[3], maps[4], a));
   MMGT_LAUNCH_OK(ctx);
   return 0;
@@ -1725,11 +1722,13 @@ int mmgt_attention_tc(mmgt_ctx* ctx, const mmgt_attention_params* p, cudaStream_
       return launch_attn_persist(ctx, maps, a, st);
     // 256 queries per CTA once both softmax groups have rows of their own (flag 15)
     if (ctx->attn_q256 && p->Lq > BQ) {
-      switch (ctx->attn_q256) {            // A/B variants: share of FMA-pipe exponentials, suspend-time hint
+      const bool lmma = p->d <= 48;        // P V at N <= 48 leaves columns 48-63 of O for the row sums
+      switch (ctx->attn_q256) {            // A/B variants: share of FMA-pipe exponentials, row sums by the tensor cores
         case 1: return launch_attn_q256<false, 0>(ctx, maps, a, st);
-        case 2: return launch_attn_q256<true, 0>(ctx, maps, a, st);
         case 4: return launch_attn_q256<false, 2>(ctx, maps, a, st);
-        case 6: return launch_attn_q256<true, 1>(ctx, maps, a, st);
+        case 7: return lmma ? launch_attn_q256<true, 1>(ctx, maps, a, st) : launch_attn_q256<false, 1>(ctx, maps, a, st);
+        case 8: return lmma ? launch_attn_q256<true, 0>(ctx, maps, a, st) : launch_attn_q256<false, 0>(ctx, maps, a, st);
+        case 9: return lmma ? launch_attn_q256<true, 2>(ctx, maps, a, st) : launch_attn_q256<false, 2>(ctx, maps, a, st);
         default: return launch_attn_q256<false, 1>(ctx, maps, a, st);
       }
     }

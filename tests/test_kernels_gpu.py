@@ -628,7 +628,7 @@ def test_attention_two_segments(dev, dtype, tc, N, Lq, Lk, Lk2, heads, d):
 def test_attention_kernel_variants(dev, N, Lq, Lk, Lk2, heads, d):
     """Flags 15 / 16 of the tensor-core attention: packed fp32 pairs (FFMA2 / FADD2) must not change a bit of either kernel;
     the 256-query kernel (one query tile + one MMA-issuing warp per softmax group, no split-KV merge) and its variants (FMA-pipe
-    exp2 for 1 / 2 of 4 score pairs, suspend-time hints on the single-thread waits) against float32."""
+    exp2 for 1 / 2 of 4 score pairs, row sums from the tensor cores) against float32."""
     if Lq < 64:
         pytest.skip("tensor-core attention needs Lq >= 64")
     eng = eng_for(dev, torch.bfloat16)
@@ -651,7 +651,7 @@ def test_attention_kernel_variants(dev, N, Lq, Lk, Lk2, heads, d):
     ref = torch.cat(refs)
     outs = {}
     try:
-        for q256, packed in ((0, False), (0, True), (1, True), (2, True), (4, True), (5, True), (6, True)):
+        for q256, packed in ((0, False), (0, True), (1, True), (4, True), (5, True), (7, True), (8, True), (9, True)):
             eng.ctx.set_attention_q256(q256)
             eng.ctx.set_attention_packed(packed)
             outs[q256, packed] = o = eng.attention(q, k, v, heads, **kw)
@@ -661,11 +661,13 @@ def test_attention_kernel_variants(dev, N, Lq, Lk, Lk2, heads, d):
         eng.ctx.set_attention_q256(ATTN_Q256_DEFAULT)
         eng.ctx.set_attention_packed(True)
     assert torch.equal(outs[0, False], outs[0, True])         # packed pairs: same IEEE operations
-    assert torch.equal(outs[1, True], outs[2, True])          # how the TMA / MMA threads wait does not touch the arithmetic
-    assert torch.equal(outs[5, True], outs[6, True])
-    if d <= 64 and Lq > 128:                                   # FMA-pipe exp2 (7.5e-5 relative) vs MUFU: far inside bf16 rounding
-        assert rel_l2(outs[5, True].float(), outs[1, True].float()) < 2e-3
-        assert rel_l2(outs[4, True].float(), outs[1, True].float()) < 2e-3
+    if d <= 64 and Lq > 128:
+        # FMA-pipe exp2 (7.5e-5 relative) vs MUFU, and row sums from the tensor cores (sum of the bf16 weights) vs fp32 sums
+        # in registers: both far inside the bf16 rounding of P
+        for v in (4, 5, 7, 8, 9):
+            assert rel_l2(outs[v, True].float(), outs[1, True].float()) < 3e-3, v
+    if d > 48:                                                 # no free accumulator columns: the register-sum kernels run
+        assert torch.equal(outs[7, True], outs[5, True]) and torch.equal(outs[8, True], outs[1, True])
 
 
 def test_attention_running_max_jumps_late(dev):
@@ -685,7 +687,7 @@ def test_attention_running_max_jumps_late(dev):
     q, k, v, k2, v2 = (t.to(device=dev, dtype=torch.bfloat16) for t in (q, k, v, k2, v2))
     ref = _attn_ref(q, torch.cat([k, k2.expand(N, -1, -1)], 1), torch.cat([v, v2.expand(N, -1, -1)], 1), heads)
     try:
-        for v2_kernel, persist, q256 in ((True, 0, 0), (False, 0, 0), (False, 2, 0), (False, 0, 1), (False, 0, 6), (False, 0, 4)):
+        for v2_kernel, persist, q256 in ((True, 0, 0), (False, 0, 0), (False, 2, 0), (False, 0, 1), (False, 0, 5), (False, 0, 7), (False, 0, 9)):
             eng.ctx.set_attention_v2(v2_kernel)
             eng.ctx.set_attention_persistent(persist)
             eng.ctx.set_attention_q256(q256)
