@@ -2,13 +2,19 @@
 //
 //   out[n, q, h, :] = softmax_k( q . k * scale ) v     over keys [ per-frame segment ; optional shared segment ]
 //
-// One CTA = one (frame, head, 128-query tile).  Warp roles:
+// Kernels in this file (mmgt_attention_tc picks one):
+//   attention_tc_q256_kernel<LMMA, POLY>     head dim <= 64, Lq > 128 (default): one CTA = (frame, head, 256 queries), two
+//                                            softmax groups on different query tiles, one MMA-issuing warp each, S / O / P in TMEM
+//   attention_tc_kernel<DCH, BN, PACKED>     head dim 80 / 160 (DCH = 2 / 3) and short query sets: one CTA = (frame, head,
+//                                            128 queries), the two softmax groups take alternate key tiles, merge at the end
+//   attention_tc64_kernel, attention_tc_persist_kernel   measured-slower A/B forms of the 128-query kernel (flags 9, 14)
+// Common structure of a CTA:
 //   warp 0 (one lane)  TMA producer: Q once, then K / V tiles through two smem rings
-//   warp 1 (one lane)  MMA issuer:   S[j&1] = Q K_j^T   (128 x BN x d_pad, accumulator in TMEM, double buffered)
-//                                    O     += P_j V_j   (128 x d_pad x BN, P from smem, V MN-major)
-//   warps 2..5         softmax: one thread per query row (= TMEM lane): tcgen05.ld S -> online max / exp2 ->
-//                      bf16 P into 128B-swizzled smem; lazy rescale of O in TMEM (only when the running max
-//                      moved by > 2^8); final 1/l scaling and the global store of O.
+//   warp 1 (one lane)  MMA issuer:   S = Q K_j^T   (128 x BN x d_pad, accumulator in TMEM, double buffered)
+//                                    O += P_j V_j  (128 x d_pad x BN, V MN-major; P from TMEM at head dim <= 64, else smem)
+//   warps 2..9         softmax: one thread per query row (= TMEM lane): tcgen05.ld S -> online max / exp2 -> bf16 P;
+//                      lazy rescale of O in TMEM (only when the running max moved by > 2^8); final 1/l scaling and the
+//                      global store of O.
 // Head dims that are not multiples of 64 (40, 80, 160) need no padded tensors: Q/K/V are described to TMA as
 // (d, heads, rows) and a 64-wide box on the d axis is zero-filled past d, which pads every head to 64/128/192.
 // The second key segment implements ReferenceNet feature injection: frames whose seg2 index is -1 (the CFG
