@@ -570,3 +570,48 @@ def test_reference_net_write_pass_host_mirror_on_cpu(monkeypatch):
     eng = FakeEngine()
     monkeypatch.setattr(net, "_engine", lambda device: eng)
     _check_refnet_banks(net, 2e-5)
+
+
+def test_reader_update_takes_the_banks_of_the_references_own_writer_controller():
+    """``reader.update(writer)`` with the REFERENCE's ``ReferenceAttentionControl(mode="write")``
+    (src/models/mutual_self_attention.py, imported unchanged) on the reference's own network: pairing is by duck typing
+    (modules named (Temporal)BasicTransformerBlock that own ``bank`` and ``norm1``, stable sort by descending width,
+    mutual_self_attention.py:269-341).  The banks that arrive on this package's reader blocks must be the reference writer's,
+    in the committed golden's order, rounded to fp16 like mutual_self_attention.py:340.  Needs the reference checkout."""
+    from oracle import reference_loader as RL
+    if not RL.reference_available():
+        pytest.skip("reference checkout not present (GPU box)")
+    from mmgt_b200.mutual_self_attention import ReferenceAttentionControl, _reader_blocks
+    from oracle.make_golden_refnet import refnet_inputs
+    from oracle.weights import make_state_dict
+    mods = RL.load_reference_modules()
+    cfg = dict(RL.SD15_CFG)
+    cfg["block_out_channels"] = list(TINY)
+    extra = dict(RL.UNET_ADDITIONAL_KWARGS)
+    extra.update(use_motion_module=False, use_audio_module=False)
+    ref_net = mods["unet_3d"].UNet3DConditionModel.from_config(cfg, **extra)
+    ref_net.load_state_dict(make_state_dict([(k, tuple(v.shape)) for k, v in ref_net.state_dict().items()], seed=8), strict=True)
+    ref_net.eval()
+    ref_writer = mods["mutual_self_attention"].ReferenceAttentionControl(
+        ref_net, do_classifier_free_guidance=True, mode="write", batch_size=1, fusion_blocks="full")
+    x, ehs = refnet_inputs()
+    with torch.no_grad():
+        ref_net(x.unsqueeze(2), torch.zeros((), dtype=torch.long), encoder_hidden_states=ehs, return_dict=False)
+
+    _, _, unet = _tiny_unet()
+    reader = ReferenceAttentionControl(unet, do_classifier_free_guidance=True, mode="read", batch_size=1, fusion_blocks="full")
+    reader.update(ref_writer)                                   # the reference's controller object, not ours
+    g = np.load(os.path.join(GOLD, "refnet_tiny.npz"))
+    blocks = _reader_blocks(unet, "full")
+    assert len(blocks) == 16
+    for i, b in enumerate(blocks):
+        assert len(b.bank) == 1 and b.bank[0].dtype == torch.float16
+        gold = torch.from_numpy(g[f"bank{i:02d}"])
+        assert b.bank[0].shape == gold.shape
+        assert rel_l2(b.bank[0].float(), gold) < 1e-3, i        # fp16 rounding of the bank: 2^-11 relative
+    reader.clear()
+    assert all(len(b.bank) == 0 for b in blocks)
+    # a writer whose forward has not run yet is refused instead of pairing empty banks
+    ref_writer.clear()
+    with pytest.raises(ValueError):
+        reader.update(ref_writer)
