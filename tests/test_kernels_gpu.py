@@ -624,7 +624,8 @@ def test_attention_two_segments(dev, dtype, tc, N, Lq, Lk, Lk2, heads, d):
         eng.ctx.set_attention_q256(ATTN_Q256_DEFAULT)
 
 
-@pytest.mark.parametrize("N,Lq,Lk,Lk2,heads,d", ATTN_CASES + [(2, 257, 129, 384, 8, 40), (5, 512, 512, 512, 8, 40), (1, 2304, 2304, 0, 8, 40)])
+@pytest.mark.parametrize("N,Lq,Lk,Lk2,heads,d", ATTN_CASES + [(2, 257, 129, 384, 8, 40), (5, 512, 512, 512, 8, 40), (1, 2304, 2304, 0, 8, 40),
+                                                        (2, 9216, 9216, 9216, 8, 40)])   # last: the 96 x 96 level of config 5
 def test_attention_kernel_variants(dev, N, Lq, Lk, Lk2, heads, d):
     """Flags 15 / 16 of the tensor-core attention: packed fp32 pairs (FFMA2 / FADD2) must not change a bit of either kernel;
     the 256-query kernel (one query tile + one MMA-issuing warp per softmax group, no split-KV merge) and its variants (FMA-pipe
